@@ -1,0 +1,1102 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under royaltracer-dx_b200/ may include, link or call this.
+//
+// Single-threaded CPU restatement of the reference's hot path (ML200/RoyalTracer-DX):
+//   camera ray -> TraceRay -> ClosestHit/Miss -> RIS direct lighting -> SamplePathSimple (GI) ->
+//   estimator E0 -> accumulation (F20).
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/Pathtracer/).  Numerics contract: oracle/det_math.h.
+//
+// PARITY STATUS: "parity unpinned" against reference outputs — the reference has no tests, golden
+// vectors or fixtures and is a Windows/DX12 app that cannot execute here.  The
+// traversal + ray/triangle test has no reference source at all (closed D3D12 driver / RT cores);
+// the contract is defined HERE (orc_trace mode 0 = brute force) from the DXR semantics the
+// reference's call sites rely on.
+//
+// Deliberate deviations from reference undefined behaviour (DESIGN.md §"Deviations"):
+//   D1 miss => path terminates, radiance 0 (ref: Miss_v7.hlsl:3-8 leaves the payload uninitialised)
+//   D2 seed uses the global sample index where the ref uses uint(time) (Pass_init_di_v7.hlsl:76-77)
+//   D3 optional jitter: 2 draws before anything else (legacy include/RayGen.hlsl:84-85)
+//   D4 emitter hit by a GI BSDF ray with zero/NaN contribution => path terminates
+//      (ref: Path_Sampler_v7.hlsl:262-268 continues with uninitialised new_origin/new_normal)
+//   D5 primary-hit emitters are accumulated like any other sample (ref bypasses accumulation,
+//      Pass_spat_di_v7.hlsl:458-463; identical when every sample of the pixel hits the emitter)
+//   D6 the DI visibility ray is skipped when its result cannot matter (!(f_g > EPSILON))
+//   D7 material id offset is a per-model uint instead of a float in vertex.normal.w
+#include "rtx_oracle.h"
+#include "det_math.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+using namespace orc;
+
+namespace {
+
+// shaders/Common_v7.hlsl:1-3
+constexpr float PI_REF = 3.1415f;
+constexpr float S_BIAS = 0.00002f;
+constexpr float EPS = 0.000001f;
+constexpr uint32_t MISS_ID = 4294967294u;   // shaders/Miss_v7.hlsl:7
+
+// ------------------------------------------------------------------------------------------ scene
+struct Box { f3 lo, hi; };
+struct Node2 { Box b; uint32_t left, right; uint32_t first, count; };   // count>0 => leaf
+
+struct Model {
+    std::vector<f3> pos;
+    std::vector<f3> nrm;
+    std::vector<uint32_t> idx;
+    uint32_t mat_offset = 0;
+    std::vector<Node2> nodes;
+    std::vector<uint32_t> order;    // triangle ids in leaf order
+    Box bounds;
+};
+
+struct Instance { uint32_t model; orc_instance_props p; Box wbox; };
+
+}  // namespace
+
+struct orc_scene {
+    std::vector<Model> models;
+    std::vector<uint32_t> material_ids;
+    std::vector<orc_material> materials;
+    std::vector<Instance> instances;
+    std::vector<orc_light_tri> lights;
+    orc_counters* ctr = nullptr;
+};
+
+namespace {
+
+orc_counters g_dummy_ctr;
+
+// ------------------------------------------------------------------------------------------ ray / triangle
+// Contract T3/T4: hit iff TMin < t < TMax; closest = lexicographic min of
+// (t, instance, primitive).  Watertight edge-function test (shear the triangle into ray space,
+// exact-zero edge functions re-evaluated in binary64).
+struct RayPre { f3 o, d; int kx, ky, kz; float Sx, Sy, Sz; };
+
+inline float comp(f3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+RayPre ray_pre(f3 o, f3 d) {
+    RayPre r; r.o = o; r.d = d;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz = 0; float m = ax;
+    if (ay > m) { kz = 1; m = ay; }
+    if (az > m) { kz = 2; }
+    int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
+    if (comp(d, kz) < 0.0f) std::swap(kx, ky);
+    r.kx = kx; r.ky = ky; r.kz = kz;
+    float dz = comp(d, kz);
+    r.Sx = comp(d, kx) / dz; r.Sy = comp(d, ky) / dz; r.Sz = 1.0f / dz;
+    return r;
+}
+
+bool tri_test(const RayPre& r, f3 v0, f3 v1, f3 v2, float tmin, float tmax, float& t, float& b1, float& b2) {
+    f3 A = v0 - r.o, B = v1 - r.o, C = v2 - r.o;
+    float Akz = comp(A, r.kz), Bkz = comp(B, r.kz), Ckz = comp(C, r.kz);
+    float Ax = comp(A, r.kx) - r.Sx * Akz, Ay = comp(A, r.ky) - r.Sy * Akz;
+    float Bx = comp(B, r.kx) - r.Sx * Bkz, By = comp(B, r.ky) - r.Sy * Bkz;
+    float Cx = comp(C, r.kx) - r.Sx * Ckz, Cy = comp(C, r.ky) - r.Sy * Ckz;
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    float det = (U + V) + W;
+    if (det == 0.0f) return false;
+    float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    float T = (U * Az + V * Bz) + W * Cz;
+    float rcp = 1.0f / det;
+    float tt = T * rcp;
+    if (!(tt > tmin && tt < tmax)) return false;
+    t = tt; b1 = V * rcp; b2 = W * rcp;
+    return true;
+}
+
+// conservative slab test (NaN-ignoring fminf/fmaxf; inflated far side)
+inline bool box_test(const Box& b, f3 o, f3 inv, float tmin, float tmax) {
+    float t0 = (b.lo.x - o.x) * inv.x, t1 = (b.hi.x - o.x) * inv.x;
+    float tn = fminf(t0, t1), tf = fmaxf(t0, t1);
+    t0 = (b.lo.y - o.y) * inv.y; t1 = (b.hi.y - o.y) * inv.y;
+    tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    t0 = (b.lo.z - o.z) * inv.z; t1 = (b.hi.z - o.z) * inv.z;
+    tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    tn = fmaxf(tn, tmin); tf = fminf(tf, tmax);
+    return tn <= tf * 1.0000004f + 1e-30f;
+}
+
+inline Box box_empty() { Box b; b.lo = mk3(INFINITY, INFINITY, INFINITY); b.hi = mk3(-INFINITY, -INFINITY, -INFINITY); return b; }
+inline void box_grow(Box& b, f3 p) {
+    b.lo = mk3(fminf(b.lo.x, p.x), fminf(b.lo.y, p.y), fminf(b.lo.z, p.z));
+    b.hi = mk3(fmaxf(b.hi.x, p.x), fmaxf(b.hi.y, p.y), fmaxf(b.hi.z, p.z));
+}
+inline void box_pad(Box& b, float pad) {
+    b.lo = mk3(b.lo.x - pad, b.lo.y - pad, b.lo.z - pad);
+    b.hi = mk3(b.hi.x + pad, b.hi.y + pad, b.hi.z + pad);
+}
+
+void build_bvh2(Model& m) {
+    uint32_t nt = (uint32_t)m.idx.size() / 3;
+    m.order.resize(nt);
+    std::vector<f3> cen(nt);
+    std::vector<Box> tb(nt);
+    Box all = box_empty();
+    for (uint32_t t = 0; t < nt; t++) {
+        m.order[t] = t;
+        Box b = box_empty();
+        for (int k = 0; k < 3; k++) box_grow(b, m.pos[m.idx[3 * t + k]]);
+        tb[t] = b;
+        cen[t] = mk3(0.5f * (b.lo.x + b.hi.x), 0.5f * (b.lo.y + b.hi.y), 0.5f * (b.lo.z + b.hi.z));
+        box_grow(all, b.lo); box_grow(all, b.hi);
+    }
+    float scale = 0.0f;
+    if (nt) {
+        scale = fmaxf(fmaxf(fabsf(all.lo.x), fabsf(all.hi.x)), fmaxf(fmaxf(fabsf(all.lo.y), fabsf(all.hi.y)),
+                      fmaxf(fabsf(all.lo.z), fabsf(all.hi.z))));
+    }
+    float pad = scale * 3.0517578125e-5f + 1e-30f;   // 2^-15 of the model's scale
+    m.bounds = all; box_pad(m.bounds, pad);
+    m.nodes.clear();
+    if (nt == 0) return;
+    m.nodes.reserve(2 * nt);
+    struct Job { uint32_t node, first, count; };
+    std::vector<Job> stack;
+    m.nodes.push_back(Node2{});
+    stack.push_back({0u, 0u, nt});
+    while (!stack.empty()) {
+        Job j = stack.back(); stack.pop_back();
+        Box b = box_empty(), cb = box_empty();
+        for (uint32_t i = j.first; i < j.first + j.count; i++) {
+            uint32_t t = m.order[i];
+            box_grow(b, tb[t].lo); box_grow(b, tb[t].hi); box_grow(cb, cen[t]);
+        }
+        box_pad(b, pad);
+        Node2& n = m.nodes[j.node];
+        n.b = b;
+        f3 ext = cb.hi - cb.lo;
+        int axis = 0; if (ext.y > ext.x) axis = 1; if (ext.z > comp(ext, axis)) axis = 2;
+        if (j.count <= 4 || comp(ext, axis) <= 0.0f) {
+            n.first = j.first; n.count = j.count; n.left = n.right = 0;
+            continue;
+        }
+        uint32_t mid = j.first + j.count / 2;
+        std::nth_element(m.order.begin() + j.first, m.order.begin() + mid, m.order.begin() + j.first + j.count,
+                         [&](uint32_t a, uint32_t c) {
+                             float ca = comp(cen[a], axis), cc = comp(cen[c], axis);
+                             return ca < cc || (ca == cc && a < c);
+                         });
+        uint32_t l = (uint32_t)m.nodes.size();
+        m.nodes.push_back(Node2{}); m.nodes.push_back(Node2{});
+        Node2& n2 = m.nodes[j.node];
+        n2.count = 0; n2.first = 0; n2.left = l; n2.right = l + 1;
+        stack.push_back({l, j.first, mid - j.first});
+        stack.push_back({l + 1, mid, j.first + j.count - mid});
+    }
+}
+
+struct Hit { float t, b1, b2; uint32_t prim, inst; };
+
+inline bool better(float t, uint32_t inst, uint32_t prim, const Hit& h) {
+    if (t < h.t) return true;
+    if (t > h.t) return false;
+    if (inst < h.inst) return true;
+    if (inst > h.inst) return false;
+    return prim < h.prim;
+}
+
+// returns true if (any_hit && found). Updates best.
+bool trace_instance(const orc_scene& S, uint32_t ii, f3 wo, f3 wd, float tmin, float tmax, bool any_hit, int mode,
+                    Hit& best, orc_counters& C) {
+    const Instance& inst = S.instances[ii];
+    const Model& M = S.models[inst.model];
+    C.instances_entered++;
+    // world -> object with the host-supplied inverse (Renderer.cpp:2091-2121); direction not renormalised,
+    // so t is the same parameter in both spaces.
+    f4 o4 = mul44(inst.p.objectToWorldInverse, wo.x, wo.y, wo.z, 1.0f);
+    f4 d4 = mul44(inst.p.objectToWorldInverse, wd.x, wd.y, wd.z, 0.0f);
+    f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
+    RayPre rp = ray_pre(o, d);
+    uint32_t nt = (uint32_t)M.idx.size() / 3;
+    auto test_tri = [&](uint32_t prim) -> bool {
+        C.tris_tested++;
+        float t, b1, b2;
+        if (!tri_test(rp, M.pos[M.idx[3 * prim]], M.pos[M.idx[3 * prim + 1]], M.pos[M.idx[3 * prim + 2]], tmin, tmax, t, b1, b2))
+            return false;
+        if (any_hit) { best.t = t; best.b1 = b1; best.b2 = b2; best.prim = prim; best.inst = ii; return true; }
+        if (best.inst == 0xFFFFFFFFu || better(t, ii, prim, best)) { best.t = t; best.b1 = b1; best.b2 = b2; best.prim = prim; best.inst = ii; }
+        return false;
+    };
+    if (mode == 0) {
+        for (uint32_t p = 0; p < nt; p++) if (test_tri(p)) return true;
+        return false;
+    }
+    if (M.nodes.empty()) return false;
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const Node2& n = M.nodes[stack[--sp]];
+        C.bvh_nodes_visited++;
+        float far = (best.inst == 0xFFFFFFFFu || any_hit) ? tmax : fminf(tmax, best.t);
+        if (!box_test(n.b, o, inv, tmin, far)) continue;
+        if (n.count) {
+            for (uint32_t i = 0; i < n.count; i++) if (test_tri(M.order[n.first + i])) return true;
+        } else {
+            stack[sp++] = n.left; stack[sp++] = n.right;
+        }
+    }
+    return false;
+}
+
+bool trace(const orc_scene& S, f3 o, f3 d, float tmin, float tmax, bool any_hit, int mode, Hit& best, orc_counters& C) {
+    best.t = tmax; best.b1 = best.b2 = 0.0f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    for (uint32_t i = 0; i < (uint32_t)S.instances.size(); i++) {
+        if (mode != 0) {
+            float far = (best.inst == 0xFFFFFFFFu || any_hit) ? tmax : fminf(tmax, best.t);
+            if (!box_test(S.instances[i].wbox, o, inv, tmin, far)) continue;
+        }
+        if (trace_instance(S, i, o, d, tmin, tmax, any_hit, mode, best, C)) return true;
+    }
+    return best.inst != 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------ shading types
+struct MatOpt {                 // shaders/Common_v7.hlsl:62-66 — every field holds a binary16 value
+    f3 Kd; float Kd_w;
+    float Pr, Pm, Ps, Pc;
+    f3 Ks; f3 Ke;
+    uint32_t mID;
+};
+struct HitInfo {                // shaders/Common_v7.hlsl:35-46
+    f3 hitPosition; uint32_t materialID; f3 hitNormal; float area; uint32_t objID;
+};
+struct ReservoirDI { f3 x2; float w_sum; f3 n2; float W; f3 L2; uint32_t M; };    // Reservoir_v7.hlsl:15-20 (L2 half3)
+struct ReservoirGI { f3 xn; float w_sum; f3 nn; float W; f3 E3; uint32_t M; };    // Reservoir_v7.hlsl:22-27 (E3 half3)
+
+struct Ctx {
+    const orc_scene* S;
+    orc_config cfg;
+    orc_counters* C;
+    int mode;
+};
+
+// OOB StructuredBuffer reads return 0
+inline orc_material fetch_material(const orc_scene& S, uint32_t id) {
+    if (id < S.materials.size()) return S.materials[id];
+    orc_material z; memset(&z, 0, sizeof z); return z;
+}
+// Pass_init_di_v7.hlsl:108-111 / Sampler_v7.hlsl:71-82
+inline MatOpt make_matopt(const orc_material& m, uint32_t id) {
+    MatOpt o;
+    o.Kd = mk3(q16(m.Kd[0]), q16(m.Kd[1]), q16(m.Kd[2])); o.Kd_w = q16(m.Kd[3]);
+    o.Pr = q16(m.Pr_Pm_Ps_Pc[0]); o.Pm = q16(m.Pr_Pm_Ps_Pc[1]); o.Ps = q16(m.Pr_Pm_Ps_Pc[2]); o.Pc = q16(m.Pr_Pm_Ps_Pc[3]);
+    o.Ks = mk3(q16(m.Ks[0]), q16(m.Ks[1]), q16(m.Ks[2]));
+    o.Ke = mk3(q16(m.Ke[0]), q16(m.Ke[1]), q16(m.Ke[2]));
+    o.mID = id;
+    return o;
+}
+
+// shaders/Common_v7.hlsl:119-138
+inline float RandomFloat(uint32_t seed[2]) {
+    uint32_t v0 = seed[0], v1 = seed[1], sum = 0u;
+    const uint32_t delta = 0x9e3779b9u;
+    for (uint32_t i = 0; i < 4u; i++) {
+        sum += delta;
+        v0 += ((v1 << 4u) + 0xA341316Cu) ^ (v1 + sum) ^ ((v1 >> 5u) + 0xC8013EA4u);
+        v1 += ((v0 << 4u) + 0xAD90777Du) ^ (v0 + sum) ^ ((v0 >> 5u) + 0x7E95761Eu);
+    }
+    seed[0] = v0; seed[1] = v1;
+    return (float)v0 / 4294967296.0f;
+}
+
+// shaders/Pass_init_di_v7.hlsl:63-77 with uint(time) := global sample index (D2)
+inline void init_seed(uint32_t x, uint32_t y, uint32_t pass, uint32_t sample, uint32_t seed[2]) {
+    seed[0] = (y * 73856093u) ^ (x * 19349663u) ^ (pass * 83492791u) ^ (sample * 293803u);
+    seed[1] = (x * 37623481u) ^ (y * 51964263u) ^ (pass * 68250729u) ^ (sample * 423977u);
+}
+
+// shaders/Common_v7.hlsl:173-198
+inline uint32_t MapPixelID(uint32_t w, uint32_t /*h*/, uint32_t x, uint32_t y) {
+    const uint32_t ts = 4;
+    uint32_t tcx = (w + ts - 1) / ts;
+    return ((y / ts) * tcx + (x / ts)) * (ts * ts) + ((y % ts) * ts + (x % ts));
+}
+
+// shaders/Common_v7.hlsl:151-160
+inline f3 SafeMultiply(float s, f3 v) {
+    f3 r = s * v;
+    if (any_nan_inf(r)) return mk3(0, 0, 0);
+    return r;
+}
+inline float SafeMultiply1(float s, float v) {   // float overload via float3 broadcast, .x taken (Appendix C.3)
+    float r = s * v;
+    if (isnan1(r) || isinf1(r)) return 0.0f;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------ GGX (shaders/GGX_v7.hlsl)
+// :1-23
+inline float ESS_LUT(const Ctx& c, const MatOpt& mat, float NdotV) {
+    NdotV = saturate1(NdotV);
+    float thetaIdxF = NdotV * 15.0f;
+    int i0 = (int)floorf(thetaIdxF);
+    int i1 = std::min(i0 + 1, 15);
+    float w = thetaIdxF - (float)i0;
+    orc_material m = fetch_material(*c.S, mat.mID);
+    float v0 = m.LUT[i0], v1 = m.LUT[i1];
+    return lerp1(v0, v1, w);
+}
+// :26-29   pow(abs(1-c),5) = x*x*x*x*x (Appendix C.3)
+inline f3 SchlickFresnel(f3 F0, float cosTheta) {
+    float x = fabsf(1.0f - cosTheta);
+    float p = (((x * x) * x) * x) * x;
+    return saturate3(mk3(F0.x + (1.0f - F0.x) * p, F0.y + (1.0f - F0.y) * p, F0.z + (1.0f - F0.z) * p));
+}
+// :31-40
+inline float D_GGX(float NdotH, float roughness) {
+    float alpha = roughness * roughness;
+    float alpha2 = alpha * alpha;
+    float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (alpha2 - 1.0f) + 1.0f);
+    return alpha2 / ((PI_REF * denom) * denom);
+}
+// :43-52
+inline float G2_SmithGGX(float NdotV, float NdotL, float alpha) {
+    float alpha2 = alpha * alpha;
+    float denomA = NdotV * sqrtf(alpha2 + ((1.0f - alpha2) * NdotL) * NdotL);
+    float denomB = NdotL * sqrtf(alpha2 + ((1.0f - alpha2) * NdotV) * NdotV);
+    return ((2.0f * NdotL) * NdotV) / (denomA + denomB);
+}
+// :55-61
+inline float G1_SmithGGX(float NdotV, float alpha) {
+    float alpha2 = alpha * alpha;
+    float denomC = sqrtf(alpha2 + ((1.0f - alpha2) * NdotV) * NdotV) + NdotV;
+    return (2.0f * NdotV) / denomC;
+}
+// :65-76
+inline void CoordinateSystem(f3 N, f3& T, f3& B) {
+    if (fabsf(N.z) < 0.999f) T = normalize3(cross3(mk3(0, 0, 1), N));
+    else T = normalize3(cross3(mk3(1, 0, 0), N));
+    B = cross3(N, T);
+}
+// :93-169.  `alpha = Pr*Pr` is a half*half product (true 16-bit types, DXRHelper.h:125).
+inline f3 SampleBRDF_GGX(const MatOpt& mat, f3 outgoing, f3 normal, uint32_t seed[2]) {
+    float alpha = hmul(mat.Pr, mat.Pr);
+    f3 N = normalize3(normal), V = normalize3(outgoing), T1, T2;
+    CoordinateSystem(N, T1, T2);
+    float vx = dot3(T1, V), vy = dot3(T2, V), vz = dot3(N, V);
+    f3 Ve = normalize3(mk3(alpha * vx, alpha * vy, vz));
+    float lensq = Ve.x * Ve.x + Ve.y * Ve.y;
+    f3 T1h = (lensq > 0.0f) ? mk3(-Ve.y, Ve.x, 0.0f) * d_rsqrt(lensq) : mk3(1, 0, 0);
+    f3 T2h = cross3(Ve, T1h);
+    float U1 = RandomFloat(seed), U2 = RandomFloat(seed);
+    float r = sqrtf(U1);
+    float phi = (2.0f * PI_REF) * U2;
+    float sn, cs; d_sincos(phi, &sn, &cs);
+    float t1 = r * cs, t2 = r * sn;
+    float s = 0.5f * (1.0f + Ve.z);
+    t2 = (1.0f - s) * sqrtf(saturate1(1.0f - t1 * t1)) + s * t2;
+    f3 Nh = (t1 * T1h + t2 * T2h) + sqrtf(saturate1((1.0f - t1 * t1) - t2 * t2)) * Ve;
+    f3 Ne = normalize3(mk3(alpha * Nh.x, alpha * Nh.y, fmaxf(0.0f, Nh.z)));
+    f3 H = (Ne.x * T1 + Ne.y * T2) + Ne.z * N;
+    f3 sample = reflect3(-V, H);
+    if (dot3(sample, normal) < 0.0f) sample = -sample;
+    return sample;
+}
+// :174-206
+inline f3 EvaluateBRDF_GGX(const Ctx& c, const MatOpt& mat, f3 normal, f3 incoming, f3 outgoing) {
+    f3 N = normalize3(normal), V = normalize3(outgoing), L = normalize3(-incoming);
+    f3 H = normalize3(V + L);
+    float NdotV = dot3(N, V), NdotL = dot3(N, L), NdotH = dot3(N, H), VdotH = dot3(V, H);
+    f3 F = SchlickFresnel(mat.Ks, VdotH);
+    float D = D_GGX(NdotH, mat.Pr);
+    float G = G2_SmithGGX(NdotV, NdotL, hmul(mat.Pr, mat.Pr));
+    float denominator = (4.0f * NdotV) * NdotL;
+    if (denominator < EPS) return mk3(0, 0, 0);
+    f3 specular = ((F * D) * G) / denominator;
+    float Ess = ESS_LUT(c, mat, NdotV);
+    float kms = (1.0f - Ess) / Ess;
+    f3 specular_ess = specular * mk3(1.0f + mat.Ks.x * kms, 1.0f + mat.Ks.y * kms, 1.0f + mat.Ks.z * kms);
+    if (any_nan_inf(specular_ess)) return mk3(0, 0, 0);
+    return specular_ess;
+}
+// :209-224
+inline float BRDF_PDF_GGX(const MatOpt& mat, f3 normal, f3 incoming, f3 outgoing) {
+    f3 N = normalize3(normal), V = normalize3(outgoing), L = normalize3(-incoming);
+    f3 H = normalize3(V + L);
+    float NdotH = dot3(N, H), NdotV = dot3(N, V);
+    float alpha = hmul(mat.Pr, mat.Pr);
+    float G1 = G1_SmithGGX(NdotV, alpha);
+    float D = D_GGX(NdotH, mat.Pr);
+    return (G1 * D) / (NdotV * 4.0f);
+}
+
+// ------------------------------------------------------------------------------------------ Lambert (include/Lambertian_v6.hlsl)
+// :2-37
+inline f3 RandomUnitVectorInHemisphere(f3 normal, uint32_t seed[2]) {
+    float u1 = RandomFloat(seed), u2 = RandomFloat(seed);
+    float r = sqrtf(u1);
+    float theta = (2.0f * 3.14159265358979323846f) * u2;
+    float sn, cs; d_sincos(theta, &sn, &cs);
+    float x = r * cs, y = r * sn;
+    float z = sqrtf(fmaxf(0.0f, (1.0f - x * x) - y * y));
+    f3 h = normal;
+    f3 up = fabsf(normal.z) < 0.999f ? mk3(0, 0, 1) : mk3(1, 0, 0);
+    f3 right = normalize3(cross3(up, h));
+    f3 forward = cross3(h, right);
+    f3 hs = (x * right + y * forward) + z * h;
+    hs = normalize3(hs);
+    if (dot3(hs, normal) < 0.0f) hs = -hs;
+    return hs;
+}
+// :51-58
+inline f3 EvaluateBRDF_Lambertian(const MatOpt& mat) { return mat.Kd / PI_REF; }
+// :61-64
+inline float BRDF_PDF_Lambertian(f3 normal, f3 incoming) { return fmaxf(dot3(normal, -incoming), EPS) / PI_REF; }
+
+// ------------------------------------------------------------------------------------------ shaders/BRDF_v7.hlsl
+// :50-70
+inline void CalculateStrategyProbabilities(const Ctx& c, const MatOpt& mat, f3 outgoing, f3 normal, float& p_d, float& p_s) {
+    if (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) { p_d = 1.0f; p_s = 0.0f; return; }
+    float cosTheta = dot3(normal, outgoing);
+    f3 fr = SchlickFresnel(mat.Ks, cosTheta);
+    p_s = fminf(1.0f, ((fr.x + fr.y) + fr.z) / 3.0f + mat.Pm);
+    p_d = 1.0f - p_s;
+}
+// :7-48  (always consumes one RandomFloat)
+inline uint32_t SelectSamplingStrategy(const Ctx& c, const MatOpt& mat, f3 outgoing, f3 normal, uint32_t seed[2], float& probability) {
+    float r = RandomFloat(seed);
+    if (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) { probability = 0.0f; return 0; }
+    float cosTheta = dot3(normal, outgoing);
+    f3 fr = SchlickFresnel(mat.Ks, cosTheta);
+    float p_s = fminf(1.0f, ((fr.x + fr.y) + fr.z) / 3.0f + mat.Pm);
+    probability = p_s;
+    if (r <= p_s) { if (mat.Pr < 0.04f) return 0; return 1; }
+    return 0;
+}
+// :74-88
+inline f3 SampleBRDF(uint32_t strategy, const MatOpt& mat, f3 outgoing, f3 normal, uint32_t seed[2]) {
+    if (strategy == 0) return RandomUnitVectorInHemisphere(normal, seed);
+    return SampleBRDF_GGX(mat, outgoing, normal, seed);
+}
+// :91-106
+inline f3 EvaluateBRDF(const Ctx& c, uint32_t strategy, const MatOpt& mat, f3 normal, f3 incidence, f3 outgoing) {
+    if (strategy == 0) return EvaluateBRDF_Lambertian(mat);
+    return EvaluateBRDF_GGX(c, mat, normal, incidence, outgoing);
+}
+// :109-124
+inline float BRDF_PDF(uint32_t strategy, const MatOpt& mat, f3 normal, f3 incidence, f3 outgoing) {
+    if (strategy == 0) return BRDF_PDF_Lambertian(normal, incidence);
+    return BRDF_PDF_GGX(mat, normal, incidence, outgoing);
+}
+
+// the "combined lobe" pattern repeated at Sampler_v7.hlsl:123-128, 248-261, 361-374, 443-456, 601-614 and
+// Path_Sampler_v7.hlsl:66-78: F = p_d*f0 + p_s*f1 (SafeMultiply'd), P likewise.
+inline f3 CombinedF(const Ctx& c, const MatOpt& mat, f3 normal, f3 incidence, f3 outgoing, float p_d, float p_s) {
+    f3 F1 = SafeMultiply(p_d, EvaluateBRDF(c, 0, mat, normal, incidence, outgoing));
+    f3 F2 = (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) ? mk3(0, 0, 0)
+                                                   : SafeMultiply(p_s, EvaluateBRDF(c, 1, mat, normal, incidence, outgoing));
+    return F1 + F2;
+}
+
+// ------------------------------------------------------------------------------------------ ClosestHit (shaders/Hit_v7.hlsl:12-61)
+inline void ClosestHit(const Ctx& c, f3 ro, f3 rd, const Hit& h, HitInfo& p) {
+    const orc_scene& S = *c.S;
+    const Instance& inst = S.instances[h.inst];
+    const Model& M = S.models[inst.model];
+    p.objID = h.inst;
+    f3 worldOrigin = ro + h.t * rd;
+    uint32_t vertId = 3 * h.prim;
+    uint32_t mslot = vertId + M.mat_offset;
+    uint32_t materialID = mslot < S.material_ids.size() ? S.material_ids[mslot] : 0u;
+    float bary[3] = {(1.0f - h.b1) - h.b2, h.b1, h.b2};
+    uint32_t i0 = M.idx[vertId], i1 = M.idx[vertId + 1], i2 = M.idx[vertId + 2];
+    f3 e1 = M.pos[i1] - M.pos[i0], e2 = M.pos[i2] - M.pos[i0];
+    f3 cross_a = cross3(e1, e2);
+    float area_l = fabsf(length3(cross_a) * 0.5f);
+    f3 flatNormal = normalize3(cross_a);
+    p.area = area_l;
+    f3 smooth = mk3(0, 0, 0);
+    const uint32_t vi[3] = {i0, i1, i2};
+    for (int i = 0; i < 3; i++) {
+        f3 n = M.nrm[vi[i]];
+        if (n.x != 0.0f && n.y != 0.0f && n.z != 0.0f) smooth = smooth + n * bary[i];
+        else smooth = smooth + flatNormal * bary[i];
+    }
+    f3 normal;
+    if (length3(smooth) > 0.0001f) normal = normalize3(smooth); else normal = flatNormal;
+    f4 wn = mul44(inst.p.objectToWorldNormal, normal.x, normal.y, normal.z, 0.0f);
+    p.hitNormal = normalize3(mk3(wn.x, wn.y, wn.z));
+    p.materialID = materialID;
+    p.hitPosition = worldOrigin;
+}
+
+// TraceRay closest (T3) + ClosestHit/Miss
+inline bool TraceClosest(const Ctx& c, f3 o, f3 d, float tmin, float tmax, HitInfo& p) {
+    c.C->closest_rays++;
+    Hit h;
+    if (!trace(*c.S, o, d, tmin, tmax, false, c.mode, h, *c.C)) { p.materialID = MISS_ID; return false; }
+    ClosestHit(c, o, d, h, p);
+    return true;
+}
+// TraceRay shadow (T4): returns isHit
+inline bool TraceShadow(const Ctx& c, f3 o, f3 d, float tmin, float tmax) {
+    c.C->shadow_rays++;
+    Hit h;
+    return trace(*c.S, o, d, tmin, tmax, true, c.mode, h, *c.C);
+}
+
+// ------------------------------------------------------------------------------------------ shaders/Sampler_v7.hlsl
+inline float LinearizeVector(f3 v) { return length3(v); }   // :1-5
+
+// :86-104
+inline float VisibilityCheck(const Ctx& c, f3 x1, f3 n1, f3 dir, float dist) {
+    f3 o = x1 + normalize3(n1) * S_BIAS;
+    float tmax = fmaxf(dist - 10.0f * S_BIAS, 2.0f * S_BIAS);
+    return TraceShadow(c, o, dir, 0.0f, tmax) ? 0.0f : 1.0f;
+}
+// :106-131
+inline f3 ReconnectDI(const Ctx& c, f3 x1, f3 n1, f3 x2, f3 n2, f3 L, f3 outgoing, const MatOpt& material) {
+    f3 dir = x2 - x1;
+    float dist = length3(dir);
+    float cosThetaX1 = fmaxf(0.0f, dot3(n1, normalize3(dir)));
+    if (dot3(n2, normalize3(-dir)) < 0.0f) n2 = -n2;
+    float cosThetaX2 = fmaxf(0.0f, dot3(n2, normalize3(-dir)));
+    float p_d, p_s;
+    CalculateStrategyProbabilities(c, material, normalize3(outgoing), n1, p_d, p_s);
+    f3 F = CombinedF(c, material, n1, normalize3(-dir), normalize3(outgoing), p_d, p_s);
+    return (((F * L) * cosThetaX1) * cosThetaX2) / (dist * dist);
+}
+// :134-161
+inline f3 ReconnectGI(const Ctx& c, f3 x1, f3 n1, f3 x2, f3 /*n2*/, f3 L, f3 outgoing, const MatOpt& material1) {
+    f3 dir = x2 - x1;
+    float cosThetaX1 = fabsf(dot3(n1, normalize3(dir)));
+    float p_d, p_s;
+    CalculateStrategyProbabilities(c, material1, normalize3(outgoing), n1, p_d, p_s);
+    f3 Fx1 = CombinedF(c, material1, n1, normalize3(-dir), normalize3(outgoing), p_d, p_s);
+    f3 fr = (Fx1 * cosThetaX1) * L;
+    if (any_nan_inf(fr)) return mk3(0, 0, 0);
+    return fr;
+}
+
+// light selection :293-308 (binary search for the first cdf > u; u == 1.0 keeps index 0, Appendix C.3)
+inline uint32_t SelectLight(const orc_scene& S, float randomValue) {
+    int left = 0, right = (int)S.lights[0].triCount - 1, selected = 0;
+    while (left <= right) {
+        int mid = left + (right - left) / 2;
+        if (randomValue < S.lights[mid].cdf) { selected = mid; right = mid - 1; }
+        else left = mid + 1;
+    }
+    return (uint32_t)selected;
+}
+
+struct LightSample { f3 point, normal_l, L_norm, emission; float dist2, dist, pdf_l, cos_x_raw, cos_y_raw; };
+
+// shared front half of SampleLightNEE (:292-346) and SampleLightNEE_GI (:529-584)
+inline void SampleLightPoint(const Ctx& c, f3 origin, uint32_t seed[2], LightSample& ls) {
+    const orc_scene& S = *c.S;
+    float randomValue = RandomFloat(seed);
+    const orc_light_tri& lt = S.lights[SelectLight(S, randomValue)];
+    const float* M = S.instances[lt.instanceID].p.objectToWorld;
+    f4 a = mul44(M, lt.x[0], lt.x[1], lt.x[2], 1.0f);
+    f4 b = mul44(M, lt.y[0], lt.y[1], lt.y[2], 1.0f);
+    f4 cc = mul44(M, lt.z[0], lt.z[1], lt.z[2], 1.0f);
+    f3 x_v = mk3(a.x, a.y, a.z), y_v = mk3(b.x, b.y, b.z), z_v = mk3(cc.x, cc.y, cc.z);
+    float xi1 = RandomFloat(seed), xi2 = RandomFloat(seed);
+    if (xi1 + xi2 > 1.0f) { xi1 = 1.0f - xi1; xi2 = 1.0f - xi2; }
+    float u = (1.0f - xi1) - xi2, v = xi1, w = xi2;
+    ls.point = (u * x_v + v * y_v) + w * z_v;
+    f3 L = ls.point - origin;
+    ls.dist2 = dot3(L, L);
+    ls.dist = sqrtf(fmaxf(ls.dist2, EPS));
+    ls.L_norm = normalize3(L);
+    f3 cross_l = cross3(y_v - x_v, z_v - x_v);
+    f3 normal_l = normalize3(cross_l);
+    if (dot3(normal_l, -ls.L_norm) < 0.0f) normal_l = -normal_l;
+    ls.normal_l = normal_l;
+    float area_l = fabsf(length3(cross_l) * 0.5f);
+    ls.pdf_l = lt.weight / fmaxf(area_l, EPS);
+    ls.emission = mk3(lt.emission[0], lt.emission[1], lt.emission[2]);
+}
+
+// :273-396 with useVisibility=false (call site :677-693)
+inline void SampleLightNEE(const Ctx& c, float& pdf_light, float& pdf_bsdf, float& p_hat, uint32_t seed[2], f3 worldOrigin,
+                           f3 normal, f3 outgoing, const MatOpt& material, f3& emission, f3& x2, f3& n2) {
+    LightSample ls;
+    SampleLightPoint(c, worldOrigin, seed, ls);
+    x2 = ls.point; n2 = ls.normal_l;
+    float cos_theta_x = dot3(normal, ls.L_norm);
+    float cos_theta_y = dot3(ls.normal_l, -ls.L_norm);
+    float G = fmaxf((cos_theta_y * cos_theta_x) / ls.dist2, EPS);
+    emission = ls.emission;
+    float p_d, p_s;
+    f3 on = normalize3(outgoing);
+    CalculateStrategyProbabilities(c, material, on, normal, p_d, p_s);
+    f3 brdf_light = CombinedF(c, material, normal, -ls.L_norm, on, p_d, p_s);
+    float pdf0 = (BRDF_PDF(0, material, normal, -ls.L_norm, on) * cos_theta_y) / ls.dist2;
+    float P1 = SafeMultiply1(p_d, pdf0);
+    float P2 = 0.0f;
+    if (!(c.cfg.flags & ORC_FLAG_LAMBERT_ONLY)) {
+        float pdf1 = (BRDF_PDF(1, material, normal, -ls.L_norm, on) * cos_theta_y) / ls.dist2;
+        P2 = SafeMultiply1(p_s, pdf1);
+    }
+    float P = P1 + P2;
+    p_hat = LinearizeVector((ls.emission * brdf_light) * G);   // * V with V == 1.0f
+    pdf_light = fmaxf(EPS, ls.pdf_l);
+    pdf_bsdf = P;
+}
+
+// :199-271
+inline void SampleLightBSDF(const Ctx& c, float& pdf_light, float& pdf_bsdf, float& p_hat, uint32_t seed[2], f3 worldOrigin,
+                            f3 normal, f3 outgoing, const MatOpt& material, uint32_t strategy, f3& emission, f3& x2, f3& n2) {
+    f3 sample = SampleBRDF(strategy, material, outgoing, normal, seed);
+    HitInfo sp;
+    bool hit = TraceClosest(c, worldOrigin, sample, S_BIAS, 10000.0f, sp);
+    if (!hit) { p_hat = 0.0f; return; }       // materials[MISS_ID] reads 0 => Ke == 0 => p_hat = 0
+    orc_material mk = fetch_material(*c.S, sp.materialID);
+    float Ke = (mk.Ke[0] + mk.Ke[1]) + mk.Ke[2];
+    emission = mk3(mk.Ke[0], mk.Ke[1], mk.Ke[2]);
+    x2 = sp.hitPosition; n2 = sp.hitNormal;
+    if (Ke > EPS) {
+        f3 L = sp.hitPosition - worldOrigin;
+        float dist = length3(L);
+        float dist2 = dist * dist;
+        float cos_theta = dot3(sp.hitNormal, -sample);
+        pdf_light = (Ke / 3.0f) / c.S->lights[0].total_weight;
+        float p_d, p_s;
+        f3 on = normalize3(outgoing);
+        CalculateStrategyProbabilities(c, material, on, normal, p_d, p_s);
+        f3 brdf = CombinedF(c, material, normal, -sample, on, p_d, p_s);
+        float pdf0 = (BRDF_PDF(0, material, normal, -sample, outgoing) * cos_theta) / dist2;
+        float P1 = SafeMultiply1(p_d, pdf0);
+        float P2 = 0.0f;
+        if (!(c.cfg.flags & ORC_FLAG_LAMBERT_ONLY)) {
+            float pdf1 = (BRDF_PDF(1, material, normal, -sample, outgoing) * cos_theta) / dist2;
+            P2 = SafeMultiply1(p_s, pdf1);
+        }
+        pdf_bsdf = P1 + P2;
+        float ndot = dot3(normal, sample);
+        p_hat = LinearizeVector(((((brdf * emission) * ndot) * cos_theta)) / dist2);
+    } else {
+        p_hat = 0.0f;
+    }
+}
+
+// shaders/Reservoir_v7.hlsl:57-80
+inline bool UpdateReservoir(ReservoirDI& r, float wi, f3 x2, f3 n2, f3 L2, uint32_t seed[2]) {
+    r.w_sum += wi;
+    if (RandomFloat(seed) < wi / r.w_sum) { r.x2 = x2; r.n2 = n2; r.L2 = q16v(L2); return true; }
+    return false;
+}
+// shaders/Reservoir_v7.hlsl:30-53
+inline bool UpdateReservoir_GI(ReservoirGI& r, float wi, f3 xn, f3 nn, f3 E3, uint32_t seed[2]) {
+    r.w_sum += wi;
+    if (RandomFloat(seed) < wi / r.w_sum) { r.xn = xn; r.nn = nn; r.E3 = q16v(E3); return true; }
+    return false;
+}
+
+// :653-736
+inline void SampleRIS(const Ctx& c, uint32_t M1, uint32_t M2, f3 outgoing, ReservoirDI& reservoir, const HitInfo& payload,
+                      const MatOpt& matOpt, uint32_t seed[2]) {
+    float p_strategy = 1.0f;
+    uint32_t strategy = SelectSamplingStrategy(c, matOpt, outgoing, payload.hitNormal, seed, p_strategy);
+    float fM1 = (float)M1, fM2 = (float)M2;
+    for (uint32_t i = 0; i < M1; i++) {
+        float pdf_light = 0.0f, pdf_bsdf = 0.0f, p_hat = 0.0f; f3 emission, x2, n2;
+        SampleLightNEE(c, pdf_light, pdf_bsdf, p_hat, seed, payload.hitPosition, payload.hitNormal, outgoing, matOpt, emission, x2, n2);
+        float mi = pdf_light / (fM1 * pdf_light + fM2 * pdf_bsdf);
+        float wi = (mi * p_hat) / pdf_light;
+        if (p_hat > 0.0f) UpdateReservoir(reservoir, wi, x2, n2, emission, seed);
+    }
+    for (uint32_t j = 0; j < M2; j++) {
+        float pdf_light = 0.0f, pdf_bsdf = 0.0f, p_hat = 0.0f; f3 emission = mk3(0, 0, 0), x2 = mk3(0, 0, 0), n2 = mk3(0, 0, 0);
+        SampleLightBSDF(c, pdf_light, pdf_bsdf, p_hat, seed, payload.hitPosition, payload.hitNormal, outgoing, matOpt, strategy, emission, x2, n2);
+        float mi = pdf_bsdf / (fM1 * pdf_light + fM2 * pdf_bsdf);
+        float wi = (mi * p_hat) / pdf_bsdf;
+        if (p_hat > 0.0f) UpdateReservoir(reservoir, wi, x2, n2, emission, seed);
+    }
+    reservoir.M = 1;
+}
+
+// :508-647 with useVisibility=false (call site Path_Sampler_v7.hlsl:133-151)
+inline f3 SampleLightNEE_GI(const Ctx& c, float& pdf_light, float& pdf_bsdf, f3& incoming, f3& x2_pos, uint32_t seed[2], f3 origin,
+                            f3 normal, f3 outgoing, f3 acc_l, float acc_pdf, f3& throughput, f3& emission, const MatOpt& material) {
+    LightSample ls;
+    SampleLightPoint(c, origin, seed, ls);
+    x2_pos = ls.point;
+    float cos_theta_x = fabsf(dot3(normal, ls.L_norm));
+    if (cos_theta_x < EPS) cos_theta_x = 0.0f;
+    float cos_theta_y = fabsf(dot3(ls.normal_l, -ls.L_norm));
+    if (cos_theta_y < EPS) cos_theta_y = 0.0f;
+    float G = cos_theta_x;
+    float p_d, p_s;
+    f3 on = normalize3(outgoing);
+    CalculateStrategyProbabilities(c, material, on, normal, p_d, p_s);
+    f3 brdf_light = CombinedF(c, material, normal, -ls.L_norm, on, p_d, p_s);
+    float P1 = SafeMultiply1(p_d, BRDF_PDF(0, material, normal, -ls.L_norm, on));
+    float P2 = (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) ? 0.0f : SafeMultiply1(p_s, BRDF_PDF(1, material, normal, -ls.L_norm, on));
+    float P = P1 + P2;
+    if (cos_theta_y > 0.0f) pdf_light = (fmaxf(EPS, ls.pdf_l) * ls.dist2) / cos_theta_y;
+    pdf_bsdf = P;
+    incoming = -ls.L_norm;
+    acc_pdf *= pdf_light;
+    acc_l = acc_l * (brdf_light * G);           // * V with V == 1.0f
+    throughput = brdf_light * G;
+    emission = ls.emission;
+    if (acc_pdf > 0.0f) return (ls.emission * acc_l) / acc_pdf;
+    return mk3(0, 0, 0);
+}
+
+// :399-505.  Returns status: 0 = continue (no emitter), 1 = emitter hit, 2 = miss (D1)
+inline int SampleLightBSDF_GI(const Ctx& c, float& pdf_light, float& pdf_bsdf, f3& incoming, f3& new_origin, f3& new_normal,
+                              f3& new_outgoing, MatOpt& new_material, uint32_t seed[2], uint32_t strategy, f3 origin, f3 normal,
+                              f3 outgoing, f3& acc_l, float& acc_pdf, f3& throughput, f3& emission, const MatOpt& material,
+                              f3& contribution) {
+    f3 sample = SampleBRDF(strategy, material, outgoing, normal, seed);
+    HitInfo sp;
+    bool hit = TraceClosest(c, origin, sample, S_BIAS, 10000.0f, sp);
+    contribution = mk3(0, 0, 0);
+    if (!hit) return 2;
+    MatOpt mat_ke = make_matopt(fetch_material(*c.S, sp.materialID), sp.materialID);
+    float p_d, p_s;
+    f3 on = normalize3(outgoing);
+    CalculateStrategyProbabilities(c, material, on, normal, p_d, p_s);
+    f3 brdf = CombinedF(c, material, normal, -sample, on, p_d, p_s);
+    float P1 = SafeMultiply1(p_d, BRDF_PDF(0, material, normal, -sample, outgoing));
+    float P2 = (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) ? 0.0f : SafeMultiply1(p_s, BRDF_PDF(1, material, normal, -sample, outgoing));
+    float P = P1 + P2;
+    pdf_bsdf = P;
+    float NdotL = dot3(normal, sample);
+    incoming = -sample;
+    bool emitter = (mat_ke.Ke.x != 0.0f || mat_ke.Ke.y != 0.0f || mat_ke.Ke.z != 0.0f);   // length(half3 Ke) > 0
+    acc_pdf *= pdf_bsdf;
+    acc_l = acc_l * (brdf * NdotL);
+    throughput = brdf * NdotL;
+    if (emitter) {
+        f3 L = sp.hitPosition - origin;
+        float dist = length3(L);
+        float dist2 = dist * dist;
+        float cos_theta = dot3(sp.hitNormal, -sample);
+        float kesum = hadd(hadd(mat_ke.Ke.x, mat_ke.Ke.y), mat_ke.Ke.z);       // half arithmetic
+        pdf_light = (((kesum / 3.0f) / c.S->lights[0].total_weight) * dist2) / cos_theta;
+        emission = mat_ke.Ke;
+        contribution = (mat_ke.Ke * acc_l) / acc_pdf;
+        return 1;
+    }
+    new_origin = sp.hitPosition; new_normal = sp.hitNormal; new_outgoing = -sample; new_material = mat_ke;
+    emission = mk3(0, 0, 0);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ shaders/Path_Sampler_v7.hlsl:3-286
+inline f3 SamplePathSimple(const Ctx& c, ReservoirGI& reservoir, f3 initPoint, f3 initNormal, f3 initOutgoing,
+                           const MatOpt& initMaterial, uint32_t seed[2]) {
+    f3 acc_f = mk3(1, 1, 1), acc_f_reconnection = mk3(1, 1, 1);
+    float acc_pdf = 1.0f;
+    f3 x1_shadow = mk3(0, 0, 0), x2_shadow = mk3(0, 0, 0);
+    f3 acc_L = mk3(0, 0, 0);
+    f3 origin = initPoint, normal = initNormal, outgoing = normalize3(initOutgoing);
+    MatOpt material = initMaterial;
+    const uint32_t nee = c.cfg.nee_samples;
+    const float fnee = (float)nee;
+    {   // :37-99
+        float p_strategy;
+        uint32_t strategy = SelectSamplingStrategy(c, material, outgoing, normal, seed, p_strategy);
+        f3 sample = SampleBRDF(strategy, material, outgoing, normal, seed);
+        HitInfo sp;
+        bool hit = TraceClosest(c, origin, sample, S_BIAS, 10000.0f, sp);
+        if (!hit) return mk3(0, 0, 0);                                          // D1
+        orc_material hm = fetch_material(*c.S, sp.materialID);
+        if (length3(mk3(hm.Ke[0], hm.Ke[1], hm.Ke[2])) > 0.0f) return mk3(0, 0, 0);   // :55-60
+        f3 incoming = normalize3(-sample);
+        float p_d, p_s;
+        CalculateStrategyProbabilities(c, material, outgoing, normal, p_d, p_s);
+        f3 F = CombinedF(c, material, normal, incoming, outgoing, p_d, p_s);
+        float P1 = SafeMultiply1(p_d, BRDF_PDF(0, material, normal, incoming, outgoing));
+        float P2 = (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) ? 0.0f : SafeMultiply1(p_s, BRDF_PDF(1, material, normal, incoming, outgoing));
+        float P = P1 + P2;
+        float NdotL = dot3(normal, sample);
+        acc_pdf *= P;
+        acc_f = acc_f * (F * NdotL);
+        outgoing = incoming;
+        material = make_matopt(hm, sp.materialID);
+        normal = sp.hitNormal;
+        origin = sp.hitPosition;
+    }
+    f3 xn = origin, nn = normalize3(normal);          // :104-106
+    for (uint32_t i = 0; i < c.cfg.bounces; i++) {    // :112-269
+        float p_strategy = 1.0f;
+        uint32_t strategy = SelectSamplingStrategy(c, material, outgoing, normal, seed, p_strategy);
+        for (uint32_t j = 0; j < nee; j++) {
+            float pdf_light = 1.0f, pdf_bsdf = 1.0f;
+            f3 throughput_NEE = mk3(1, 1, 1), emission_NEE = mk3(0, 0, 0), incoming_NEE, x2;
+            f3 contribution = SampleLightNEE_GI(c, pdf_light, pdf_bsdf, incoming_NEE, x2, seed, origin, normal, outgoing, acc_f,
+                                                acc_pdf, throughput_NEE, emission_NEE, material);
+            float mi = pdf_light / (fnee * pdf_light + pdf_bsdf);
+            f3 E_reconnection = ((acc_f_reconnection * mi) * emission_NEE) * throughput_NEE;
+            f3 E_path = mi * contribution;
+            float wi = LinearizeVector(E_path);
+            acc_L = acc_L + mi * contribution;
+            if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
+            if (UpdateReservoir_GI(reservoir, wi, xn, normalize3(nn), E_reconnection, seed)) {
+                x1_shadow = origin + S_BIAS * normalize3(normal);
+                x2_shadow = x2;
+            }
+        }
+        (void)strategy;
+        float pdf_light = 1.0f, pdf_bsdf = 1.0f;
+        f3 throughput_BSDF = mk3(1, 1, 1), emission_BSDF = mk3(0, 0, 0), incoming_BSDF;
+        f3 new_origin, new_normal, new_outgoing; MatOpt new_material;
+        strategy = SelectSamplingStrategy(c, material, outgoing, normal, seed, p_strategy);
+        f3 contribution;
+        int st = SampleLightBSDF_GI(c, pdf_light, pdf_bsdf, incoming_BSDF, new_origin, new_normal, new_outgoing, new_material, seed,
+                                    strategy, origin, normal, outgoing, acc_f, acc_pdf, throughput_BSDF, emission_BSDF, material,
+                                    contribution);
+        if (st == 2) break;                                                        // D1
+        acc_f_reconnection = acc_f_reconnection * throughput_BSDF;
+        if (length3(contribution) > 0.0f) {
+            float mi = pdf_bsdf / (fnee * pdf_light + pdf_bsdf);
+            f3 E_reconnection = (acc_f_reconnection * mi) * emission_BSDF;
+            f3 E_path = mi * contribution;
+            float wi = LinearizeVector(E_path);
+            acc_L = acc_L + E_path;
+            if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
+            UpdateReservoir_GI(reservoir, wi, xn, normalize3(nn), E_reconnection, seed);
+            break;
+        } else {
+            if (st == 1) break;                                                    // D4
+            origin = new_origin; material = new_material; outgoing = new_outgoing; normal = new_normal;
+        }
+    }
+    f3 ds = x2_shadow - x1_shadow;
+    if (nee > 0 && length3(ds) > EPS) {              // :271-283
+        float len = length3(ds);
+        bool isHit = TraceShadow(c, x1_shadow, normalize3(ds), 0.5f * S_BIAS, fmaxf(S_BIAS, len - (S_BIAS * 5.0f)));
+        reservoir.w_sum *= isHit ? 0.0f : 1.0f;
+    }
+    return acc_L;
+}
+
+// ------------------------------------------------------------------------------------------ camera (Pass_init_di_v7.hlsl:59,80-95)
+inline void CameraRay(const orc_config& cfg, const orc_camera& cam, uint32_t x, uint32_t y, float jx, float jy, f3& o, f3& dir) {
+    float dimx = (float)cfg.width, dimy = (float)cfg.height;
+    f4 o4 = mul44(cam.viewI, 0.0f, 0.0f, 0.0f, 1.0f);
+    o = mk3(o4.x, o4.y, o4.z);
+    float dx = (((float)x + jx) / dimx) * 2.0f - 1.0f;
+    float dy = (((float)y + jy) / dimy) * 2.0f - 1.0f;
+    f4 target = mul44(cam.projectionI, dx, -dy, 1.0f, 1.0f);
+    f4 d4 = mul44(cam.viewI, target.x, target.y, target.z, 0.0f);
+    dir = normalize3(mk3(d4.x, d4.y, d4.z));
+}
+
+struct PixelDebug {
+    f3 cam_o, cam_d; uint32_t hit_inst, hit_prim; float hit_t;
+    uint32_t mID; f3 x1, n1;
+    ReservoirDI rdi; ReservoirGI rgi; float p_hat; f3 C; uint32_t seed_end[2]; f3 acc_L;
+};
+
+// Pass_init_di_v7.hlsl:48-190 followed by the E0 final shade (Pass_spat_di_v7.hlsl:334-372 with no neighbours)
+inline f3 RenderSample(const Ctx& c, const orc_camera& cam, uint32_t x, uint32_t y, uint32_t sample, PixelDebug* dbg) {
+    uint32_t seed[2];
+    init_seed(x, y, 1u, sample, seed);
+    float jx = 0.0f, jy = 0.0f;
+    if (c.cfg.flags & ORC_FLAG_JITTER) { jx = RandomFloat(seed); jy = RandomFloat(seed); }    // D3
+    f3 origin, direction;
+    CameraRay(c.cfg, cam, x, y, jx, jy, origin, direction);
+    c.C->paths++;
+    if (dbg) { dbg->cam_o = origin; dbg->cam_d = direction; }
+    // primary ray :91-99 — trace here (not via TraceClosest) to expose the raw hit for debugging
+    c.C->closest_rays++;
+    Hit h;
+    HitInfo payload;
+    bool hit = trace(*c.S, origin, direction, 0.0001f, 10000.0f, false, c.mode, h, *c.C);
+    if (dbg) { dbg->hit_inst = h.inst; dbg->hit_prim = h.prim; dbg->hit_t = hit ? h.t : -1.0f; }
+    if (!hit) return mk3(0, 0, 0);                                                  // D1
+    ClosestHit(c, origin, direction, h, payload);
+    uint32_t mID = payload.materialID;
+    orc_material fm = fetch_material(*c.S, mID);
+    MatOpt matOpt = make_matopt(fm, mID);
+    if (dbg) { dbg->mID = mID; dbg->x1 = payload.hitPosition; dbg->n1 = payload.hitNormal; }
+    if (length3(mk3(fm.Ke[0], fm.Ke[1], fm.Ke[2])) > 0.0f) return matOpt.Ke;       // :103-106,132 ; D5 (L1 is half3)
+    ReservoirDI reservoir; memset(&reservoir, 0, sizeof reservoir);
+    ReservoirGI reservoir_GI; memset(&reservoir_GI, 0, sizeof reservoir_GI);
+    f3 o = -direction;
+    SampleRIS(c, c.cfg.nee_samples_di, 1u, o, reservoir, payload, matOpt, seed);    // :151-159
+    f3 x1 = payload.hitPosition, n1 = normalize3(payload.hitNormal);               // :161-164
+    // GetP_Hat(..., true) :166  (Sampler_v7.hlsl:163-171)
+    f3 rdi = ReconnectDI(c, x1, n1, reservoir.x2, reservoir.n2, reservoir.L2, o, matOpt);
+    float f_g = LinearizeVector(rdi);
+    float v = 1.0f;
+    if (f_g > EPS) {                                                                // D6
+        f3 d21 = reservoir.x2 - x1;
+        v = VisibilityCheck(c, x1, n1, normalize3(d21), length3(d21));
+    }
+    float p_hat = f_g * v;
+    reservoir.W = (p_hat > EPS) ? reservoir.w_sum / p_hat : 0.0f;                   // GetW :183-188
+    f3 acc_L = SamplePathSimple(c, reservoir_GI, payload.hitPosition, payload.hitNormal, o, matOpt, seed);   // :173
+    // E0 final shade
+    f3 Cdi = ReconnectDI(c, x1, n1, reservoir.x2, reservoir.n2, reservoir.L2, o, matOpt) * reservoir.W;
+    f3 f_gi = ReconnectGI(c, x1, n1, reservoir_GI.xn, reservoir_GI.nn, reservoir_GI.E3, o, matOpt);   // GetP_Hat_GI(..., false)
+    float p_hat_gi = LinearizeVector(f_gi);
+    reservoir_GI.W = (p_hat_gi > EPS) ? reservoir_GI.w_sum / p_hat_gi : 0.0f;       // GetW_GI :190-195
+    reservoir_GI.M = 1;
+    f3 Cc = Cdi + f_gi * reservoir_GI.W;
+    if (dbg) { dbg->rdi = reservoir; dbg->rgi = reservoir_GI; dbg->p_hat = p_hat; dbg->C = Cc; dbg->seed_end[0] = seed[0]; dbg->seed_end[1] = seed[1]; dbg->acc_L = acc_L; }
+    return Cc;
+}
+
+// shaders/Common_v7.hlsl:353-376
+inline float srgb1(float c) {
+    if (c <= 0.0031308f) return 12.92f * c;
+    return 1.055f * d_pow(c, 1.0f / 2.4f) - 0.055f;
+}
+
+}  // namespace
+
+// ============================================================================================ C interface
+extern "C" {
+
+orc_scene* orc_scene_create(void) { return new orc_scene(); }
+void orc_scene_destroy(orc_scene* s) { delete s; }
+
+int orc_add_model(orc_scene* s, const orc_vertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni, uint32_t material_id_offset) {
+    Model m;
+    m.pos.resize(nv); m.nrm.resize(nv);
+    for (uint32_t i = 0; i < nv; i++) {
+        m.pos[i] = mk3(v[i].position[0], v[i].position[1], v[i].position[2]);
+        m.nrm[i] = mk3(v[i].normal_material[0], v[i].normal_material[1], v[i].normal_material[2]);
+    }
+    m.idx.assign(idx, idx + (ni / 3) * 3);
+    m.mat_offset = material_id_offset;
+    s->models.push_back(std::move(m));
+    return (int)s->models.size() - 1;
+}
+void orc_set_material_ids(orc_scene* s, const uint32_t* ids, uint32_t n) { s->material_ids.assign(ids, ids + n); }
+void orc_set_materials(orc_scene* s, const orc_material* m, uint32_t n) { s->materials.assign(m, m + n); }
+void orc_set_instances(orc_scene* s, const uint32_t* model_ids, const orc_instance_props* props, uint32_t n) {
+    s->instances.resize(n);
+    for (uint32_t i = 0; i < n; i++) { s->instances[i].model = model_ids[i]; s->instances[i].p = props[i]; }
+}
+void orc_set_lights(orc_scene* s, const orc_light_tri* l, uint32_t n) { s->lights.assign(l, l + n); }
+
+void orc_build(orc_scene* s) {
+    for (auto& m : s->models) build_bvh2(m);
+    for (auto& in : s->instances) {
+        const Model& m = s->models[in.model];
+        Box w = box_empty();
+        if (!m.idx.empty()) {
+            for (int k = 0; k < 8; k++) {
+                f3 p = mk3((k & 1) ? m.bounds.hi.x : m.bounds.lo.x, (k & 2) ? m.bounds.hi.y : m.bounds.lo.y, (k & 4) ? m.bounds.hi.z : m.bounds.lo.z);
+                f4 q = mul44(in.p.objectToWorld, p.x, p.y, p.z, 1.0f);
+                box_grow(w, mk3(q.x, q.y, q.z));
+            }
+            float sc = fmaxf(fmaxf(fabsf(w.lo.x), fabsf(w.hi.x)), fmaxf(fmaxf(fabsf(w.lo.y), fabsf(w.hi.y)), fmaxf(fabsf(w.lo.z), fabsf(w.hi.z))));
+            box_pad(w, sc * 3.0517578125e-5f + 1e-30f);
+        }
+        in.wbox = w;
+    }
+}
+
+void orc_trace(orc_scene* s, const orc_ray* rays, uint32_t n, orc_hit* out, int any_hit, int mode) {
+    orc_counters C; memset(&C, 0, sizeof C);
+    for (uint32_t i = 0; i < n; i++) {
+        Hit h;
+        f3 o = mk3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]);
+        f3 d = mk3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
+        bool hit = trace(*s, o, d, rays[i].tmin, rays[i].tmax, any_hit != 0, mode, h, C);
+        if (hit) { out[i].t = h.t; out[i].u = h.b1; out[i].v = h.b2; out[i].prim = h.prim; out[i].inst = h.inst; }
+        else { out[i].t = rays[i].tmax; out[i].u = out[i].v = 0.0f; out[i].prim = 0xFFFFFFFFu; out[i].inst = 0xFFFFFFFFu; }
+    }
+}
+
+void orc_render(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t first_sample, uint32_t n_samples, uint32_t step,
+                float* accum, orc_counters* counters, int trace_mode) {
+    orc_counters local; memset(&local, 0, sizeof local);
+    Ctx c; c.S = s; c.cfg = *cfg; c.C = counters ? counters : &local; c.mode = trace_mode;
+    if (step == 0) step = 1;
+    for (uint32_t y = 0; y < cfg->height; y += step)
+        for (uint32_t x = 0; x < cfg->width; x += step) {
+            float* px = accum + 4 * ((size_t)y * cfg->width + x);
+            for (uint32_t k = 0; k < n_samples; k++) {
+                f3 C = RenderSample(c, *cam, x, y, first_sample + k, nullptr);
+                // Pass_spat_di_v7.hlsl:388-404: drop non-finite samples, sum += C, n += 1
+                if (!any_nan_inf(C)) { px[0] += C.x; px[1] += C.y; px[2] += C.z; px[3] += 1.0f; }
+            }
+        }
+}
+
+void orc_resolve(const float* accum, uint32_t n_pixels, uint8_t* rgba8) {
+    for (uint32_t i = 0; i < n_pixels; i++) {
+        const float* a = accum + 4 * (size_t)i;
+        float n = a[3];
+        float c[3] = {a[0] / n, a[1] / n, a[2] / n};          // :405 averagedColor = sum / frameCount
+        bool nan = isnan1(c[0]) || isnan1(c[1]) || isnan1(c[2]);
+        bool inf = isinf1(c[0]) || isinf1(c[1]) || isinf1(c[2]);
+        if (nan) { c[0] = 1; c[1] = 0; c[2] = 1; }             // :429-430
+        if (inf) { c[0] = 0; c[1] = 1; c[2] = 1; }             // :431-432
+        for (int k = 0; k < 3; k++) {
+            float v = srgb1(c[k]);                              // :440
+            v = saturate1(v);                                   // RGBA8_UNORM store clamps, then round-to-nearest
+            rgba8[4 * i + k] = (uint8_t)(int)(v * 255.0f + 0.5f);
+        }
+        rgba8[4 * i + 3] = 255;
+    }
+}
+
+void orc_kat_rng(uint32_t sx, uint32_t sy, uint32_t n, float* out, uint32_t* seed_out) {
+    uint32_t seed[2] = {sx, sy};
+    for (uint32_t i = 0; i < n; i++) out[i] = RandomFloat(seed);
+    seed_out[0] = seed[0]; seed_out[1] = seed[1];
+}
+void orc_kat_seed(uint32_t x, uint32_t y, uint32_t pass, uint32_t sample, uint32_t* seed_out) { init_seed(x, y, pass, sample, seed_out); }
+void orc_kat_sincos(const float* x, uint32_t n, float* s, float* c) { for (uint32_t i = 0; i < n; i++) d_sincos(x[i], &s[i], &c[i]); }
+void orc_kat_half(const float* x, uint32_t n, float* out) { for (uint32_t i = 0; i < n; i++) out[i] = q16(x[i]); }
+void orc_kat_pow(const float* x, float y, uint32_t n, float* out) { for (uint32_t i = 0; i < n; i++) out[i] = d_pow(x[i], y); }
+uint32_t orc_kat_map_pixel(uint32_t w, uint32_t h, uint32_t x, uint32_t y) { return MapPixelID(w, h, x, y); }
+
+void orc_kat_bsdf(const orc_scene* s, int op, uint32_t mat_id, const float* n, const float* in, const float* o, uint32_t* seed, float* out) {
+    orc_counters C; memset(&C, 0, sizeof C);
+    Ctx c; c.S = s; memset(&c.cfg, 0, sizeof c.cfg); c.C = &C; c.mode = 0;
+    MatOpt m = make_matopt(fetch_material(*s, mat_id), mat_id);
+    f3 N = mk3(n[0], n[1], n[2]), I = mk3(in[0], in[1], in[2]), O = mk3(o[0], o[1], o[2]);
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    switch (op) {
+        case 0: case 1: { f3 r = EvaluateBRDF(c, (uint32_t)op, m, N, I, O); out[0] = r.x; out[1] = r.y; out[2] = r.z; break; }
+        case 2: case 3: out[0] = BRDF_PDF((uint32_t)(op - 2), m, N, I, O); break;
+        case 4: CalculateStrategyProbabilities(c, m, O, N, out[0], out[1]); break;
+        case 5: case 6: { f3 r = SampleBRDF((uint32_t)(op - 5), m, O, N, seed); out[0] = r.x; out[1] = r.y; out[2] = r.z; break; }
+        case 7: { float p; out[0] = (float)SelectSamplingStrategy(c, m, O, N, seed, p); out[1] = p; break; }
+        default: break;
+    }
+}
+
+void orc_kat_camera_ray(const orc_config* cfg, const orc_camera* cam, uint32_t x, uint32_t y, float jx, float jy, float* o3d3) {
+    f3 o, d; CameraRay(*cfg, *cam, x, y, jx, jy, o, d);
+    o3d3[0] = o.x; o3d3[1] = o.y; o3d3[2] = o.z; o3d3[3] = d.x; o3d3[4] = d.y; o3d3[5] = d.z;
+}
+
+// out64 layout (floats; uints bit-cast): see tests/orc.py PIXEL_DEBUG_FIELDS
+void orc_debug_pixel(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t x, uint32_t y, uint32_t sample, float* out, int trace_mode) {
+    orc_counters C; memset(&C, 0, sizeof C);
+    Ctx c; c.S = s; c.cfg = *cfg; c.C = &C; c.mode = trace_mode;
+    PixelDebug d; memset(&d, 0, sizeof d);
+    d.hit_inst = d.hit_prim = 0xFFFFFFFFu;
+    f3 Cc = RenderSample(c, *cam, x, y, sample, &d);
+    auto put3 = [&](int i, f3 v) { out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; };
+    auto putu = [&](int i, uint32_t u) { memcpy(&out[i], &u, 4); };
+    memset(out, 0, 64 * sizeof(float));
+    put3(0, d.cam_o); put3(3, d.cam_d); putu(6, d.hit_inst); putu(7, d.hit_prim); out[8] = d.hit_t; putu(9, d.mID);
+    put3(10, d.x1); put3(13, d.n1);
+    put3(16, d.rdi.x2); out[19] = d.rdi.w_sum; put3(20, d.rdi.n2); out[23] = d.rdi.W; put3(24, d.rdi.L2);
+    put3(27, d.rgi.xn); out[30] = d.rgi.w_sum; put3(31, d.rgi.nn); out[34] = d.rgi.W; put3(35, d.rgi.E3);
+    out[38] = d.p_hat; put3(39, Cc); putu(42, d.seed_end[0]); putu(43, d.seed_end[1]); put3(44, d.acc_L);
+    putu(47, (uint32_t)C.closest_rays); putu(48, (uint32_t)C.shadow_rays);
+}
+
+}  // extern "C"

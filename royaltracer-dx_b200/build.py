@@ -1,0 +1,48 @@
+"""Build recipe: compiles the CUDA engine for sm_100a into librtx_b200.so (in-tree, next to this file) and the
+C++ host-side mirror of the reference's Renderer slices into librtx_host.so.  Run: python build.py [--force]."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB = os.path.join(HERE, "librtx_b200.so")
+HOSTLIB = os.path.join(HERE, "librtx_host.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",            # reproducible fp32: no implicit FMA contraction (see csrc/dmath.cuh)
+    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(d, exts):
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts))
+
+
+def build(force=False, verbose=False):
+    cu = _sources(CSRC, (".cu",))
+    deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(HERE, "..", "include", "rtx_b200.h")]
+    if force or _newer(LIB, deps):
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cu
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    hs = _sources(HOST, (".cpp",))
+    hdeps = _sources(HOST, (".cpp", ".h")) + [os.path.join(HERE, "..", "include", "rtx_b200.h")]
+    if hs and (force or _newer(HOSTLIB, hdeps)):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOSTLIB] + hs
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return LIB, HOSTLIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,449 @@
+// api.cu — the C ABI (include/rtx_b200.h): context, scene upload, acceleration-structure builds, render passes.
+// Plays the role of the DXR runtime + pipeline state behind rdn/Renderer.cpp's calls.
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "trace.h"
+#include "wavefront.h"
+
+namespace rtx {
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+}  // namespace rtx
+
+using namespace rtx;
+
+struct ModelRec {
+    uint8_t* d_verts = nullptr; uint32_t* d_idx = nullptr;
+    uint32_t n_verts = 0, n_tris = 0, mat_offset = 0;
+    Bvh8 bvh;
+};
+
+struct rtx_ctx {
+    rtx_config cfg;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    std::vector<ModelRec> models;
+    uint32_t* d_material_ids = nullptr; uint32_t n_material_ids = 0;
+    rtx_material* d_materials = nullptr; uint32_t n_materials = 0;
+    rtx_instance_desc* d_descs = nullptr; rtx_instance_props* d_props = nullptr; uint32_t n_instances = 0;
+    uint32_t* d_inst_model = nullptr;
+    float4* d_inst_recs = nullptr;
+    Bvh8 tlas;
+    BlasRef* d_blas = nullptr; BlasBounds* d_bounds = nullptr; ModelRef* d_model_refs = nullptr; uint32_t n_tables = 0;
+    rtx_light_triangle* d_lights = nullptr; uint32_t n_lights = 0;
+    rtx_camera_params cam; bool have_cam = false;
+    WaveBuffers wb; bool wb_ready = false;
+    float4* d_trace_o = nullptr; float4* d_trace_d = nullptr; float4* d_trace_ha = nullptr; uint32_t* d_trace_hi = nullptr;
+    rtx_hit* d_trace_out = nullptr; uint32_t trace_cap = 0;
+    TraceStats* d_stats = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool pass_timed = false;
+};
+
+static rtx_status fail(rtx_status code, const char* msg) { set_error(msg); return code; }
+
+extern "C" const char* rtx_last_error(void) { return g_err.c_str(); }
+
+extern "C" rtx_status rtx_create(const rtx_config* cfg, rtx_ctx** out) {
+    if (!cfg || !out) return fail(RTX_ERR_ARG, "rtx_create: null argument");
+    if (cfg->struct_size != sizeof(rtx_config)) return fail(RTX_ERR_ARG, "rtx_create: rtx_config.struct_size mismatch");
+    if (cfg->width == 0 || cfg->height == 0) return fail(RTX_ERR_ARG, "rtx_create: zero-sized image");
+    int ndev = 0;
+    RTX_CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(RTX_ERR_CUDA, "rtx_create: no such CUDA device (no CPU fallback exists)");
+    RTX_CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    RTX_CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(RTX_ERR_CUDA, "rtx_create: kernels are built for sm_100a only");
+    rtx_ctx* c = new rtx_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.samples_per_pass == 0) c->cfg.samples_per_pass = 1;
+    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else { RTX_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (int i = 0; i < 4; i++) RTX_CK(cudaEventCreate(&c->ev[i]));
+    RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
+    RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
+    memset(&c->cam, 0, sizeof c->cam);
+    *out = c;
+    return RTX_OK;
+}
+
+static void free_tables(rtx_ctx* c) {
+    if (c->d_blas) cudaFree(c->d_blas);
+    if (c->d_bounds) cudaFree(c->d_bounds);
+    if (c->d_model_refs) cudaFree(c->d_model_refs);
+    c->d_blas = nullptr; c->d_bounds = nullptr; c->d_model_refs = nullptr; c->n_tables = 0;
+}
+
+extern "C" void rtx_destroy(rtx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& m : c->models) { if (m.d_verts) cudaFree(m.d_verts); if (m.d_idx) cudaFree(m.d_idx); free_bvh(&m.bvh); }
+    void* ptrs[] = {c->d_material_ids, c->d_materials, c->d_descs, c->d_props, c->d_inst_model, c->d_inst_recs, c->d_lights,
+                    c->d_trace_o, c->d_trace_d, c->d_trace_ha, c->d_trace_hi, c->d_trace_out, c->d_stats};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    free_bvh(&c->tlas);
+    free_tables(c);
+    if (c->wb_ready) wave_free(&c->wb);
+    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+template <typename T>
+static rtx_status upload(T** dptr, const T* host, size_t n, cudaStream_t s) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    RTX_CK(cudaMalloc((void**)dptr, (n ? n : 1) * sizeof(T)));
+    if (n) RTX_CK(cudaMemcpyAsync(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    RTX_CK(cudaStreamSynchronize(s));
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_upload_model(rtx_ctx* c, const rtx_vertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni,
+                                       uint32_t material_id_offset, uint32_t* model_id_out) {
+    if (!c || (!v && nv) || (!idx && ni)) return fail(RTX_ERR_ARG, "rtx_upload_model: null argument");
+    if (ni % 3) return fail(RTX_ERR_ARG, "rtx_upload_model: index count is not a multiple of 3");
+    for (uint32_t i = 0; i < ni; i++) if (idx[i] >= nv) return fail(RTX_ERR_ARG, "rtx_upload_model: index out of range");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    ModelRec m;
+    m.n_verts = nv; m.n_tris = ni / 3; m.mat_offset = material_id_offset;
+    rtx_status st;
+    if ((st = upload((rtx_vertex**)&m.d_verts, v, nv, c->stream)) != RTX_OK) return st;
+    if ((st = upload(&m.d_idx, idx, ni, c->stream)) != RTX_OK) return st;
+    RTX_CK(build_blas(m.d_verts, nv, m.d_idx, m.n_tris, &m.bvh, c->stream));
+    c->launches += 8;
+    c->models.push_back(m);
+    free_tables(c);
+    if (model_id_out) *model_id_out = (uint32_t)c->models.size() - 1;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_blas_info_get(rtx_ctx* c, uint32_t model_id, rtx_blas_info* out) {
+    if (!c || !out || model_id >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_blas_info_get: bad argument");
+    const ModelRec& m = c->models[model_id];
+    out->n_nodes = m.bvh.n_nodes; out->n_tris = m.bvh.n_prims;
+    out->bytes = (uint64_t)m.bvh.n_nodes * 80 + (uint64_t)m.bvh.n_prims * 48;
+    out->sah_cost = 0.0f; out->build_ms = m.bvh.build_ms;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_set_material_ids(rtx_ctx* c, const uint32_t* ids, uint32_t n) {
+    if (!c || (!ids && n)) return fail(RTX_ERR_ARG, "rtx_set_material_ids: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    c->n_material_ids = n;
+    return upload(&c->d_material_ids, ids, n, c->stream);
+}
+
+extern "C" rtx_status rtx_set_materials(rtx_ctx* c, const rtx_material* m, uint32_t n) {
+    if (!c || (!m && n)) return fail(RTX_ERR_ARG, "rtx_set_materials: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    c->n_materials = n;
+    return upload(&c->d_materials, m, n, c->stream);
+}
+
+static rtx_status ensure_tables(rtx_ctx* c) {
+    if (c->d_blas && c->n_tables == c->models.size()) return RTX_OK;
+    free_tables(c);
+    const size_t n = c->models.size();
+    std::vector<BlasRef> br(n); std::vector<BlasBounds> bb(n); std::vector<ModelRef> mr(n);
+    for (size_t i = 0; i < n; i++) {
+        const ModelRec& m = c->models[i];
+        br[i].nodes = m.bvh.nodes; br[i].tris = m.bvh.prims;
+        for (int k = 0; k < 3; k++) { bb[i].lo[k] = m.bvh.lo[k]; bb[i].hi[k] = m.bvh.hi[k]; }
+        mr[i].verts = m.d_verts; mr[i].idx = m.d_idx; mr[i].mat_offset = m.mat_offset; mr[i].n_tris = m.n_tris;
+    }
+    rtx_status st;
+    if ((st = upload(&c->d_blas, br.data(), n, c->stream)) != RTX_OK) return st;
+    if ((st = upload(&c->d_bounds, bb.data(), n, c->stream)) != RTX_OK) return st;
+    if ((st = upload(&c->d_model_refs, mr.data(), n, c->stream)) != RTX_OK) return st;
+    c->n_tables = (uint32_t)n;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* descs, const rtx_instance_props* props, uint32_t n) {
+    if (!c || ((!descs || !props) && n)) return fail(RTX_ERR_ARG, "rtx_set_instances: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    std::vector<uint32_t> inst_model(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (descs[i].blas >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_set_instances: instance references an unknown model");
+        if (c->models[descs[i].blas].n_tris == 0) return fail(RTX_ERR_ARG, "rtx_set_instances: instance of an empty model");
+        inst_model[i] = (uint32_t)descs[i].blas;
+    }
+    rtx_status st;
+    if ((st = ensure_tables(c)) != RTX_OK) return st;
+    if ((st = upload(&c->d_descs, descs, n, c->stream)) != RTX_OK) return st;
+    if ((st = upload(&c->d_props, props, n, c->stream)) != RTX_OK) return st;
+    if ((st = upload(&c->d_inst_model, inst_model.data(), n, c->stream)) != RTX_OK) return st;
+    c->n_instances = n;
+    if (c->d_inst_recs) { cudaFree(c->d_inst_recs); c->d_inst_recs = nullptr; }
+    free_bvh(&c->tlas);
+    float4 *d_lo = nullptr, *d_hi = nullptr;
+    RTX_CK(cudaMalloc((void**)&c->d_inst_recs, (size_t)(n ? n : 1) * 64));
+    RTX_CK(cudaMalloc((void**)&d_lo, (size_t)(n ? n : 1) * 16));
+    RTX_CK(cudaMalloc((void**)&d_hi, (size_t)(n ? n : 1) * 16));
+    cudaError_t e = launch_instance_records(c->d_descs, c->d_props, c->d_bounds, n, c->d_inst_recs, d_lo, d_hi, c->stream);
+    if (e == cudaSuccess && n) e = build_tlas(c->d_inst_recs, d_lo, d_hi, n, &c->tlas, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_lo); cudaFree(d_hi);
+    c->launches += 6;
+    RTX_CK(e);
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_set_emissive_triangles(rtx_ctx* c, const rtx_light_triangle* l, uint32_t n) {
+    if (!c || (!l && n)) return fail(RTX_ERR_ARG, "rtx_set_emissive_triangles: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    c->n_lights = n;
+    if (n == 0) {   // an out-of-bounds read of t6 returns zeros: keep one zero record
+        rtx_light_triangle z; memset(&z, 0, sizeof z);
+        return upload(&c->d_lights, &z, 1, c->stream);
+    }
+    return upload(&c->d_lights, l, n, c->stream);
+}
+
+static rtx_status ensure_wave(rtx_ctx* c) {
+    if (c->wb_ready) return RTX_OK;
+    RTX_CK(wave_alloc(&c->wb, c->cfg.width, c->cfg.height, c->cfg.samples_per_pass));
+    c->wb_ready = true;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
+    if (!c || !cam) return fail(RTX_ERR_ARG, "rtx_set_camera: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    // Pass_spat_di_v7.hlsl:407-423: any element of view differing from the previous view by more than s_bias resets the accumulation
+    bool different = !c->have_cam;
+    if (c->have_cam)
+        for (int i = 0; i < 16; i++) if (fabsf(cam->view[i] - c->cam.view[i]) > RTX_S_BIAS) { different = true; break; }
+    c->cam = *cam; c->have_cam = true;
+    RTX_CK(cudaMemcpyAsync(c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, c->stream));
+    if (different) RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+
+static SceneAS make_as(rtx_ctx* c) {
+    SceneAS a;
+    a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
+    return a;
+}
+
+static rtx_status check_overflow(rtx_ctx* c) {
+    unsigned int flag = 0;
+    RTX_CK(read_stack_overflow(&flag, c->stream));
+    if (flag) return fail(RTX_ERR_STATE, "traversal stack overflow (BVH deeper than RTX_STACK_SIZE)");
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_t n_samples) {
+    if (!c) return fail(RTX_ERR_ARG, "rtx_render_pass: null context");
+    if (!c->have_cam) return fail(RTX_ERR_STATE, "rtx_render_pass: camera not set");
+    if (!c->n_instances || !c->tlas.nodes) return fail(RTX_ERR_STATE, "rtx_render_pass: no instances");
+    if (!c->d_materials || !c->d_material_ids) return fail(RTX_ERR_STATE, "rtx_render_pass: materials not set");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if (!c->d_lights && (st = rtx_set_emissive_triangles(c, nullptr, 0)) != RTX_OK) return st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    SceneData S;
+    S.models = c->d_model_refs; S.inst_model = c->d_inst_model; S.props = c->d_props;
+    S.material_ids = c->d_material_ids; S.n_material_ids = c->n_material_ids;
+    S.materials = c->d_materials; S.n_materials = c->n_materials;
+    S.lights = c->d_lights;
+    S.cfg_flags = c->cfg.flags; S.bounces = c->cfg.bounces; S.nee_samples = c->cfg.nee_samples; S.nee_samples_di = c->cfg.nee_samples_di;
+    S.width = c->cfg.width; S.height = c->cfg.height;
+    const SceneAS AS = make_as(c);
+    uint32_t done = 0;
+    while (done < n_samples) {
+        const uint32_t spp = std::min(c->cfg.samples_per_pass, n_samples - done);
+        PassTiming t;
+        RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, c->ev, &t));
+        done += spp;
+    }
+    c->pass_timed = true;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_reset_accum(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_synchronize(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    return check_overflow(c);
+}
+
+extern "C" rtx_status rtx_read_accum(rtx_ctx* c, float* host_out) {
+    if (!c || !host_out) return fail(RTX_ERR_ARG, "rtx_read_accum: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    RTX_CK(cudaMemcpyAsync(host_out, c->wb.accum, (size_t)c->cfg.width * c->cfg.height * 16, cudaMemcpyDeviceToHost, c->stream));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    return check_overflow(c);
+}
+
+extern "C" rtx_status rtx_read_output(rtx_ctx* c, uint8_t* rgba8_out) {
+    if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    const uint32_t npx = c->cfg.width * c->cfg.height;
+    RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
+    RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_accum_device_ptr(rtx_ctx* c, void** out) {
+    if (!c || !out) return fail(RTX_ERR_ARG, "rtx_accum_device_ptr: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    *out = c->wb.accum;
+    return RTX_OK;
+}
+
+// rays arrive as rtx_ray (o, tmin, d, tmax) = two float4 per ray, AoS; the kernels want two SoA planes.
+__global__ void k_split_rays(const float4* __restrict__ rays, uint32_t n, float4* __restrict__ o, float4* __restrict__ d) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    o[i] = rays[2 * i]; d[i] = rays[2 * i + 1];
+}
+__global__ void k_pack_hits(const float4* __restrict__ ha, const uint32_t* __restrict__ hi, uint32_t n, int any_hit, const float4* __restrict__ d,
+                            rtx_hit* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rtx_hit h;
+    if (any_hit) { h.t = 0.0f; h.u = 0.0f; h.v = 0.0f; h.prim = 0xFFFFFFFFu; h.inst = hi[i] == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u; }
+    else {
+        const float4 a = ha[i];
+        h.inst = hi[i];
+        if (h.inst == 0xFFFFFFFFu) { h.t = d[i].w; h.u = h.v = 0.0f; h.prim = 0xFFFFFFFFu; }
+        else { h.t = a.x; h.u = a.y; h.v = a.z; h.prim = __float_as_uint(a.w); }
+    }
+    out[i] = h;
+}
+
+static rtx_status ensure_trace_cap(rtx_ctx* c, uint32_t n) {
+    if (n <= c->trace_cap) return RTX_OK;
+    void* ptrs[] = {c->d_trace_o, c->d_trace_d, c->d_trace_ha, c->d_trace_hi};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    c->d_trace_o = c->d_trace_d = c->d_trace_ha = nullptr; c->d_trace_hi = nullptr; c->trace_cap = 0;
+    RTX_CK(cudaMalloc((void**)&c->d_trace_o, (size_t)n * 16));
+    RTX_CK(cudaMalloc((void**)&c->d_trace_d, (size_t)n * 16));
+    RTX_CK(cudaMalloc((void**)&c->d_trace_ha, (size_t)n * 16));
+    RTX_CK(cudaMalloc((void**)&c->d_trace_hi, (size_t)n * 4));
+    c->trace_cap = n;
+    return RTX_OK;
+}
+
+static rtx_status trace_device_impl(rtx_ctx* c, const void* d_rays, uint32_t n, void* d_hits, int any_hit, bool stats) {
+    if (!c || (!d_rays && n) || (!d_hits && n)) return fail(RTX_ERR_ARG, "rtx_trace: null argument");
+    if (!c->n_instances || !c->tlas.nodes) return fail(RTX_ERR_STATE, "rtx_trace: no instances");
+    if (n == 0) return RTX_OK;
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_trace_cap(c, n)) != RTX_OK) return st;
+    unsigned int* cursor = (unsigned int*)(c->d_stats) ;  // placeholder, replaced below
+    (void)cursor;
+    static_assert(sizeof(rtx_ray) == 32, "rtx_ray must be 32 bytes");
+    const unsigned grid = (n + 255) / 256;
+    k_split_rays<<<grid, 256, 0, c->stream>>>((const float4*)d_rays, n, c->d_trace_o, c->d_trace_d);
+    // the cursor lives right after the stats block
+    unsigned int* d_cursor = nullptr;
+    if (!c->wb_ready) { if ((st = ensure_wave(c)) != RTX_OK) return st; }
+    d_cursor = c->wb.cursor;
+    RTX_CK(launch_trace(make_as(c), c->d_trace_o, c->d_trace_d, nullptr, n, d_cursor, c->d_trace_ha, c->d_trace_hi, any_hit != 0,
+                        stats ? c->d_stats : nullptr, c->stream));
+    k_pack_hits<<<grid, 256, 0, c->stream>>>(c->d_trace_ha, c->d_trace_hi, n, any_hit, c->d_trace_d, (rtx_hit*)d_hits);
+    c->launches += 3;
+    RTX_CK(cudaGetLastError());
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_trace_device(rtx_ctx* c, const void* d_rays, uint32_t n, void* d_hits, int any_hit) {
+    return trace_device_impl(c, d_rays, n, d_hits, any_hit, false);
+}
+extern "C" rtx_status rtx_trace_stats(rtx_ctx* c, const void* d_rays, uint32_t n, void* d_hits, int any_hit) {
+    return trace_device_impl(c, d_rays, n, d_hits, any_hit, true);
+}
+
+extern "C" rtx_status rtx_trace(rtx_ctx* c, const rtx_ray* rays, uint32_t n, rtx_hit* out, int any_hit) {
+    if (!c || (!rays && n) || (!out && n)) return fail(RTX_ERR_ARG, "rtx_trace: null argument");
+    if (n == 0) return RTX_OK;
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    void* d_rays = nullptr; void* d_hits = nullptr;
+    RTX_CK(cudaMalloc(&d_rays, (size_t)n * sizeof(rtx_ray)));
+    RTX_CK(cudaMalloc(&d_hits, (size_t)n * sizeof(rtx_hit)));
+    RTX_CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(rtx_ray), cudaMemcpyHostToDevice, c->stream));
+    rtx_status st = trace_device_impl(c, d_rays, n, d_hits, any_hit, false);
+    if (st == RTX_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_hits, (size_t)n * sizeof(rtx_hit), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); st = RTX_ERR_CUDA; }
+    }
+    cudaFree(d_rays); cudaFree(d_hits);
+    if (st != RTX_OK) return st;
+    return check_overflow(c);
+}
+
+extern "C" rtx_status rtx_get_counters(rtx_ctx* c, rtx_counters* out) {
+    if (!c || !out) return fail(RTX_ERR_ARG, "rtx_get_counters: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    memset(out, 0, sizeof *out);
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    if (c->wb_ready) {
+        unsigned long long h[8];
+        RTX_CK(cudaMemcpy(h, c->wb.ray_counters, sizeof h, cudaMemcpyDeviceToHost));
+        out->closest_rays = h[0]; out->shadow_rays = h[1]; out->paths = h[2];
+    }
+    TraceStats ts;
+    RTX_CK(cudaMemcpy(&ts, c->d_stats, sizeof ts, cudaMemcpyDeviceToHost));
+    out->nodes_visited = ts.nodes; out->tris_tested = ts.tris; out->instances_entered = ts.insts;
+    out->kernel_launches = c->launches;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_reset_counters(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    if (c->wb_ready) RTX_CK(cudaMemset(c->wb.ray_counters, 0, 64));
+    RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
+    c->launches = 0;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_last_pass_ms(rtx_ctx* c, float* trace_ms, float* total_ms) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    if (!c->pass_timed) return fail(RTX_ERR_STATE, "rtx_last_pass_ms: no pass rendered yet");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_CK(cudaEventSynchronize(c->ev[1]));
+    float t = 0.0f;
+    RTX_CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[1]));
+    if (total_ms) *total_ms = t;
+    if (trace_ms) *trace_ms = 0.0f;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_debug_pixel(rtx_ctx* c, uint32_t x, uint32_t y, float* out64) {
+    if (!c || !out64 || !c->wb_ready) return fail(RTX_ERR_ARG, "rtx_debug_pixel: bad argument");
+    if (x >= c->cfg.width || y >= c->cfg.height) return fail(RTX_ERR_ARG, "rtx_debug_pixel: pixel out of range");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    SceneData S; memset(&S, 0, sizeof S); S.width = c->cfg.width; S.height = c->cfg.height;
+    RTX_CK(wave_debug_pixel(c->wb, S, x, y, c->stream, out64));
+    return RTX_OK;
+}

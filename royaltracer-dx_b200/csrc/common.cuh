@@ -1,0 +1,61 @@
+// common.cuh — shared declarations of the sm_100a engine (device structs, error handling).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/rtx_b200.h"
+
+namespace rtx {
+
+void set_error(const std::string& s);
+
+#define RTX_CK(call)                                                                           \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            char b__[512];                                                                     \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            rtx::set_error(b__);                                                               \
+            return RTX_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// shaders/Common_v7.hlsl:1-3, Miss_v7.hlsl:7
+#define RTX_PI_REF 3.1415f
+#define RTX_S_BIAS 0.00002f
+#define RTX_EPS 0.000001f
+#define RTX_MISS_ID 4294967294u
+
+// ---- acceleration structure (DESIGN.md §"Data layout in HBM") ------------------------------------
+// 80-B compressed 8-wide node, stored as 5 x uint4:
+//   n0 = (px, py, pz, ex | ey<<8 | ez<<16 | imask<<24)
+//   n1 = (child_base, prim_base, meta[0..3], meta[4..7])
+//   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
+//   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
+//   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
+// meta: 0 = empty; inner = 0b001_sssss with sssss = 24 + slot; leaf = unary(count 1..3) << 5 | offset in the
+// node's primitive range (< 24).
+// 48-B triangle = 3 x float4: (v0.xyz, bits(prim)), (v1.xyz, 0), (v2.xyz, 0).
+// 64-B instance record = 4 x float4: rows 0..2 of world->object (from objectToWorldInverse), (blas, instance, 0, 0).
+struct BlasRef {
+    const uint4* nodes;
+    const float4* tris;
+};
+
+struct SceneAS {
+    const uint4* tlas_nodes;
+    const float4* inst_recs;
+    const BlasRef* blas;
+    uint32_t n_instances;
+};
+
+// Ray queue entry layout (SoA): o_tmin[j] = (o.xyz, tmin), d_tmax[j] = (d.xyz, tmax).
+// Hit record (20 B/ray): hit_a[j] = (t, b1, b2, bits(prim)); hit_inst[j] = instance (0xFFFFFFFF = miss).
+
+struct TraceStats {
+    unsigned long long nodes, tris, insts;
+};
+
+}  // namespace rtx

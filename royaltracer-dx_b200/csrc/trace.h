@@ -1,0 +1,35 @@
+// trace.h — host-side entry points of the traversal kernels and the GPU BVH builder.
+#pragma once
+#include "common.cuh"
+
+namespace rtx {
+
+// Drains a ray queue (see common.cuh for the queue layout).  n is read from *n_ptr on the device when n_ptr is
+// non-null (wavefront queues), else n_fixed.  `cursor` is a device scratch word.
+cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
+                         unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
+                         cudaStream_t stream);
+cudaError_t read_stack_overflow(unsigned int* host_flag, cudaStream_t stream);
+
+struct Bvh8 {
+    uint4* nodes = nullptr;     // 5 x uint4 per node
+    float4* prims = nullptr;    // PRIM_F4 x float4 per primitive, in leaf order
+    uint32_t n_nodes = 0, n_prims = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // padded bounds of everything inside
+    float build_ms = 0.0f;
+};
+
+// BLAS over an indexed triangle list (vertex stride 28 B, position first).  Returns device allocations owned by the caller.
+cudaError_t build_blas(const uint8_t* d_vertices, uint32_t n_vertices, const uint32_t* d_indices, uint32_t n_tris,
+                       Bvh8* out, cudaStream_t stream);
+// TLAS over instance records (4 x float4 each, already in device memory) with world-space boxes lo/hi (float4 each).
+cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances,
+                       Bvh8* out, cudaStream_t stream);
+void free_bvh(Bvh8* b);
+
+// Fills instance records + world boxes from descs/props (device arrays) and per-model BLAS bounds.
+struct BlasBounds { float lo[3]; float hi[3]; };
+cudaError_t launch_instance_records(const rtx_instance_desc* d_descs, const rtx_instance_props* d_props, const BlasBounds* d_bounds,
+                                    uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, cudaStream_t stream);
+
+}  // namespace rtx

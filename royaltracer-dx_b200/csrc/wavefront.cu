@@ -1,0 +1,596 @@
+// wavefront.cu — the logic stages of the wavefront path tracer.
+//
+// The reference runs one megakernel raygen thread per pixel (shaders/Pass_init_di_v7.hlsl:48-190) that calls TraceRay
+// up to 5 + bounces times.  Here the same per-path program is cut at every TraceRay into stages; between stages
+// the rays sit in compacted queues that the persistent traversal kernels (trace.cu) drain:
+//
+//   generate -> [extend] -> shade_primary -> [extend] -> di_finish -> [connect DI] [extend] -> gi_step(0) ->
+//   ([extend] -> gi_step(i))* -> [connect GI] -> finalize -> accumulate
+//
+// Each path draws its random numbers in exactly the order of the reference's sequential program (the RNG state
+// travels in the path state), so the result is independent of queue order.  Path state is a structure of float4
+// arrays (wavefront.h); queue slots are claimed with one atomic per warp (ballot + popc compaction).
+#include "trace.h"
+#include "wavefront.h"
+
+namespace rtx {
+
+#define CKE(call)                            \
+    do {                                     \
+        cudaError_t e__ = (call);            \
+        if (e__ != cudaSuccess) return e__;  \
+    } while (0)
+
+#define WF_BLOCK 128
+
+struct StateView {
+    float4* base; uint32_t n;
+    __device__ __forceinline__ float4& at(int plane, uint32_t pid) const { return base[(size_t)plane * n + pid]; }
+};
+
+__device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+__device__ __forceinline__ float4 f4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ float4 f4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }
+
+// Warp-level queue compaction: one atomicAdd per warp claims a contiguous run of slots.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void push_ray(const RayQueue& q, bool emit, f3 o, float tmin, f3 d, float tmax, uint32_t pid) {
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (mask == 0u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(q.count, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+        const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
+        q.o_tmin[slot] = f4(o, tmin);
+        q.d_tmax[slot] = f4(d, tmax);
+        q.pid[slot] = pid;
+    }
+}
+
+// camera ray, shaders/Pass_init_di_v7.hlsl:59,80-95
+__device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t W, uint32_t H, uint32_t x, uint32_t y, float jx, float jy,
+                                          f3& o, f3& dir) {
+    float dimx = (float)W, dimy = (float)H;
+    o = mul43(cam->viewI, 0.0f, 0.0f, 0.0f, 1.0f);
+    float dx = (((float)x + jx) / dimx) * 2.0f - 1.0f;
+    float dy = (((float)y + jy) / dimy) * 2.0f - 1.0f;
+    f3 target = mul43(cam->projectionI, dx, -dy, 1.0f, 1.0f);
+    f3 d = mul43(cam->viewI, target.x, target.y, target.z, 0.0f);
+    dir = normalize3(d);
+}
+
+__global__ void __launch_bounds__(WF_BLOCK)
+k_generate(StateView st, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H, uint32_t first_sample,
+           uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi, unsigned long long* ray_counters) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { *q0.count = st.n; atomicAdd(&ray_counters[2], (unsigned long long)st.n); }
+    if (p >= st.n) return;
+    const uint32_t npx = W * H;
+    const uint32_t pixel = p % npx, s = p / npx;
+    const uint32_t x = pixel % W, y = pixel / W;
+    uint2 seed = init_seed(x, y, 1u, first_sample + s);
+    float jx = 0.0f, jy = 0.0f;
+    if (flags & RTX_FLAG_JITTER) { jx = RandomFloat(seed); jy = RandomFloat(seed); }
+    f3 o, dir;
+    CameraRay(cam, W, H, x, y, jx, jy, o, dir);
+    q0.o_tmin[p] = f4(o, 0.0001f);
+    q0.d_tmax[p] = f4(dir, 10000.0f);
+    q0.pid[p] = p;
+    st.at(SP_N1, p) = make_float4(0, 0, 0, __uint_as_float(seed.x));
+    st.at(SP_O, p) = f4u(-dir, seed.y);
+    st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
+    vis_di[p] = 1.0f; vis_gi[p] = 1.0f;
+}
+
+// shaders/Reservoir_v7.hlsl:57-80 / :30-53 on unpacked fields
+__device__ __forceinline__ bool UpdateReservoir(f3& rx, f3& rn, f3& rL, float& w_sum, float wi, f3 x2, f3 n2, f3 L2, uint2& seed) {
+    w_sum += wi;
+    if (RandomFloat(seed) < wi / w_sum) { rx = x2; rn = n2; rL = q16v(L2); return true; }
+    return false;
+}
+
+// SampleLightNEE with useVisibility=false, shaders/Sampler_v7.hlsl:273-396 (call site :677-693)
+__device__ __forceinline__ void SampleLightNEE(const SceneData& S, float& pdf_light, float& pdf_bsdf, float& p_hat, uint2& seed, f3 worldOrigin,
+                                               f3 normal, f3 outgoing, const MatOpt& material, f3& emission, f3& x2, f3& n2) {
+    LightSample ls;
+    SampleLightPoint(S, worldOrigin, seed, ls);
+    x2 = ls.point; n2 = ls.normal_l;
+    float cos_theta_x = dot3(normal, ls.L_norm);
+    float cos_theta_y = dot3(ls.normal_l, -ls.L_norm);
+    float G = fmaxf((cos_theta_y * cos_theta_x) / ls.dist2, RTX_EPS);
+    emission = ls.emission;
+    float p_d, p_s;
+    f3 on = normalize3(outgoing);
+    CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
+    f3 brdf_light = CombinedF(S, material, normal, -ls.L_norm, on, p_d, p_s);
+    float P = CombinedP_scaled(S, material, normal, -ls.L_norm, on, p_d, p_s, cos_theta_y, ls.dist2);
+    p_hat = length3((ls.emission * brdf_light) * G);
+    pdf_light = fmaxf(RTX_EPS, ls.pdf_l);
+    pdf_bsdf = P;
+}
+
+// ---- stage: primary hit -> RIS over NEE candidates -> BSDF candidate ray (Pass_init_di_v7.hlsl:99-159, Sampler_v7.hlsl:653-700)
+__global__ void __launch_bounds__(WF_BLOCK)
+k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
+                RayQueue qout, unsigned long long* ray_counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *qin.count;
+    if (j == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
+    bool emit = false; f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0); uint32_t pid = 0;
+    if (j < n) {
+        pid = qin.pid[j];
+        const uint32_t inst = hit_inst[j];
+        if (inst != 0xFFFFFFFFu) {                                  // miss: radiance 0 (DESIGN.md deviation D1)
+            const float4 ha = hit_a[j];
+            const f3 o = xyz(qin.o_tmin[j]), d = xyz(qin.d_tmax[j]);
+            HitInfo payload;
+            ClosestHit(S, o, d, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, payload);
+            f3 ke_full;
+            const MatOpt mat = load_matopt(S, payload.materialID, &ke_full);
+            if (length3(ke_full) > 0.0f) {                          // :103-106 ; L1 = half3(Ke) (deviation D5: accumulated)
+                st.at(SP_RESULT, pid) = f4(mat.Ke, 0.0f);
+            } else {
+                uint2 seed = make_uint2(__float_as_uint(st.at(SP_N1, pid).w), __float_as_uint(st.at(SP_O, pid).w));
+                const f3 outgoing = -d;
+                const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, payload.hitNormal, seed);
+                f3 rx = mk3(0, 0, 0), rn = mk3(0, 0, 0), rL = mk3(0, 0, 0); float w_sum = 0.0f;
+                const float fM1 = (float)S.nee_samples_di, fM2 = 1.0f;
+                for (uint32_t i = 0; i < S.nee_samples_di; i++) {
+                    float pdf_light = 0.0f, pdf_bsdf = 0.0f, p_hat = 0.0f; f3 emission, x2, n2;
+                    SampleLightNEE(S, pdf_light, pdf_bsdf, p_hat, seed, payload.hitPosition, payload.hitNormal, outgoing, mat, emission, x2, n2);
+                    float mi = pdf_light / (fM1 * pdf_light + fM2 * pdf_bsdf);
+                    float wi = (mi * p_hat) / pdf_light;
+                    if (p_hat > 0.0f) UpdateReservoir(rx, rn, rL, w_sum, wi, x2, n2, emission, seed);
+                }
+                const f3 sample = SampleBRDF(strategy, mat, outgoing, payload.hitNormal, seed);   // Sampler_v7.hlsl:218-220
+                emit = true; ro = payload.hitPosition; rd = sample;
+                st.at(SP_X1, pid) = f4u(payload.hitPosition, payload.materialID);
+                st.at(SP_N1, pid) = f4u(payload.hitNormal, seed.x);
+                st.at(SP_O, pid) = f4u(outgoing, seed.y);
+                st.at(SP_DI_X2, pid) = f4(rx, w_sum);
+                st.at(SP_DI_N2, pid) = f4(rn, 0.0f);
+                st.at(SP_DI_L2, pid) = f4(rL, 0.0f);
+                st.at(SP_RESULT, pid) = make_float4(0, 0, 0, 1.0f);
+            }
+        }
+    }
+    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+}
+
+// ---- stage: BSDF candidate of the DI reservoir, DI visibility ray, first indirect ray
+// (Sampler_v7.hlsl:231-270,729-735; Pass_init_di_v7.hlsl:161-167; Path_Sampler_v7.hlsl:13-52)
+__global__ void __launch_bounds__(WF_BLOCK)
+k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
+            RayQueue q_shadow, RayQueue qout, unsigned long long* ray_counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *qin.count;
+    if (j == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
+    bool emit = false, emit_sh = false; uint32_t pid = 0;
+    f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
+    if (j < n) {
+        pid = qin.pid[j];
+        const float4 a0 = st.at(SP_X1, pid), a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
+        const f3 x1 = xyz(a0), hitNormal = xyz(a1), o = xyz(a2);
+        const uint32_t mID = __float_as_uint(a0.w);
+        uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
+        const MatOpt mat = load_matopt(S, mID, nullptr);
+        float4 b0 = st.at(SP_DI_X2, pid);
+        f3 rx = xyz(b0), rn = xyz(st.at(SP_DI_N2, pid)), rL = xyz(st.at(SP_DI_L2, pid)); float w_sum = b0.w;
+        const f3 sample = xyz(qin.d_tmax[j]);
+        const uint32_t inst = hit_inst[j];
+        if (inst != 0xFFFFFFFFu) {                                  // miss => materials[MISS] reads 0 => p_hat = 0
+            const float4 ha = hit_a[j];
+            HitInfo sp;
+            ClosestHit(S, x1, sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
+            float4 kd, ks, ke, pr;
+            fetch_material_head(S, sp.materialID, kd, ks, ke, pr);
+            const float Ke = (ke.x + ke.y) + ke.z;
+            if (Ke > RTX_EPS) {
+                const f3 emission = mk3(ke.x, ke.y, ke.z);
+                f3 L = sp.hitPosition - x1;
+                float dist = length3(L);
+                float dist2 = dist * dist;
+                float cos_theta = dot3(sp.hitNormal, -sample);
+                float pdf_light = (Ke / 3.0f) / __ldg(&S.lights[0].total_weight);
+                float p_d, p_s;
+                f3 on = normalize3(o);
+                CalculateStrategyProbabilities(S, mat, on, hitNormal, p_d, p_s);
+                f3 brdf = CombinedF(S, mat, hitNormal, -sample, on, p_d, p_s);
+                float pdf_bsdf = CombinedP_scaled(S, mat, hitNormal, -sample, o, p_d, p_s, cos_theta, dist2);
+                float ndot = dot3(hitNormal, sample);
+                float p_hat = length3((((brdf * emission) * ndot) * cos_theta) / dist2);
+                float mi = pdf_bsdf / ((float)S.nee_samples_di * pdf_light + 1.0f * pdf_bsdf);
+                float wi = (mi * p_hat) / pdf_bsdf;
+                if (p_hat > 0.0f) UpdateReservoir(rx, rn, rL, w_sum, wi, sp.hitPosition, sp.hitNormal, emission, seed);
+            }
+        }
+        // GetP_Hat(..., true): Sampler_v7.hlsl:163-171
+        const f3 n1 = normalize3(hitNormal);
+        const f3 rdi = ReconnectDI(S, x1, n1, rx, rn, rL, o, mat);
+        const float f_g = length3(rdi);
+        if (f_g > RTX_EPS) {                                        // deviation D6; VisibilityCheck :86-104
+            const f3 d21 = rx - x1;
+            const float dist = length3(d21);
+            emit_sh = true;
+            so = x1 + normalize3(n1) * RTX_S_BIAS;
+            sd = normalize3(d21);
+            stmax = fmaxf(dist - 10.0f * RTX_S_BIAS, 2.0f * RTX_S_BIAS);
+        }
+        st.at(SP_DI_X2, pid) = f4(rx, w_sum);
+        st.at(SP_DI_N2, pid) = f4(rn, f_g);
+        st.at(SP_DI_L2, pid) = f4(rL, 0.0f);
+        st.at(SP_DI_R, pid) = f4(rdi, 0.0f);
+        // SamplePathSimple step 1: Path_Sampler_v7.hlsl:24-52
+        const f3 outgoing = normalize3(o);
+        const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, hitNormal, seed);
+        const f3 s2 = SampleBRDF(strategy, mat, outgoing, hitNormal, seed);
+        emit = true; ro = x1; rd = s2;
+        st.at(SP_N1, pid) = f4u(hitNormal, seed.x);
+        st.at(SP_O, pid) = f4u(o, seed.y);
+        st.at(SP_GI_XN, pid) = make_float4(0, 0, 0, 0);
+        st.at(SP_GI_NN, pid) = make_float4(0, 0, 0, 1.0f);
+        st.at(SP_GI_E3, pid) = make_float4(0, 0, 0, 0);
+        st.at(SP_ORIGIN, pid) = f4u(x1, mID);
+        st.at(SP_NORMAL, pid) = f4(hitNormal, 0.0f);
+        st.at(SP_OUTGOING, pid) = f4(outgoing, 0.0f);
+        st.at(SP_ACC_F, pid) = make_float4(1, 1, 1, 0);
+        st.at(SP_ACC_FR, pid) = make_float4(1, 1, 1, 0);
+        st.at(SP_SH1, pid) = make_float4(0, 0, 0, 0);
+        st.at(SP_SH2, pid) = make_float4(0, 0, 0, 0);
+    }
+    push_ray(q_shadow, emit_sh, so, 0.0f, sd, stmax, pid);
+    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+}
+
+// SampleLightNEE_GI with useVisibility=false, Sampler_v7.hlsl:508-647 (call site Path_Sampler_v7.hlsl:133-151)
+__device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_light, float& pdf_bsdf, f3& x2_pos, uint2& seed, f3 origin, f3 normal,
+                                                f3 outgoing, f3 acc_l, float acc_pdf, f3& throughput, f3& emission, const MatOpt& material) {
+    LightSample ls;
+    SampleLightPoint(S, origin, seed, ls);
+    x2_pos = ls.point;
+    float cos_theta_x = fabsf(dot3(normal, ls.L_norm));
+    if (cos_theta_x < RTX_EPS) cos_theta_x = 0.0f;
+    float cos_theta_y = fabsf(dot3(ls.normal_l, -ls.L_norm));
+    if (cos_theta_y < RTX_EPS) cos_theta_y = 0.0f;
+    float G = cos_theta_x;
+    float p_d, p_s;
+    f3 on = normalize3(outgoing);
+    CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
+    f3 brdf_light = CombinedF(S, material, normal, -ls.L_norm, on, p_d, p_s);
+    float P = CombinedP(S, material, normal, -ls.L_norm, on, p_d, p_s);
+    if (cos_theta_y > 0.0f) pdf_light = (fmaxf(RTX_EPS, ls.pdf_l) * ls.dist2) / cos_theta_y;
+    pdf_bsdf = P;
+    acc_pdf *= pdf_light;
+    acc_l = acc_l * (brdf_light * G);
+    throughput = brdf_light * G;
+    emission = ls.emission;
+    if (acc_pdf > 0.0f) return (ls.emission * acc_l) / acc_pdf;
+    return mk3(0, 0, 0);
+}
+
+// ---- stage: one step of the indirect path (Path_Sampler_v7.hlsl:54-269 + Sampler_v7.hlsl:436-504).
+// iter == 0 consumes the hit of the initial indirect ray; iter >= 1 consumes the BSDF ray of loop iteration iter-1.
+// If the path goes on and iter < bounces it runs iteration `iter`'s NEE candidates and emits its BSDF ray.
+__global__ void __launch_bounds__(WF_BLOCK)
+k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
+          RayQueue q_shadow, RayQueue qout, uint32_t iter, unsigned long long* ray_counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *qin.count;
+    if (j == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
+    bool emit = false, emit_sh = false; uint32_t pid = 0;
+    f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
+    if (j < n) {
+        pid = qin.pid[j];
+        const float4 d0 = st.at(SP_ORIGIN, pid);
+        f3 origin = xyz(d0), normal = xyz(st.at(SP_NORMAL, pid)), outgoing = xyz(st.at(SP_OUTGOING, pid));
+        f3 acc_f = xyz(st.at(SP_ACC_F, pid)), acc_fr = xyz(st.at(SP_ACC_FR, pid));
+        float4 c0 = st.at(SP_GI_XN, pid), c1 = st.at(SP_GI_NN, pid);
+        f3 xn = xyz(c0), nn = xyz(c1), E3 = xyz(st.at(SP_GI_E3, pid));
+        float w_sum = c0.w, acc_pdf = c1.w;
+        f3 x1s = xyz(st.at(SP_SH1, pid)), x2s = xyz(st.at(SP_SH2, pid));
+        float4 a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
+        uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
+        MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
+        const f3 sample = xyz(qin.d_tmax[j]);
+        const uint32_t inst = hit_inst[j];
+        const float fnee = (float)S.nee_samples;
+        bool cont = false;
+        if (inst != 0xFFFFFFFFu) {                                  // miss: path ends (deviation D1)
+            const float4 ha = hit_a[j];
+            HitInfo sp;
+            ClosestHit(S, origin, sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
+            f3 ke_full;
+            const MatOpt hm = load_matopt(S, sp.materialID, &ke_full);
+            if (iter == 0u) {
+                if (!(length3(ke_full) > 0.0f)) {                   // Path_Sampler_v7.hlsl:55-98
+                    const f3 incoming = normalize3(-sample);
+                    float p_d, p_s;
+                    CalculateStrategyProbabilities(S, material, outgoing, normal, p_d, p_s);
+                    const f3 F = CombinedF(S, material, normal, incoming, outgoing, p_d, p_s);
+                    const float P = CombinedP(S, material, normal, incoming, outgoing, p_d, p_s);
+                    const float NdotL = dot3(normal, sample);
+                    acc_pdf *= P;
+                    acc_f = acc_f * (F * NdotL);
+                    outgoing = incoming; material = hm; normal = sp.hitNormal; origin = sp.hitPosition;
+                    xn = origin; nn = normalize3(normal);           // :104-106
+                    cont = true;
+                }
+            } else {                                                // Sampler_v7.hlsl:436-504
+                float p_d, p_s;
+                const f3 on = normalize3(outgoing);
+                CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
+                const f3 brdf = CombinedF(S, material, normal, -sample, on, p_d, p_s);
+                const float pdf_bsdf = CombinedP(S, material, normal, -sample, outgoing, p_d, p_s);
+                const float NdotL = dot3(normal, sample);
+                const bool emitter = (hm.Ke.x != 0.0f || hm.Ke.y != 0.0f || hm.Ke.z != 0.0f);
+                acc_pdf *= pdf_bsdf;
+                acc_f = acc_f * (brdf * NdotL);
+                const f3 throughput = brdf * NdotL;
+                f3 contribution = mk3(0, 0, 0), emission = mk3(0, 0, 0);
+                float pdf_light = 1.0f;
+                if (emitter) {
+                    f3 L = sp.hitPosition - origin;
+                    float dist = length3(L);
+                    float dist2 = dist * dist;
+                    float cos_theta = dot3(sp.hitNormal, -sample);
+                    float kesum = hadd(hadd(hm.Ke.x, hm.Ke.y), hm.Ke.z);
+                    pdf_light = (((kesum / 3.0f) / __ldg(&S.lights[0].total_weight)) * dist2) / cos_theta;
+                    emission = hm.Ke;
+                    contribution = (hm.Ke * acc_f) / acc_pdf;
+                }
+                acc_fr = acc_fr * throughput;                       // Path_Sampler_v7.hlsl:232
+                if (length3(contribution) > 0.0f) {                 // :235-261
+                    float mi = pdf_bsdf / (fnee * pdf_light + pdf_bsdf);
+                    f3 E_reconnection = (acc_fr * mi) * emission;
+                    f3 E_path = mi * contribution;
+                    float wi = length3(E_path);
+                    if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
+                    w_sum += wi;
+                    if (RandomFloat(seed) < wi / w_sum) { E3 = q16v(E_reconnection); }   // UpdateReservoir_GI; (xn, nn) are the path's
+                } else if (!emitter) {
+                    origin = sp.hitPosition; material = hm; outgoing = -sample; normal = sp.hitNormal;
+                    cont = true;
+                }                                                   // emitter with zero contribution: ends (deviation D4)
+            }
+        }
+        if (cont && iter < S.bounces) {                             // Path_Sampler_v7.hlsl:114-225 (iteration `iter`)
+            uint32_t strategy = SelectSamplingStrategy(S, material, outgoing, normal, seed);
+            for (uint32_t k = 0; k < S.nee_samples; k++) {
+                float pdf_light = 1.0f, pdf_bsdf = 1.0f;
+                f3 throughput_NEE = mk3(1, 1, 1), emission_NEE = mk3(0, 0, 0), x2;
+                f3 contribution = SampleLightNEE_GI(S, pdf_light, pdf_bsdf, x2, seed, origin, normal, outgoing, acc_f, acc_pdf,
+                                                    throughput_NEE, emission_NEE, material);
+                float mi = pdf_light / (fnee * pdf_light + pdf_bsdf);
+                f3 E_reconnection = ((acc_fr * mi) * emission_NEE) * throughput_NEE;
+                f3 E_path = mi * contribution;
+                float wi = length3(E_path);
+                if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
+                w_sum += wi;
+                if (RandomFloat(seed) < wi / w_sum) {
+                    E3 = q16v(E_reconnection);
+                    x1s = origin + RTX_S_BIAS * normalize3(normal);
+                    x2s = x2;
+                }
+            }
+            strategy = SelectSamplingStrategy(S, material, outgoing, normal, seed);
+            const f3 s2 = SampleBRDF(strategy, material, outgoing, normal, seed);
+            emit = true; ro = origin; rd = s2;
+        } else {
+            // the path's sampling is over: one shadow ray for the reservoir winner (Path_Sampler_v7.hlsl:271-283)
+            const f3 ds = x2s - x1s;
+            const float len = length3(ds);
+            if (S.nee_samples > 0u && len > RTX_EPS) {
+                emit_sh = true; so = x1s; sd = normalize3(ds);
+                stmax = fmaxf(RTX_S_BIAS, len - (RTX_S_BIAS * 5.0f));
+            }
+        }
+        st.at(SP_ORIGIN, pid) = f4u(origin, material.mID);
+        st.at(SP_NORMAL, pid) = f4(normal, 0.0f);
+        st.at(SP_OUTGOING, pid) = f4(outgoing, 0.0f);
+        st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
+        st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
+        st.at(SP_GI_XN, pid) = f4(xn, w_sum);
+        st.at(SP_GI_NN, pid) = f4(nn, acc_pdf);
+        st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
+        st.at(SP_SH1, pid) = f4(x1s, 0.0f);
+        st.at(SP_SH2, pid) = f4(x2s, 0.0f);
+        st.at(SP_N1, pid) = make_float4(a1.x, a1.y, a1.z, __uint_as_float(seed.x));
+        st.at(SP_O, pid) = make_float4(a2.x, a2.y, a2.z, __uint_as_float(seed.y));
+    }
+    push_ray(q_shadow, emit_sh, so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
+    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+}
+
+// ---- stage: estimator E0 (Pass_init_di_v7.hlsl:166-181 + Pass_spat_di_v7.hlsl:334-372 with no accepted neighbours)
+__global__ void __launch_bounds__(WF_BLOCK)
+k_finalize(StateView st, SceneData S, const float* __restrict__ vis_di, const float* __restrict__ vis_gi,
+           const uint32_t* __restrict__ shadow_counts, unsigned long long* ray_counters) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
+    if (p >= st.n) return;
+    const float4 res = st.at(SP_RESULT, p);
+    if (res.w == 0.0f) return;
+    const float4 a0 = st.at(SP_X1, p);
+    const f3 x1 = xyz(a0), hitNormal = xyz(st.at(SP_N1, p)), o = xyz(st.at(SP_O, p));
+    const MatOpt mat = load_matopt(S, __float_as_uint(a0.w), nullptr);
+    const f3 n1 = normalize3(hitNormal);
+    const f3 rdi = xyz(st.at(SP_DI_R, p));
+    const float f_g = st.at(SP_DI_N2, p).w, w_sum = st.at(SP_DI_X2, p).w;
+    const float p_hat = f_g * vis_di[p];
+    const float W = (p_hat > RTX_EPS) ? w_sum / p_hat : 0.0f;
+    const f3 Cdi = rdi * W;
+    const float4 c0 = st.at(SP_GI_XN, p);
+    const float w_sum_gi = c0.w * vis_gi[p];
+    const f3 f_gi = ReconnectGI(S, x1, n1, xyz(c0), xyz(st.at(SP_GI_E3, p)), o, mat);
+    const float p_hat_gi = length3(f_gi);
+    const float W_GI = (p_hat_gi > RTX_EPS) ? w_sum_gi / p_hat_gi : 0.0f;
+    const f3 C = Cdi + f_gi * W_GI;
+    st.at(SP_RESULT, p) = f4(C, 2.0f);
+    st.at(SP_GI_XN, p) = make_float4(c0.x, c0.y, c0.z, w_sum_gi);
+    st.at(SP_DI_R, p) = f4(rdi, W);
+    st.at(SP_GI_E3, p).w = W_GI;
+    st.at(SP_DI_L2, p).w = p_hat;
+}
+
+// ---- F20 accumulation, Pass_spat_di_v7.hlsl:383-404: drop non-finite samples, sum += C, n += 1 (samples in index order)
+__global__ void __launch_bounds__(WF_BLOCK)
+k_accumulate(StateView st, uint32_t npx, uint32_t spp, float4* __restrict__ accum) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    float4 a = accum[px];
+    for (uint32_t s = 0; s < spp; s++) {
+        const float4 c = st.at(SP_RESULT, s * npx + px);
+        if (!any_nan_inf(mk3(c.x, c.y, c.z))) { a.x += c.x; a.y += c.y; a.z += c.z; a.w += 1.0f; }
+    }
+    accum[px] = a;
+}
+
+// sRGBGammaCorrection, shaders/Common_v7.hlsl:353-376; output write Pass_spat_di_v7.hlsl:405,428-441
+__device__ __forceinline__ float srgb1(float c) {
+    if (c <= 0.0031308f) return 12.92f * c;
+    return 1.055f * d_pow(c, 1.0f / 2.4f) - 0.055f;
+}
+__global__ void k_resolve(const float4* __restrict__ accum, uint32_t npx, uchar4* __restrict__ out) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const float4 a = accum[px];
+    float c[3] = {a.x / a.w, a.y / a.w, a.z / a.w};
+    const bool nan = isnan1(c[0]) || isnan1(c[1]) || isnan1(c[2]);
+    const bool inf = isinf1(c[0]) || isinf1(c[1]) || isinf1(c[2]);
+    if (nan) { c[0] = 1; c[1] = 0; c[2] = 1; }
+    if (inf) { c[0] = 0; c[1] = 1; c[2] = 1; }
+    unsigned char o[3];
+    for (int k = 0; k < 3; k++) o[k] = (unsigned char)(int)(saturate1(srgb1(c[k])) * 255.0f + 0.5f);
+    out[px] = make_uchar4(o[0], o[1], o[2], 255);
+}
+
+__global__ void k_debug_pixel(StateView st, uint32_t p, const float* vis_di, const float* vis_gi, float* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int i = 0; i < 64; i++) out[i] = 0.0f;
+    auto put3 = [&](int i, float4 v) { out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; };
+    const float4 a0 = st.at(SP_X1, p), a1 = st.at(SP_N1, p), a2 = st.at(SP_O, p);
+    out[9] = a0.w; put3(10, a0); put3(13, a1);
+    const float4 b0 = st.at(SP_DI_X2, p), b1 = st.at(SP_DI_N2, p), b2 = st.at(SP_DI_L2, p), b3 = st.at(SP_DI_R, p);
+    put3(16, b0); out[19] = b0.w; put3(20, b1); out[23] = b3.w; put3(24, b2);
+    const float4 c0 = st.at(SP_GI_XN, p), c1 = st.at(SP_GI_NN, p), c2 = st.at(SP_GI_E3, p);
+    put3(27, c0); out[30] = c0.w; put3(31, c1); out[34] = c2.w; put3(35, c2);
+    out[38] = b2.w;
+    put3(39, st.at(SP_RESULT, p));
+    out[42] = a1.w; out[43] = a2.w;
+    out[49] = st.at(SP_RESULT, p).w; out[50] = vis_di[p]; out[51] = vis_gi[p]; out[52] = b1.w;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static cudaError_t alloc_queue(RayQueue* q, uint32_t n) {
+    CKE(cudaMalloc((void**)&q->o_tmin, (size_t)n * 16));
+    CKE(cudaMalloc((void**)&q->d_tmax, (size_t)n * 16));
+    CKE(cudaMalloc((void**)&q->pid, (size_t)n * 4));
+    q->count = nullptr;
+    return cudaSuccess;
+}
+static void free_queue(RayQueue* q) {
+    if (q->o_tmin) cudaFree(q->o_tmin);
+    if (q->d_tmax) cudaFree(q->d_tmax);
+    if (q->pid) cudaFree(q->pid);
+    q->o_tmin = q->d_tmax = nullptr; q->pid = nullptr;
+}
+
+cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp) {
+    const uint32_t npx = width * height;
+    const uint32_t n = npx * spp;
+    B->n_paths = n;
+    memset(B->q, 0, sizeof B->q); memset(B->sq, 0, sizeof B->sq);
+    CKE(cudaMalloc((void**)&B->state, (size_t)NSTATE * n * 16));
+    for (int i = 0; i < 2; i++) { CKE(alloc_queue(&B->q[i], n)); CKE(alloc_queue(&B->sq[i], n)); }
+    CKE(cudaMalloc((void**)&B->hit_a, (size_t)n * 16));
+    CKE(cudaMalloc((void**)&B->hit_inst, (size_t)n * 4));
+    CKE(cudaMalloc((void**)&B->vis_di, (size_t)n * 4));
+    CKE(cudaMalloc((void**)&B->vis_gi, (size_t)n * 4));
+    CKE(cudaMalloc((void**)&B->counts, 128 * 4));
+    CKE(cudaMalloc((void**)&B->cursor, 16));
+    CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
+    CKE(cudaMemset(B->ray_counters, 0, 64));
+    CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
+    CKE(cudaMemset(B->accum, 0, (size_t)npx * 16));
+    CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
+    CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
+    CKE(cudaMalloc((void**)&B->debug, 64 * 4));
+    return cudaSuccess;
+}
+
+void wave_free(WaveBuffers* B) {
+    if (B->state) cudaFree(B->state);
+    for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
+    void* ptrs[] = {B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    *B = WaveBuffers();
+}
+
+// any-hit trace whose result is scattered to a per-path visibility array
+__global__ void __launch_bounds__(WF_BLOCK)
+k_scatter_vis(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ pid, const uint32_t* __restrict__ hit_inst, float* __restrict__ vis) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *n_ptr) return;
+    if (hit_inst[j] != 0xFFFFFFFFu) vis[pid[j]] = 0.0f;
+}
+
+cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
+                             uint64_t* launches, cudaEvent_t* ev, PassTiming* timing) {
+    const uint32_t npx = S.width * S.height;
+    const uint32_t n = npx * spp;
+    if (n > B.n_paths) return cudaErrorInvalidValue;
+    StateView st{B.state, n};
+    const unsigned grid = (n + WF_BLOCK - 1) / WF_BLOCK;
+    uint64_t L = 0;
+    CKE(cudaMemsetAsync(B.counts, 0, 128 * 4, stream));
+    // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
+    RayQueue q0 = B.q[0], q1 = B.q[1], sdi = B.sq[0], sgi = B.sq[1];
+    q0.count = B.counts + 0; q1.count = B.counts + 1; sdi.count = B.counts + 2; sgi.count = B.counts + 3;
+    CKE(cudaEventRecord(ev[0], stream));
+    k_generate<<<grid, WF_BLOCK, 0, stream>>>(st, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi, B.ray_counters); L++;
+    CKE(launch_trace(AS, q0.o_tmin, q0.d_tmax, q0.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    k_shade_primary<<<grid, WF_BLOCK, 0, stream>>>(st, S, q0, B.hit_a, B.hit_inst, q1, B.ray_counters); L++;
+    CKE(launch_trace(AS, q1.o_tmin, q1.d_tmax, q1.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    RayQueue qa = B.q[0]; qa.count = B.counts + 4;
+    k_di_finish<<<grid, WF_BLOCK, 0, stream>>>(st, S, q1, B.hit_a, B.hit_inst, sdi, qa, B.ray_counters); L++;
+    // DI visibility (connect): result scattered into vis_di.  hit_inst is reused afterwards by the closest trace.
+    CKE(launch_trace(AS, sdi.o_tmin, sdi.d_tmax, sdi.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
+    k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(sdi.count, sdi.pid, B.hit_inst, B.vis_di); L++;
+    CKE(launch_trace(AS, qa.o_tmin, qa.d_tmax, qa.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    int cur = 0;
+    RayQueue qin = qa;
+    for (uint32_t iter = 0; iter <= S.bounces; iter++) {
+        RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
+        k_gi_step<<<grid, WF_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters); L++;
+        if (iter < S.bounces) {
+            CKE(launch_trace(AS, qout.o_tmin, qout.d_tmax, qout.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+            qin = qout; cur ^= 1;
+        }
+    }
+    CKE(launch_trace(AS, sgi.o_tmin, sgi.d_tmax, sgi.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
+    k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(sgi.count, sgi.pid, B.hit_inst, B.vis_gi); L++;
+    k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters); L++;
+    k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum); L++;
+    CKE(cudaEventRecord(ev[1], stream));
+    CKE(cudaGetLastError());
+    if (launches) *launches += L;
+    (void)timing;
+    return cudaSuccess;
+}
+
+cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream, uint64_t* launches) {
+    k_resolve<<<(n_pixels + 255) / 256, 256, 0, stream>>>(B.accum, n_pixels, (uchar4*)B.output);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uint32_t y, cudaStream_t stream, float* host_out64) {
+    StateView st{B.state, B.n_paths};
+    k_debug_pixel<<<1, 32, 0, stream>>>(st, y * S.width + x, B.vis_di, B.vis_gi, B.debug);
+    CKE(cudaMemcpyAsync(host_out64, B.debug, 64 * 4, cudaMemcpyDeviceToHost, stream));
+    return cudaStreamSynchronize(stream);
+}
+
+}  // namespace rtx

@@ -1,0 +1,62 @@
+// wavefront.h — host interface of the wavefront stages (generate / shade / connect / accumulate).
+#pragma once
+#include "common.cuh"
+#include "shade.cuh"
+
+namespace rtx {
+
+// Structure-of-arrays path state: NSTATE float4 planes of n_paths entries each (DESIGN.md §"Data layout in HBM").
+enum StatePlane {
+    SP_X1 = 0,      // x1.xyz (payload.hitPosition), bits(mID)
+    SP_N1,          // payload.hitNormal.xyz, bits(seed.x)
+    SP_O,           // o = -direction, bits(seed.y)
+    SP_DI_X2,       // reservoir.x2, w_sum
+    SP_DI_N2,       // reservoir.n2, f_g
+    SP_DI_L2,       // reservoir.L2 (binary16 values), -
+    SP_DI_R,        // ReconnectDI(x1,n1,x2,n2,L2,o) vector, -
+    SP_GI_XN,       // reservoir_GI.xn, w_sum
+    SP_GI_NN,       // reservoir_GI.nn, acc_pdf
+    SP_GI_E3,       // reservoir_GI.E3 (binary16 values), -
+    SP_ORIGIN,      // path origin, bits(current material id)
+    SP_NORMAL,      // path normal
+    SP_OUTGOING,    // path outgoing
+    SP_ACC_F,       // acc_f
+    SP_ACC_FR,      // acc_f_reconnection
+    SP_SH1,         // x1_shadow, flag (1 = a reservoir winner exists)
+    SP_SH2,         // x2_shadow
+    SP_RESULT,      // per-sample radiance C, flag (1 = sampling path: finalize computes C)
+    NSTATE
+};
+
+struct RayQueue {
+    float4* o_tmin; float4* d_tmax; uint32_t* pid; uint32_t* count;   // count lives on the device
+};
+
+struct WaveBuffers {
+    uint32_t n_paths = 0;
+    float4* state = nullptr;           // NSTATE * n_paths
+    RayQueue q[2];                     // closest-hit ray queues (ping-pong)
+    RayQueue sq[2];                    // shadow queues: [0] DI visibility, [1] GI reservoir winner
+    float4* hit_a = nullptr; uint32_t* hit_inst = nullptr;    // hit records of the queue just traced
+    float* vis_di = nullptr; float* vis_gi = nullptr;         // per path, 1 = visible
+    uint32_t* counts = nullptr;        // 4 queue counters + scratch
+    unsigned int* cursor = nullptr;
+    unsigned long long* ray_counters = nullptr;   // [0] closest, [1] shadow, [2] paths
+    float4* accum = nullptr;           // gPermanentData
+    uint8_t* output = nullptr;         // gOutput slice 0
+    rtx_camera_params* cam = nullptr;  // b0 (device copy)
+    float* debug = nullptr;            // 64 floats
+};
+
+cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp);
+void wave_free(WaveBuffers* B);
+
+struct PassTiming { float trace_ms, total_ms; };
+
+// One DispatchRays-equivalent: samples [first_sample, first_sample + spp) of every pixel.
+cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
+                             cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev /*4 events*/, PassTiming* timing);
+cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream, uint64_t* launches);
+cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uint32_t y, cudaStream_t stream, float* host_out64);
+
+}  // namespace rtx
