@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     hs = _sources(HOST, (".cpp",))
     hdeps = _sources(HOST, (".cpp", ".h")) + [os.path.join(HERE, "..", "include", "rtx_b200.h")]
     if hs and (force or _newer(HOSTLIB, hdeps)):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOSTLIB] + hs
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOSTLIB] + hs + [
+            "-L" + HERE, "-lrtx_b200", "-Wl,-rpath,$ORIGIN"]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     return LIB, HOSTLIB

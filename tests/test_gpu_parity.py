@@ -1,0 +1,149 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): hit instance/primitive IDs bit-exact; here t,u,v and the accumulated radiance are
+bit-exact as well (tolerance 0) because both sides fix the fp32 operation order (oracle/det_math.h, csrc/dmath.cuh)."""
+import numpy as np
+import pytest
+
+from util import bits, compare_hits, host_inputs, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(rtdx, scene, W, H, **kw):
+    ctx = rtdx.Context(W, H, **kw)
+    up = ctx.upload_scene(scene)
+    return ctx, up
+
+
+def _oracle(orc, scene, up):
+    return orc.OracleScene(scene, up["props"], up["lights"])
+
+
+def _assert_hits_equal(gpu, ref):
+    r = compare_hits(gpu, ref)
+    assert r["inst"] == 0 and r["prim"] == 0 and r["t"] == 0 and r["u"] == 0 and r["v"] == 0, r
+
+
+def test_trace_cornell_camera_and_random(rtdx, orc):
+    sc = rtdx.scenes.cornell()
+    ctx, up = _upload(rtdx, sc, 256, 256)
+    osc = _oracle(orc, sc, up)
+    rays = rtdx.scenes.camera_rays(up["camera"], 256, 256)
+    _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
+    rng = np.random.RandomState(7)
+    rays = random_rays(rtdx, rng, 200000, (-1, 0, -1), (1, 2, 1))
+    ref = osc.trace(rays, mode=0)
+    _assert_hits_equal(ctx.trace(rays), ref)
+    # any-hit agrees with "closest exists"
+    ah = ctx.trace(rays, any_hit=True)
+    assert np.array_equal(ah["inst"] != rtdx.MISS, ref["inst"] != rtdx.MISS)
+    ctx.close()
+
+
+def test_trace_edge_cases(rtdx, orc):
+    sc = rtdx.scenes.cornell()
+    ctx, up = _upload(rtdx, sc, 64, 64)
+    osc = _oracle(orc, sc, up)
+    assert ctx.trace(np.zeros(0, dtype=rtdx.ray_dt)).size == 0            # empty batch
+    rays = np.zeros(6, dtype=rtdx.ray_dt)
+    rays["origin"] = (0, 1, 0)
+    rays["direction"] = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]   # axis-aligned, d has zeros
+    rays["tmin"] = 1e-4
+    rays["tmax"] = 1e4
+    _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
+    rays["tmax"] = 0.5                                                      # TMax before any surface
+    assert (ctx.trace(rays)["inst"] == rtdx.MISS).all()
+    # rays starting exactly on a surface with TMin = s_bias (the reference's bounce convention)
+    rays["origin"] = (0.3, 0.0, 0.2)
+    rays["tmin"] = 2e-5
+    rays["tmax"] = 1e4
+    _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_side", [8, 40])
+def test_trace_mesh_room(rtdx, orc, n_side):
+    sc = rtdx.scenes.mesh_room(n=n_side)
+    ctx, up = _upload(rtdx, sc, 128, 128)
+    osc = _oracle(orc, sc, up)
+    rng = np.random.RandomState(11)
+    rays = np.concatenate([rtdx.scenes.camera_rays(up["camera"], 128, 128), random_rays(rtdx, rng, 100000, (-5, 0.1, -5), (5, 5.9, 5))])
+    ref = osc.trace(rays, mode=1)
+    _assert_hits_equal(ctx.trace(rays), ref)
+    sub = rays[:4000]
+    _assert_hits_equal(osc.trace(sub, mode=1), osc.trace(sub, mode=0))     # oracle BVH2 == brute force
+    ctx.close()
+
+
+def test_trace_instanced(rtdx, orc):
+    sc = rtdx.scenes.instanced_blobs(n_models=3, n_side=6, lattice=4)
+    ctx, up = _upload(rtdx, sc, 128, 128)
+    osc = _oracle(orc, sc, up)
+    rng = np.random.RandomState(13)
+    rays = np.concatenate([rtdx.scenes.camera_rays(up["camera"], 128, 128), random_rays(rtdx, rng, 50000, (-2.5, -2.5, -2.5), (2.5, 2.5, 2.5))])
+    ref = osc.trace(rays, mode=1)
+    _assert_hits_equal(ctx.trace(rays), ref)
+    sub = rays[::37]
+    _assert_hits_equal(osc.trace(sub, mode=1), osc.trace(sub, mode=0))
+    ctx.close()
+
+
+def _render_both(rtdx, orc, sc, W, H, spp, bounces, flags, spp_per_pass=1, step=1):
+    ctx, up = _upload(rtdx, sc, W, H, bounces=bounces, flags=flags, samples_per_pass=spp_per_pass)
+    osc = _oracle(orc, sc, up)
+    ctx.reset_counters()
+    ctx.render_pass(0, spp)
+    ctx.synchronize()
+    gpu = ctx.read_accum()
+    cnt = ctx.counters()
+    ref, octr = osc.render(up["camera"], W, H, 0, spp, bounces=bounces, flags=flags, step=step)
+    return ctx, gpu, cnt, ref, octr
+
+
+def test_render_cornell_c1_bit_exact(rtdx, orc):
+    """BASELINE config C1: Cornell 36 tris, 256x256, 16 spp, depth 4 (bounces=2), Lambert only, jitter on."""
+    sc = rtdx.scenes.cornell()
+    flags = rtdx.FLAG_JITTER | rtdx.FLAG_LAMBERT_ONLY
+    ctx, gpu, cnt, ref, octr = _render_both(rtdx, orc, sc, 256, 256, 16, 2, flags, spp_per_pass=4)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (cnt, octr)
+    mism = bits(gpu) != bits(ref)
+    assert mism.sum() == 0, "radiance mismatches: %d of %d floats" % (mism.sum(), mism.size)
+    # output image (F20)
+    assert np.array_equal(ctx.read_output(), orc.resolve(ref))
+    ctx.close()
+
+
+def test_render_mesh_room_ggx(rtdx, orc):
+    """C2-shaped (GGX + diffuse, smooth normals, two instances) at a size the oracle finishes in seconds."""
+    sc = rtdx.scenes.mesh_room(n=24)
+    ctx, gpu, cnt, ref, octr = _render_both(rtdx, orc, sc, 96, 64, 2, 6, 0)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (cnt, octr)
+    mism = bits(gpu) != bits(ref)
+    assert mism.sum() == 0, "radiance mismatches: %d of %d floats" % (mism.sum(), mism.size)
+    ctx.close()
+
+
+def test_render_instanced_emitters(rtdx, orc):
+    """C3-shaped: TLAS over rotated/scaled instances, many emissive triangles, NEE."""
+    sc = rtdx.scenes.instanced_blobs(n_models=3, n_side=6, lattice=4, emissive_fraction=0.1)
+    ctx, gpu, cnt, ref, octr = _render_both(rtdx, orc, sc, 96, 64, 2, 3, 0)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (cnt, octr)
+    mism = bits(gpu) != bits(ref)
+    assert mism.sum() == 0, "radiance mismatches: %d of %d floats" % (mism.sum(), mism.size)
+    ctx.close()
+
+
+def test_accumulation_reset_on_camera_change(rtdx):
+    sc = rtdx.scenes.cornell()
+    ctx, up = _upload(rtdx, sc, 64, 64, bounces=2, flags=rtdx.FLAG_LAMBERT_ONLY)
+    ctx.render_pass(0, 2)
+    a = ctx.read_accum()
+    assert a[..., 3].max() == 2.0
+    ctx.set_camera(up["camera"])                       # same view: accumulation continues (Pass_spat_di_v7.hlsl:407-423)
+    ctx.render_pass(2, 1)
+    assert ctx.read_accum()[..., 3].max() == 3.0
+    cam2 = rtdx.camera_params((0.2, 1.0, 3.4), sc.center, sc.up, 1.0)
+    ctx.set_camera(cam2)                               # view changed by more than s_bias: reset
+    ctx.render_pass(0, 1)
+    assert ctx.read_accum()[..., 3].max() == 1.0
+    ctx.close()
