@@ -116,6 +116,12 @@ rtx_status rtx_get_counters(rtx_ctx*, rtx_counters* out);
 rtx_status rtx_reset_counters(rtx_ctx*);
 /* device time in ms of the traversal kernels / all kernels of the last rtx_render_pass (CUDA events on the ctx stream) */
 rtx_status rtx_last_pass_ms(rtx_ctx*, float* trace_ms, float* total_ms);
+/* runtime options.  RTX_OPT_TRACE_STATS: closest-hit traversals of rtx_render_pass also count nodes/triangles/instances
+ * (instrumented kernel variant: for the roofline's B_ray, never for timed runs).  RTX_OPT_STAGE_TIMING: record CUDA events
+ * around every traversal launch of a pass so that rtx_last_pass_ms can report the traversal share. */
+#define RTX_OPT_TRACE_STATS   1u
+#define RTX_OPT_STAGE_TIMING  2u
+rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);
 

@@ -59,6 +59,7 @@ def lib():
         L.orc_build.argtypes = [vp]
         L.orc_trace.argtypes = [vp, vp, u32, vp, C.c_int, C.c_int]
         L.orc_render.argtypes = [vp, C.POINTER(OrcConfig), vp, u32, u32, u32, vp, C.POINTER(OrcCounters), C.c_int]
+        L.orc_render_rows.argtypes = [vp, C.POINTER(OrcConfig), vp, u32, u32, u32, u32, u32, vp, C.POINTER(OrcCounters), C.c_int]
         L.orc_resolve.argtypes = [vp, u32, vp]
         L.orc_kat_rng.argtypes = [u32, u32, u32, vp, vp]
         L.orc_kat_seed.argtypes = [u32, u32, u32, u32, vp]
@@ -128,6 +129,28 @@ class OracleScene:
         c = np.ascontiguousarray(cam)
         self.L.orc_render(self.h, C.byref(cfg), _p(c), first_sample, n_samples, step, _p(accum), C.byref(ctr), mode)
         return accum, {k: getattr(ctr, k) for k, _ in OrcCounters._fields_}
+
+    def render_threads(self, cam, width, height, first_sample, n_samples, n_threads, bounces=3, nee_samples=4, nee_samples_di=4,
+                       flags=0, step=1, accum=None, mode=1):
+        """Same result as render(); rows are split over n_threads host threads (ctypes releases the GIL)."""
+        import threading
+        cfg = OrcConfig(width, height, bounces, nee_samples, nee_samples_di, flags)
+        if accum is None:
+            accum = np.zeros((height, width, 4), dtype=np.float32)
+        c = np.ascontiguousarray(cam)
+        rows = [r for r in range(0, height, step)]
+        chunks = [rows[i::n_threads] for i in range(n_threads)]
+        ctrs = [OrcCounters() for _ in range(n_threads)]
+
+        def work(i):
+            for y in chunks[i]:
+                self.L.orc_render_rows(self.h, C.byref(cfg), _p(c), first_sample, n_samples, step, y, y + 1, _p(accum), C.byref(ctrs[i]), mode)
+
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        tot = {k: sum(getattr(ct, k) for ct in ctrs) for k, _ in OrcCounters._fields_}
+        return accum, tot
 
     def debug_pixel(self, cam, width, height, x, y, sample, bounces=3, nee_samples=4, nee_samples_di=4, flags=0, mode=1):
         cfg = OrcConfig(width, height, bounces, nee_samples, nee_samples_di, flags)

@@ -1015,12 +1015,23 @@ void orc_trace(orc_scene* s, const orc_ray* rays, uint32_t n, orc_hit* out, int 
     }
 }
 
+void orc_render_rows(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t first_sample, uint32_t n_samples, uint32_t step,
+                     uint32_t y0, uint32_t y1, float* accum, orc_counters* counters, int trace_mode);
+
 void orc_render(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t first_sample, uint32_t n_samples, uint32_t step,
                 float* accum, orc_counters* counters, int trace_mode) {
+    orc_render_rows(s, cfg, cam, first_sample, n_samples, step, 0, cfg->height, accum, counters, trace_mode);
+}
+
+// rows [y0, y1) only: the scene is read-only, so disjoint row ranges may run on different host threads
+void orc_render_rows(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t first_sample, uint32_t n_samples, uint32_t step,
+                     uint32_t y0, uint32_t y1, float* accum, orc_counters* counters, int trace_mode) {
     orc_counters local; memset(&local, 0, sizeof local);
     Ctx c; c.S = s; c.cfg = *cfg; c.C = counters ? counters : &local; c.mode = trace_mode;
     if (step == 0) step = 1;
-    for (uint32_t y = 0; y < cfg->height; y += step)
+    if (y1 > cfg->height) y1 = cfg->height;
+    y0 = ((y0 + step - 1) / step) * step;
+    for (uint32_t y = y0; y < y1; y += step)
         for (uint32_t x = 0; x < cfg->width; x += step) {
             float* px = accum + 4 * ((size_t)y * cfg->width + x);
             for (uint32_t k = 0; k < n_samples; k++) {

@@ -68,6 +68,9 @@ void orc_trace(orc_scene*, const orc_ray* rays, uint32_t n, orc_hit* out, int an
  * of every pixel with x % step == 0 && y % step == 0 into accum (float4 per pixel, row-major W*H). */
 void orc_render(orc_scene*, const orc_config*, const orc_camera*, uint32_t first_sample, uint32_t n_samples,
                 uint32_t step, float* accum, orc_counters* counters, int trace_mode);
+/* same, rows [y0, y1) only; disjoint row ranges may run concurrently on several host threads */
+void orc_render_rows(orc_scene*, const orc_config*, const orc_camera*, uint32_t first_sample, uint32_t n_samples,
+                     uint32_t step, uint32_t y0, uint32_t y1, float* accum, orc_counters* counters, int trace_mode);
 /* F20 output: sRGB(sum/n) -> RGBA8 */
 void orc_resolve(const float* accum, uint32_t n_pixels, uint8_t* rgba8);
 

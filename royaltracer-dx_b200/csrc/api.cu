@@ -39,7 +39,8 @@ struct rtx_ctx {
     rtx_hit* d_trace_out = nullptr; uint32_t trace_cap = 0;
     TraceStats* d_stats = nullptr;
     uint64_t launches = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    PassTiming timing;
+    bool trace_stats = false;
     bool pass_timed = false;
 };
 
@@ -63,7 +64,7 @@ extern "C" rtx_status rtx_create(const rtx_config* cfg, rtx_ctx** out) {
     if (c->cfg.samples_per_pass == 0) c->cfg.samples_per_pass = 1;
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
     else { RTX_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    for (int i = 0; i < 4; i++) RTX_CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < WAVE_MAX_EVENTS; i++) RTX_CK(cudaEventCreate(&c->timing.ev[i]));
     RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
     RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
     memset(&c->cam, 0, sizeof c->cam);
@@ -89,7 +90,7 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     free_bvh(&c->tlas);
     free_tables(c);
     if (c->wb_ready) wave_free(&c->wb);
-    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -261,8 +262,8 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
     uint32_t done = 0;
     while (done < n_samples) {
         const uint32_t spp = std::min(c->cfg.samples_per_pass, n_samples - done);
-        PassTiming t;
-        RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, c->ev, &t));
+        c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
+        RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
         done += spp;
     }
     c->pass_timed = true;
@@ -431,11 +432,25 @@ extern "C" rtx_status rtx_last_pass_ms(rtx_ctx* c, float* trace_ms, float* total
     if (!c) return fail(RTX_ERR_ARG, "null context");
     if (!c->pass_timed) return fail(RTX_ERR_STATE, "rtx_last_pass_ms: no pass rendered yet");
     RTX_CK(cudaSetDevice(c->cfg.device));
-    RTX_CK(cudaEventSynchronize(c->ev[1]));
+    RTX_CK(cudaEventSynchronize(c->timing.ev[1]));
     float t = 0.0f;
-    RTX_CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[1]));
+    RTX_CK(cudaEventElapsedTime(&t, c->timing.ev[0], c->timing.ev[1]));
     if (total_ms) *total_ms = t;
-    if (trace_ms) *trace_ms = 0.0f;
+    float tr = 0.0f;
+    for (int i = 0; i < c->timing.n_closest; i++) {
+        float d = 0.0f;
+        RTX_CK(cudaEventElapsedTime(&d, c->timing.ev[2 + 2 * i], c->timing.ev[3 + 2 * i]));
+        tr += d;
+    }
+    if (trace_ms) *trace_ms = tr;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    if (option == RTX_OPT_TRACE_STATS) c->trace_stats = value != 0;
+    else if (option == RTX_OPT_STAGE_TIMING) c->timing.stage_timing = value != 0;
+    else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;
 }
 

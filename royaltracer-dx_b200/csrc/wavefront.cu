@@ -537,46 +537,61 @@ k_scatter_vis(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ p
 }
 
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
-                             uint64_t* launches, cudaEvent_t* ev, PassTiming* timing) {
+                             uint64_t* launches, PassTiming* T) {
     const uint32_t npx = S.width * S.height;
     const uint32_t n = npx * spp;
     if (n > B.n_paths) return cudaErrorInvalidValue;
     StateView st{B.state, n};
     const unsigned grid = (n + WF_BLOCK - 1) / WF_BLOCK;
     uint64_t L = 0;
+    T->n_closest = 0; T->n_shadow = 0;
+    int ev_next = 2;
+    int shadow_ev[4]; int n_shadow_ev = 0;
+    auto closest = [&](const RayQueue& q) -> cudaError_t {
+        const bool timed = T->stage_timing && ev_next + 2 <= WAVE_MAX_EVENTS - 4;
+        if (timed) CKE(cudaEventRecord(T->ev[ev_next], stream));
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, false, T->stats, stream)); L++;
+        if (timed) { CKE(cudaEventRecord(T->ev[ev_next + 1], stream)); ev_next += 2; T->n_closest++; }
+        return cudaSuccess;
+    };
+    auto shadow = [&](const RayQueue& q, float* vis) -> cudaError_t {
+        const bool timed = T->stage_timing && n_shadow_ev + 2 <= 4;
+        if (timed) CKE(cudaEventRecord(T->ev[WAVE_MAX_EVENTS - 4 + n_shadow_ev], stream));
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
+        if (timed) { CKE(cudaEventRecord(T->ev[WAVE_MAX_EVENTS - 4 + n_shadow_ev + 1], stream)); n_shadow_ev += 2; T->n_shadow++; }
+        k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(q.count, q.pid, B.hit_inst, vis); L++;
+        return cudaSuccess;
+    };
+    (void)shadow_ev;
     CKE(cudaMemsetAsync(B.counts, 0, 128 * 4, stream));
     // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
     RayQueue q0 = B.q[0], q1 = B.q[1], sdi = B.sq[0], sgi = B.sq[1];
     q0.count = B.counts + 0; q1.count = B.counts + 1; sdi.count = B.counts + 2; sgi.count = B.counts + 3;
-    CKE(cudaEventRecord(ev[0], stream));
+    CKE(cudaEventRecord(T->ev[0], stream));
     k_generate<<<grid, WF_BLOCK, 0, stream>>>(st, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi, B.ray_counters); L++;
-    CKE(launch_trace(AS, q0.o_tmin, q0.d_tmax, q0.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    CKE(closest(q0));
     k_shade_primary<<<grid, WF_BLOCK, 0, stream>>>(st, S, q0, B.hit_a, B.hit_inst, q1, B.ray_counters); L++;
-    CKE(launch_trace(AS, q1.o_tmin, q1.d_tmax, q1.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    CKE(closest(q1));
     RayQueue qa = B.q[0]; qa.count = B.counts + 4;
     k_di_finish<<<grid, WF_BLOCK, 0, stream>>>(st, S, q1, B.hit_a, B.hit_inst, sdi, qa, B.ray_counters); L++;
-    // DI visibility (connect): result scattered into vis_di.  hit_inst is reused afterwards by the closest trace.
-    CKE(launch_trace(AS, sdi.o_tmin, sdi.d_tmax, sdi.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
-    k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(sdi.count, sdi.pid, B.hit_inst, B.vis_di); L++;
-    CKE(launch_trace(AS, qa.o_tmin, qa.d_tmax, qa.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+    CKE(shadow(sdi, B.vis_di));                 // DI visibility (connect); hit_inst is reused by the next closest trace
+    CKE(closest(qa));
     int cur = 0;
     RayQueue qin = qa;
     for (uint32_t iter = 0; iter <= S.bounces; iter++) {
         RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
         k_gi_step<<<grid, WF_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters); L++;
         if (iter < S.bounces) {
-            CKE(launch_trace(AS, qout.o_tmin, qout.d_tmax, qout.count, 0, B.cursor, B.hit_a, B.hit_inst, false, nullptr, stream)); L++;
+            CKE(closest(qout));
             qin = qout; cur ^= 1;
         }
     }
-    CKE(launch_trace(AS, sgi.o_tmin, sgi.d_tmax, sgi.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
-    k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(sgi.count, sgi.pid, B.hit_inst, B.vis_gi); L++;
+    CKE(shadow(sgi, B.vis_gi));
     k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters); L++;
     k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum); L++;
-    CKE(cudaEventRecord(ev[1], stream));
+    CKE(cudaEventRecord(T->ev[1], stream));
     CKE(cudaGetLastError());
     if (launches) *launches += L;
-    (void)timing;
     return cudaSuccess;
 }
 

@@ -51,11 +51,18 @@ struct WaveBuffers {
 cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp);
 void wave_free(WaveBuffers* B);
 
-struct PassTiming { float trace_ms, total_ms; };
+#define WAVE_MAX_EVENTS 96
+struct PassTiming {
+    cudaEvent_t ev[WAVE_MAX_EVENTS] = {};   // [0],[1] bracket the pass; pairs from [2] bracket closest-hit traversal launches,
+    int n_closest = 0;                 // then pairs bracketing any-hit launches
+    int n_shadow = 0;
+    bool stage_timing = false;
+    TraceStats* stats = nullptr;       // non-null: use the counting traversal variant
+};
 
 // One DispatchRays-equivalent: samples [first_sample, first_sample + spp) of every pixel.
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
-                             cudaStream_t stream, uint64_t* launches, cudaEvent_t* ev /*4 events*/, PassTiming* timing);
+                             cudaStream_t stream, uint64_t* launches, PassTiming* timing);
 cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream, uint64_t* launches);
 cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uint32_t y, cudaStream_t stream, float* host_out64);
 

@@ -51,8 +51,10 @@ def test_trace_edge_cases(rtdx, orc):
     rays["tmin"] = 1e-4
     rays["tmax"] = 1e4
     _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
-    rays["tmax"] = 0.5                                                      # TMax before any surface
+    rays["tmax"] = 0.01                                                     # TMax before any surface
     assert (ctx.trace(rays)["inst"] == rtdx.MISS).all()
+    rays["tmax"] = 0.5                                                      # TMax cuts some of the hits
+    _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
     # rays starting exactly on a surface with TMin = s_bias (the reference's bounce convention)
     rays["origin"] = (0.3, 0.0, 0.2)
     rays["tmin"] = 2e-5
