@@ -89,7 +89,7 @@ RayPre ray_pre(f3 o, f3 d) {
     if (comp(d, kz) < 0.0f) std::swap(kx, ky);
     r.kx = kx; r.ky = ky; r.kz = kz;
     float dz = comp(d, kz);
-    r.Sx = comp(d, kx) / dz; r.Sy = comp(d, ky) / dz; r.Sz = 1.0f / dz;
+    r.Sz = 1.0f / dz; r.Sx = comp(d, kx) * r.Sz; r.Sy = comp(d, ky) * r.Sz;
     return r;
 }
 

@@ -11,7 +11,7 @@
 namespace rtx {
 
 #define TRACE_BLOCK 128
-#define FETCH_THRESHOLD 20   // refill when fewer than this many lanes are active
+#define FETCH_THRESHOLD 24   // refill the warp's idle lanes when fewer than this many lanes are still traversing
 
 template <bool ANY_HIT, bool STATS>
 __global__ void __launch_bounds__(TRACE_BLOCK, 4)
@@ -20,28 +20,55 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
              float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st) {
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     uint2 stack[RTX_STACK_SIZE];
+    Trav T;
+    bool active = false;
+    bool exhausted = (S.n_instances == 0u);
+    uint32_t j = 0;
+    unsigned int c_nodes = 0, c_tris = 0, c_insts = 0;
 
-    // This first version keeps the whole traversal of one ray inside traverse(); lanes that finish early wait
-    // for the slowest lane of the batch.  Batches are 32 consecutive rays.
     for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t j = base + lane;
-        if (j < n) {
-            const float4 o = __ldg(o_tmin + j), d = __ldg(d_tmax + j);
-            HitRec h;
-            h.t = d.w; h.b1 = 0.0f; h.b2 = 0.0f; h.prim = 0xFFFFFFFFu; h.inst = 0xFFFFFFFFu;
-            traverse<ANY_HIT, STATS>(S, o.x, o.y, o.z, d.x, d.y, d.z, o.w, d.w, h, stack, st);
-            if (ANY_HIT) {
-                hit_inst[j] = h.inst;
-            } else {
-                hit_a[j] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-                hit_inst[j] = h.inst;
+        // ---- refill idle lanes: one atomic per warp claims a run of consecutive rays
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active) {
+                j = base + __popc(idle & lt_mask);
+                if (j < n) {
+                    trav_init(T, S, __ldg(o_tmin + j), __ldg(d_tmax + j));
+                    active = true;
+                }
             }
+            if (base + __popc(idle) >= n) exhausted = true;
         }
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        if (act == 0u) break;
+        // ---- traverse until too few lanes are left (or to the end once the queue is drained)
+        const int threshold = exhausted ? 1 : FETCH_THRESHOLD;
+        do {
+            if (active) {
+                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts)) {
+                    active = false;
+                    if (!ANY_HIT) hit_a[j] = make_float4(T.h.t, T.h.b1, T.h.b2, __uint_as_float(T.h.prim));
+                    hit_inst[j] = T.h.inst;
+                }
+            }
+        } while (__popc(__ballot_sync(0xffffffffu, active)) >= threshold);
+    }
+    if (S.n_instances == 0u) {   // empty scene: everything misses
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            if (!ANY_HIT) hit_a[i] = make_float4(__ldg(d_tmax + i).w, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+            hit_inst[i] = 0xFFFFFFFFu;
+        }
+    }
+    if (STATS) {
+        atomicAdd(&st->nodes, (unsigned long long)c_nodes);
+        atomicAdd(&st->tris, (unsigned long long)c_tris);
+        atomicAdd(&st->insts, (unsigned long long)c_insts);
     }
 }
 

@@ -33,35 +33,44 @@ __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x 
 
 struct RaySpace {          // the ray in the space currently traversed + derived constants
     float ox, oy, oz;
-    float dx, dy, dz;
-    float ix, iy, iz;      // clamped reciprocal direction (box tests only)
-    float Sx, Sy, Sz;      // watertight shear constants
+    float ix, iy, iz;      // approximate reciprocal direction, clamped away from 0 (box tests only: conservative, not reproducible)
+    float Sx, Sy, Sz;      // watertight shear constants (BLAS space only)
     uint32_t k;            // kx | ky<<2 | kz<<4
     uint32_t octinv4;      // (dx>=0 | dy>=0 <<1 | dz>=0 <<2) * 0x01010101
 };
 
 __device__ __forceinline__ float sel3(float x, float y, float z, uint32_t k) { return k == 0 ? x : (k == 1 ? y : z); }
 
-__device__ __forceinline__ void setup_space(RaySpace& r, float ox, float oy, float oz, float dx, float dy, float dz) {
-    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// box-test part: origin, reciprocal direction, octant
+__device__ __forceinline__ void setup_box(RaySpace& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+    r.ox = ox; r.oy = oy; r.oz = oz;
     const float tiny = 1e-20f;
-    r.ix = 1.0f / (fabsf(dx) > tiny ? dx : copysignf(tiny, dx));
-    r.iy = 1.0f / (fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
-    r.iz = 1.0f / (fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
-    uint32_t oct = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u);
+    r.ix = rcp_approx(fabsf(dx) > tiny ? dx : copysignf(tiny, dx));
+    r.iy = rcp_approx(fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
+    r.iz = rcp_approx(fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
+    const uint32_t oct = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u);
     r.octinv4 = oct * 0x01010101u;
-    // watertight precompute (same rule as the oracle: first maximum in x,y,z order; swap if d[kz] < 0)
-    float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+}
+// triangle-test part (same rule as the oracle: first maximum in x,y,z order; swap kx,ky if d[kz] < 0;
+// Sz = 1/d[kz] (IEEE), Sx = d[kx]*Sz, Sy = d[ky]*Sz)
+__device__ __forceinline__ void setup_tri(RaySpace& r, float dx, float dy, float dz) {
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     uint32_t kz = 0; float m = ax;
     if (ay > m) { kz = 1; m = ay; }
     if (az > m) { kz = 2; }
-    uint32_t kx = (kz + 1) % 3, ky = (kx + 1) % 3;
-    float dkz = sel3(dx, dy, dz, kz);
-    if (dkz < 0.0f) { uint32_t t = kx; kx = ky; ky = t; }
+    uint32_t kx = (kz == 2u) ? 0u : kz + 1u, ky = (kx == 2u) ? 0u : kx + 1u;
+    const float dkz = sel3(dx, dy, dz, kz);
+    if (dkz < 0.0f) { const uint32_t t = kx; kx = ky; ky = t; }
     r.k = kx | (ky << 2) | (kz << 4);
-    r.Sx = sel3(dx, dy, dz, kx) / dkz;
-    r.Sy = sel3(dx, dy, dz, ky) / dkz;
     r.Sz = 1.0f / dkz;
+    r.Sx = sel3(dx, dy, dz, kx) * r.Sz;
+    r.Sy = sel3(dx, dy, dz, ky) * r.Sz;
 }
 
 // Watertight ray/triangle test; identical operation order to oracle/rtx_oracle.cpp tri_test().
@@ -106,7 +115,7 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
     const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * r.iy;
     const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * r.iz;
     const float bx = (px - r.ox) * r.ix, by = (py - r.oy) * r.iy, bz = (pz - r.oz) * r.iz;
-    const bool nx = r.dx < 0.0f, ny = r.dy < 0.0f, nz = r.dz < 0.0f;
+    const bool nx = !(r.octinv4 & 1u), ny = !(r.octinv4 & 2u), nz = !(r.octinv4 & 4u);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -151,108 +160,115 @@ __device__ __forceinline__ bool hit_better(float t, uint32_t inst, uint32_t prim
     return prim < h.prim;
 }
 
-// Full traversal of one ray.  `h.t` must be initialised to the ray's TMax and h.inst to 0xFFFFFFFF.
-// Returns true if anything was hit.
+// Traversal state of one ray (registers) — lets a persistent warp retire and replace single lanes.
+struct Trav {
+    RaySpace r;                 // current space
+    float wox, woy, woz, wdx, wdy, wdz;   // world-space ray
+    float wix, wiy, wiz; uint32_t woct4;   // world-space box-test constants (restored when a BLAS is left)
+    float tmin, tmax;
+    HitRec h;
+    const uint4* nodes; const float4* prims;
+    uint2 G;
+    uint32_t cur_inst;
+    int sp;
+    bool in_blas;
+};
+
+__device__ __forceinline__ void trav_init(Trav& T, const SceneAS& S, float4 o_tmin, float4 d_tmax) {
+    T.wox = o_tmin.x; T.woy = o_tmin.y; T.woz = o_tmin.z; T.wdx = d_tmax.x; T.wdy = d_tmax.y; T.wdz = d_tmax.z;
+    T.tmin = o_tmin.w; T.tmax = d_tmax.w;
+    setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
+    T.wix = T.r.ix; T.wiy = T.r.iy; T.wiz = T.r.iz; T.woct4 = T.r.octinv4;
+    T.h.t = d_tmax.w; T.h.b1 = 0.0f; T.h.b2 = 0.0f; T.h.prim = 0xFFFFFFFFu; T.h.inst = 0xFFFFFFFFu;
+    T.nodes = S.tlas_nodes; T.prims = S.inst_recs;
+    T.G = make_uint2(0u, 0x80000000u);
+    T.cur_inst = 0; T.sp = 0; T.in_blas = false;
+}
+
+// One traversal step: at most one node intersection, then the node's leaf primitives, then a pop.
+// Returns true when the ray is finished.
 template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ bool traverse(const SceneAS& S, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float tmin, float tmax_ray, HitRec& h, uint2* stack, TraceStats* st) {
-    RaySpace r;
-    setup_space(r, ox, oy, oz, dx, dy, dz);
-    const uint4* nodes = S.tlas_nodes;
-    const float4* prims = S.inst_recs;
-    bool in_blas = false;
-    uint32_t cur_inst = 0;
-    int sp = 0;
-    uint2 G = make_uint2(0u, 0x80000000u);
-    uint2 Gt = make_uint2(0u, 0u);
-    unsigned long long c_nodes = 0, c_tris = 0, c_insts = 0;
-    if (S.n_instances == 0) return false;
+__device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stack, unsigned int* c_nodes, unsigned int* c_tris,
+                                          unsigned int* c_insts) {
+    uint2 G = T.G, Gt;
+    int sp = T.sp;
+    if (G.y & 0xff000000u) {
+        const uint32_t bit = 31u - __clz(G.y);
+        G.y &= ~(1u << bit);
+        const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
+        if (G.y & 0xff000000u) RTX_PUSH(G);
+        const uint32_t slot = (bit - 24u) ^ (T.r.octinv4 & 0xffu);
+        const uint32_t rel = __popc(imask & ~(0xffffffffu << slot));
+        const uint4* np = T.nodes + (size_t)(G.x + rel) * 5;
+        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (STATS) (*c_nodes)++;
+        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t);
+        G.x = n1.x;
+        Gt.x = n1.y;
+        G.y = (hm & 0xff000000u) | (n0.w >> 24);
+        Gt.y = hm & 0x00ffffffu;
+    } else {
+        Gt = G;
+        G = make_uint2(0u, 0u);
+    }
 
-    for (;;) {
-        if (G.y & 0xff000000u) {
-            const uint32_t bit = 31u - __clz(G.y);
-            G.y &= ~(1u << bit);
-            const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
-            if (G.y & 0xff000000u) RTX_PUSH(G);
-            const uint32_t slot = (bit - 24u) ^ (r.octinv4 & 0xffu);
-            const uint32_t rel = __popc(imask & ~(0xffffffffu << slot));
-            const uint32_t ni = G.x + rel;
-            const uint4* np = nodes + (size_t)ni * 5;
-            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (STATS) c_nodes++;
-            const float far = ANY_HIT ? tmax_ray : h.t;
-            const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, tmin, far);
-            G.x = n1.x;
-            Gt.x = n1.y;
-            G.y = (hm & 0xff000000u) | (n0.w >> 24);
-            Gt.y = hm & 0x00ffffffu;
+    while (Gt.y != 0u) {
+        const uint32_t bit = 31u - __clz(Gt.y);
+        Gt.y &= ~(1u << bit);
+        if (T.in_blas) {
+            const float4* tp = T.prims + (size_t)(Gt.x + bit) * 3;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (STATS) (*c_tris)++;
+            float t, b1, b2;
+            if (tri_test(T.r, a, b, c, T.tmin, T.tmax, t, b1, b2)) {
+                const uint32_t prim = __float_as_uint(a.w);
+                if (ANY_HIT) {
+                    T.h.t = t; T.h.b1 = b1; T.h.b2 = b2; T.h.prim = prim; T.h.inst = T.cur_inst;
+                    return true;
+                }
+                if (T.h.inst == 0xFFFFFFFFu || hit_better(t, T.cur_inst, prim, T.h)) {
+                    T.h.t = t; T.h.b1 = b1; T.h.b2 = b2; T.h.prim = prim; T.h.inst = T.cur_inst;
+                }
+            }
         } else {
-            Gt = G;
-            G = make_uint2(0u, 0u);
-        }
-
-        while (Gt.y != 0u) {
-            const uint32_t bit = 31u - __clz(Gt.y);
-            Gt.y &= ~(1u << bit);
-            if (in_blas) {
-                const float4* tp = prims + (size_t)(Gt.x + bit) * 3;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                if (STATS) c_tris++;
-                float t, b1, b2;
-                if (tri_test(r, a, b, c, tmin, tmax_ray, t, b1, b2)) {
-                    const uint32_t prim = __float_as_uint(a.w);
-                    if (ANY_HIT) {
-                        h.t = t; h.b1 = b1; h.b2 = b2; h.prim = prim; h.inst = cur_inst;
-                        if (STATS) { atomicAdd(&st->nodes, c_nodes); atomicAdd(&st->tris, c_tris); atomicAdd(&st->insts, c_insts); }
-                        return true;
-                    }
-                    if (h.inst == 0xFFFFFFFFu || hit_better(t, cur_inst, prim, h)) {
-                        h.t = t; h.b1 = b1; h.b2 = b2; h.prim = prim; h.inst = cur_inst;
-                    }
-                }
-            } else {
-                // instance leaf: enter the BLAS.  Save what is left of this level, then a sentinel.
-                const float4* ip = prims + (size_t)(Gt.x + bit) * 4;
-                const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-                if (STATS) c_insts++;
-                if (Gt.y) RTX_PUSH(Gt);
-                if (G.y & 0xff000000u) RTX_PUSH(G);
-                RTX_PUSH(make_uint2(0xffffffffu, 0u));
-                const float tox = ((r0.x * ox + r0.y * oy) + r0.z * oz) + r0.w * 1.0f;
-                const float toy = ((r1.x * ox + r1.y * oy) + r1.z * oz) + r1.w * 1.0f;
-                const float toz = ((r2.x * ox + r2.y * oy) + r2.z * oz) + r2.w * 1.0f;
-                const float tdx = ((r0.x * dx + r0.y * dy) + r0.z * dz) + r0.w * 0.0f;
-                const float tdy = ((r1.x * dx + r1.y * dy) + r1.z * dz) + r1.w * 0.0f;
-                const float tdz = ((r2.x * dx + r2.y * dy) + r2.z * dz) + r2.w * 0.0f;
-                setup_space(r, tox, toy, toz, tdx, tdy, tdz);
-                const BlasRef br = S.blas[__float_as_uint(r3.x)];
-                nodes = br.nodes; prims = br.tris;
-                cur_inst = __float_as_uint(r3.y);
-                in_blas = true;
-                G = make_uint2(0u, 0x80000000u);
-                Gt = make_uint2(0u, 0u);
-                break;
-            }
-        }
-
-        if ((G.y & 0xff000000u) == 0u) {
-            // pop
-            bool done = false;
-            for (;;) {
-                if (sp == 0) { done = true; break; }
-                G = stack[--sp];
-                if (G.x == 0xffffffffu && G.y == 0u) {   // sentinel: back to the TLAS / world space
-                    setup_space(r, ox, oy, oz, dx, dy, dz);
-                    nodes = S.tlas_nodes; prims = S.inst_recs; in_blas = false;
-                    continue;
-                }
-                break;
-            }
-            if (done) break;
+            // instance leaf: enter the BLAS.  Save what is left of this level, then a sentinel.
+            const float4* ip = T.prims + (size_t)(Gt.x + bit) * 4;
+            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            if (STATS) (*c_insts)++;
+            if (Gt.y) RTX_PUSH(Gt);
+            if (G.y & 0xff000000u) RTX_PUSH(G);
+            RTX_PUSH(make_uint2(0xffffffffu, 0u));
+            const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
+            const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
+            const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
+            const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
+            const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
+            const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
+            setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
+            setup_tri(T.r, tdx, tdy, tdz);
+            const BlasRef br = S.blas[__float_as_uint(r3.x)];
+            T.nodes = br.nodes; T.prims = br.tris;
+            T.cur_inst = __float_as_uint(r3.y);
+            T.in_blas = true;
+            G = make_uint2(0u, 0x80000000u);
+            break;
         }
     }
-    if (STATS) { atomicAdd(&st->nodes, c_nodes); atomicAdd(&st->tris, c_tris); atomicAdd(&st->insts, c_insts); }
-    return h.inst != 0xFFFFFFFFu;
+
+    if ((G.y & 0xff000000u) == 0u) {
+        for (;;) {   // pop
+            if (sp == 0) { T.sp = 0; return true; }
+            G = stack[--sp];
+            if (G.x == 0xffffffffu && G.y == 0u) {   // sentinel: back to the TLAS / world space
+                T.r.ox = T.wox; T.r.oy = T.woy; T.r.oz = T.woz; T.r.ix = T.wix; T.r.iy = T.wiy; T.r.iz = T.wiz; T.r.octinv4 = T.woct4;
+                T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.in_blas = false;
+                continue;
+            }
+            break;
+        }
+    }
+    T.G = G; T.sp = sp;
+    return false;
 }
 
 }  // namespace rtx
