@@ -128,7 +128,7 @@ extern "C" rtx_status rtx_blas_info_get(rtx_ctx* c, uint32_t model_id, rtx_blas_
     const ModelRec& m = c->models[model_id];
     out->n_nodes = m.bvh.n_nodes; out->n_tris = m.bvh.n_prims;
     out->bytes = (uint64_t)m.bvh.n_nodes * 80 + (uint64_t)m.bvh.n_prims * 48;
-    out->sah_cost = 0.0f; out->build_ms = m.bvh.build_ms;
+    out->sah_cost = m.bvh.sah_cost; out->build_ms = m.bvh.build_ms;
     return RTX_OK;
 }
 

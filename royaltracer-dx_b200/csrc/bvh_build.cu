@@ -7,14 +7,17 @@
 // Pipeline (all on the context stream, no host data structures):
 //   1. primitive boxes + scene bounds        (k_tri_boxes, atomics on order-preserving uints)
 //   2. 63-bit Morton codes of box centres     (k_morton)  + radix sort (cub::DeviceRadixSort — plumbing)
-//   3. binary radix tree over the sorted keys (k_lbvh, Karras 2012) and bottom-up box fit (k_fit)
-//   4. surface-area-guided collapse to 8-wide nodes: every wide node repeatedly opens the child with the largest
-//      surface area until it has 8 children; subtrees of <= 3 primitives become leaves; children are assigned to
+//   3. binary hierarchy by parallel locally-ordered clustering over the sorted order (k_ploc_*): every round each cluster
+//      finds the neighbour (+-16 positions) with the smallest merged surface area; mutual pairs merge.  Each merge also
+//      fills the node's table of the SAH dynamic programme (cost of covering the subtree with 1..7 wide-node roots)
+//   4. SAH-optimal collapse to 8-wide nodes (k_collapse, one launch per tree level): follows the programme's decisions
+//      (which subtrees become leaves of <= 3 primitives, how the 8 child slots are split); children are assigned to
 //      octant slots so that (slot ^ ray octant) is a front-to-back order; boxes are quantised to 8 bits per plane
-//      in the node's local power-of-two grid (k_collapse, one launch per tree level).
+//      in the node's local power-of-two grid.
 // Boxes are padded by 2^-15 of the model's coordinate scale so that the (bit-exact, contract-defining)
 // ray/triangle test never reports a hit the conservative box tests culled.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "trace.h"
 
@@ -29,7 +32,7 @@ namespace rtx {
 #define MAX_LEAF 3
 
 struct BuildCounters {
-    unsigned int nodes, prims, tasks_out;
+    unsigned int nodes, prims, tasks_out, hier_nodes;
     unsigned int bounds[6];   // order-preserving encodings: lo xyz (min), hi xyz (max)
 };
 
@@ -47,7 +50,7 @@ __device__ __host__ __forceinline__ float dec_f(unsigned int e) {
 }
 
 __global__ void k_init_counters(BuildCounters* c) {
-    c->nodes = 1; c->prims = 0; c->tasks_out = 0;
+    c->nodes = 1; c->prims = 0; c->tasks_out = 0; c->hier_nodes = 0;
     c->bounds[0] = c->bounds[1] = c->bounds[2] = 0xffffffffu;
     c->bounds[3] = c->bounds[4] = c->bounds[5] = 0u;
 }
@@ -120,85 +123,145 @@ __global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict
     vals[t] = t;
 }
 
-// ---- binary radix tree (Karras 2012).  Node ids: internal i in [0, n-2], leaf j -> (n-1)+j.
-__device__ __forceinline__ int lcp(const unsigned long long* __restrict__ keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    unsigned long long a = keys[i], b = keys[j];
-    if (a == b) return 64 + __clz(i ^ j);
-    return __clzll(a ^ b);
-}
+// ---- binary hierarchy by parallel locally-ordered clustering (PLOC) over the Morton-sorted primitives.
+// Node ids: leaf j (sorted position) -> j, inner nodes -> n + k in creation order.  Every merge also fills the node's
+// table of the surface-area-heuristic dynamic programme that later picks the optimal 8-wide collapse:
+//   C(m,1) = min(C_leaf(m), C_inner(m)),  C(m,i) = min(C_dist(m,i), C(m,i-1)),
+//   C_inner(m) = A_m * c_node + C_dist(m,8),  C_dist(m,j) = min_k C(left,k) + C(right,j-k),  C_leaf(m) = A_m * P_m * c_prim (P_m <= 3)
+#define PLOC_RADIUS 16
+#define C_NODE 1.0f
+#define C_PRIM 0.3f
 
-__global__ void k_lbvh(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ child, int2* __restrict__ range,
-                       int* __restrict__ parent) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int d = (lcp(keys, n, i, i + 1) - lcp(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = lcp(keys, n, i, i - d);
-    int lmax = 2;
-    while (lcp(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int l = 0;
-    for (int t = lmax / 2; t >= 1; t /= 2)
-        if (lcp(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    int j = i + l * d;
-    int dnode = lcp(keys, n, i, j);
-    int s = 0, t = l;
-    do {
-        t = (t + 1) / 2;
-        if (lcp(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    int gamma = i + s * d + min(d, 0);
-    int first = min(i, j), last = max(i, j);
-    int left = (first == gamma) ? (n - 1 + gamma) : gamma;
-    int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-    child[i] = make_int2(left, right);
-    range[i] = make_int2(first, last);
-    parent[left] = i;
-    parent[right] = i;
-    if (i == 0) parent[0] = -1;
-}
-
-__global__ void k_fit(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ vals, int n,
-                      const int2* __restrict__ child, const int* __restrict__ parent, unsigned int* __restrict__ flags,
-                      float4* __restrict__ nlo, float4* __restrict__ nhi, const BuildCounters* c) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    float s = 0.0f;
-    for (int k = 0; k < 6; k++) s = fmaxf(s, fabsf(dec_f(c->bounds[k])));
-    const float pad = s * 3.0517578125e-5f + 1e-30f;
-    uint32_t p = vals[j];
-    float4 l = plo[p], h = phi[p];
-    l.x -= pad; l.y -= pad; l.z -= pad; h.x += pad; h.y += pad; h.z += pad;
-    int id = n - 1 + j;
-    nlo[id] = l; nhi[id] = h;
-    int par = parent[id];
-    while (par >= 0) {
-        __threadfence();
-        unsigned int old = atomicAdd(&flags[par], 1u);
-        if (old == 0u) return;
-        int2 ch = child[par];
-        float4 al = __ldcg(&nlo[ch.x]), ah = __ldcg(&nhi[ch.x]), bl = __ldcg(&nlo[ch.y]), bh = __ldcg(&nhi[ch.y]);
-        l = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.0f);
-        h = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.0f);
-        nlo[par] = l; nhi[par] = h;
-        id = par;
-        par = parent[id];
-    }
-}
-
-// ---- collapse to 8-wide compressed nodes
-struct CollapseArgs {
-    const int2* child; const int2* range;
-    const float4* nlo; const float4* nhi;
-    const uint32_t* vals;
+struct Hier {
+    float4* nlo; float4* nhi;       // boxes of all 2n-1 nodes
+    int2* child;                    // inner nodes
+    int* cnt;                       // primitives under an inner node
+    float* cost;                    // 7 floats per inner node: C(m,1..7)
+    unsigned char* dec;             // 8 bytes per inner node: [0] = 1 if C(m,1) is a leaf; [j-1], j=2..8: best k of C_dist(m,j),
+                                    //   bit 7 set (j <= 7) if C(m,j) = C(m,j-1) (use fewer roots)
     int n;
-    uint4* out_nodes; float4* out_prims;
-    BuildCounters* ctr;
 };
 
 __device__ __forceinline__ float box_area(float4 l, float4 h) {
     float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
     return 2.0f * (dx * dy + dy * dz + dz * dx);
 }
+
+__global__ void k_leaf_boxes(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ vals, int n,
+                             float4* __restrict__ nlo, float4* __restrict__ nhi, int* __restrict__ clusters, const BuildCounters* c) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float s = 0.0f;
+    for (int k = 0; k < 6; k++) s = fmaxf(s, fabsf(dec_f(c->bounds[k])));
+    const float pad = s * 3.0517578125e-5f + 1e-30f;
+    const uint32_t p = vals[j];
+    float4 l = plo[p], h = phi[p];
+    nlo[j] = make_float4(l.x - pad, l.y - pad, l.z - pad, 0.0f);
+    nhi[j] = make_float4(h.x + pad, h.y + pad, h.z + pad, 0.0f);
+    clusters[j] = j;
+}
+
+__global__ void k_ploc_nn(const int* __restrict__ clusters, int nc, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                          int* __restrict__ nn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const int ci = clusters[i];
+    const float4 l = nlo[ci], h = nhi[ci];
+    float best = INFINITY; int bj = -1; unsigned bh = 0xffffffffu;
+    const int j0 = max(0, i - PLOC_RADIUS), j1 = min(nc - 1, i + PLOC_RADIUS);
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const int cj = clusters[j];
+        const float4 l2 = nlo[cj], h2 = nhi[cj];
+        const float4 ul = make_float4(fminf(l.x, l2.x), fminf(l.y, l2.y), fminf(l.z, l2.z), 0.0f);
+        const float4 uh = make_float4(fmaxf(h.x, h2.x), fmaxf(h.y, h2.y), fmaxf(h.z, h2.z), 0.0f);
+        const float a = box_area(ul, uh);
+        // Equal areas (regular grids) are ordered by a symmetric hash of the pair: a strict total order on pairs, so the
+        // smallest pair of every neighbourhood is mutual and ties cannot form long one-directional chains.
+        unsigned hp = (unsigned)min(ci, cj) * 0x9E3779B1u ^ (unsigned)max(ci, cj) * 0x85EBCA77u;
+        hp ^= hp >> 15; hp *= 0x2C1B3C6Du; hp ^= hp >> 12;
+        if (a < best || (a == best && hp < bh)) { best = a; bj = j; bh = hp; }
+    }
+    nn[i] = bj;
+}
+
+__device__ __forceinline__ void node_costs(const Hier& H, int id, float out[7]) {
+    if (id < H.n) {                       // single primitive: a leaf whatever the budget
+        const float c = box_area(H.nlo[id], H.nhi[id]) * C_PRIM;
+        for (int i = 0; i < 7; i++) out[i] = c;
+    } else {
+        const float* c = H.cost + (size_t)(id - H.n) * 7;
+        for (int i = 0; i < 7; i++) out[i] = c[i];
+    }
+}
+
+__global__ void k_ploc_merge(const int* __restrict__ clusters, int nc, const int* __restrict__ nn, Hier H, BuildCounters* ctr,
+                             int* __restrict__ out_val, int* __restrict__ valid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const int j = nn[i];
+    const int a = clusters[i];
+    if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+            const int b = clusters[j];
+            const int k = (int)atomicAdd(&ctr->hier_nodes, 1u);
+            const int id = H.n + k;
+            const float4 la = H.nlo[a], ha = H.nhi[a], lb = H.nlo[b], hb = H.nhi[b];
+            const float4 l = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+            const float4 h = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+            H.nlo[id] = l; H.nhi[id] = h;
+            H.child[k] = make_int2(a, b);
+            const int pa = a < H.n ? 1 : H.cnt[a - H.n], pb = b < H.n ? 1 : H.cnt[b - H.n];
+            const int P = pa + pb;
+            H.cnt[k] = P;
+            // SAH dynamic programme
+            float ca[7], cb[7];
+            node_costs(H, a, ca); node_costs(H, b, cb);
+            const float A = box_area(l, h);
+            float dist[9]; unsigned char dk[9];
+            for (int jj = 2; jj <= 8; jj++) {
+                float best = INFINITY; int bk = 1;
+                for (int kk = 1; kk < jj; kk++) {
+                    if (kk > 7 || jj - kk > 7) continue;
+                    const float c = ca[kk - 1] + cb[jj - kk - 1];
+                    if (c < best) { best = c; bk = kk; }
+                }
+                dist[jj] = best; dk[jj] = (unsigned char)bk;
+            }
+            float* C = H.cost + (size_t)k * 7;
+            unsigned char* D = H.dec + (size_t)k * 8;
+            const float c_leaf = (P <= MAX_LEAF) ? A * (float)P * C_PRIM : INFINITY;
+            const float c_inner = A * C_NODE + dist[8];
+            C[0] = fminf(c_leaf, c_inner);
+            D[0] = (c_leaf <= c_inner) ? 1 : 0;
+            D[7] = dk[8];
+            for (int ii = 2; ii <= 7; ii++) {
+                if (C[ii - 2] <= dist[ii]) { C[ii - 1] = C[ii - 2]; D[ii - 1] = (unsigned char)(dk[ii] | 0x80u); }
+                else { C[ii - 1] = dist[ii]; D[ii - 1] = dk[ii]; }
+            }
+            out_val[i] = id; valid[i] = 1;
+        } else {
+            out_val[i] = -1; valid[i] = 0;
+        }
+    } else {
+        out_val[i] = a; valid[i] = 1;
+    }
+}
+
+__global__ void k_ploc_compact(const int* __restrict__ out_val, const int* __restrict__ valid, const int* __restrict__ pos, int nc,
+                               int* __restrict__ clusters_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    if (valid[i]) clusters_out[pos[i]] = out_val[i];
+}
+
+// ---- collapse to 8-wide compressed nodes
+struct CollapseArgs {
+    Hier H;
+    const uint32_t* vals;
+    uint4* out_nodes; float4* out_prims;
+    BuildCounters* ctr;
+};
 
 struct TriSource {       // 3 x float4 per primitive
     const uint8_t* verts; const uint32_t* idx;
@@ -227,15 +290,26 @@ __device__ __forceinline__ int exp_for_extent(float ext) {
     return max(1, min(254, biased));
 }
 
+// sorted positions of the (<= MAX_LEAF) primitives under node id
+__device__ __forceinline__ int collect_prims(const Hier& H, int id, int out[MAX_LEAF]) {
+    int n = 0; int st[4]; int sp = 0; st[sp++] = id;
+    while (sp) {
+        const int m = st[--sp];
+        if (m < H.n) { if (n < MAX_LEAF) out[n++] = m; }
+        else { const int2 c = H.child[m - H.n]; st[sp++] = c.y; st[sp++] = c.x; }
+    }
+    return n;
+}
+
 template <int PRIM_F4, typename Source>
-__device__ void emit_node(const CollapseArgs& A, const Source& src, const int* cid, int cnt, float4 plo, float4 phi,
+__device__ void emit_node(const CollapseArgs& A, const Source& src, const int* cid, const bool* is_leaf, int cnt, float4 plo, float4 phi,
                           uint32_t out_idx, uint2* tasks_out) {
-    const int n = A.n;
+    const Hier& H = A.H;
     // slot assignment: greedy on cost[c][s] = dot(centre_c - centre_parent, sign vector of s)
     float ccx[8], ccy[8], ccz[8];
     const float pcx = 0.5f * (plo.x + phi.x), pcy = 0.5f * (plo.y + phi.y), pcz = 0.5f * (plo.z + phi.z);
     for (int c = 0; c < cnt; c++) {
-        float4 l = A.nlo[cid[c]], h = A.nhi[cid[c]];
+        float4 l = H.nlo[cid[c]], h = H.nhi[cid[c]];
         ccx[c] = 0.5f * (l.x + h.x) - pcx; ccy[c] = 0.5f * (l.y + h.y) - pcy; ccz[c] = 0.5f * (l.z + h.z) - pcz;
     }
     int slot_child[8];
@@ -253,7 +327,6 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
         }
         slot_child[bs] = bc; child_done |= 1u << bc; slot_done |= 1u << bs;
     }
-    // classify + count
     unsigned imask = 0; int n_inner = 0, n_prims = 0;
     int cnt_of[8];
     for (int s = 0; s < 8; s++) {
@@ -261,14 +334,12 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
         int c = slot_child[s];
         if (c < 0) continue;
         int id = cid[c];
-        int pc = (id >= n - 1) ? 1 : (A.range[id].y - A.range[id].x + 1);
-        if (pc > MAX_LEAF) { imask |= 1u << s; n_inner++; }
-        else { cnt_of[s] = pc; n_prims += pc; }
+        if (!is_leaf[c]) { imask |= 1u << s; n_inner++; }
+        else { cnt_of[s] = (id < H.n) ? 1 : H.cnt[id - H.n]; n_prims += cnt_of[s]; }
     }
     const uint32_t child_base = n_inner ? atomicAdd(&A.ctr->nodes, (unsigned)n_inner) : 0u;
     const uint32_t prim_base = n_prims ? atomicAdd(&A.ctr->prims, (unsigned)n_prims) : 0u;
     const uint32_t task_base = n_inner ? atomicAdd(&A.ctr->tasks_out, (unsigned)n_inner) : 0u;
-    // quantisation grid
     const int ex = exp_for_extent(phi.x - plo.x), ey = exp_for_extent(phi.y - plo.y), ez = exp_for_extent(phi.z - plo.z);
     const float sx = __uint_as_float((unsigned)ex << 23), sy = __uint_as_float((unsigned)ey << 23), sz = __uint_as_float((unsigned)ez << 23);
     unsigned char meta[8], qlo[3][8], qhi[3][8];
@@ -279,7 +350,7 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
         int c = slot_child[s];
         if (c < 0) continue;
         int id = cid[c];
-        float4 l = A.nlo[id], h = A.nhi[id];
+        float4 l = H.nlo[id], h = H.nhi[id];
         const float lov[3] = {l.x, l.y, l.z}, hiv[3] = {h.x, h.y, h.z}, pv[3] = {plo.x, plo.y, plo.z}, sv[3] = {sx, sy, sz};
         for (int a = 0; a < 3; a++) {
             int ql = (int)floorf((lov[a] - pv[a]) / sv[a]);
@@ -294,11 +365,11 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
             tasks_out[task_base + inner_rank] = make_uint2((unsigned)id, child_base + inner_rank);
             inner_rank++;
         } else {
-            int pc = cnt_of[s];
+            int pr[MAX_LEAF];
+            const int pc = collect_prims(H, id, pr);
             meta[s] = (unsigned char)((((1u << pc) - 1u) << 5) | (unsigned)prim_off);
-            int first = (id >= n - 1) ? (id - (n - 1)) : A.range[id].x;
             for (int k = 0; k < pc; k++)
-                src.write(A.out_prims + (size_t)(prim_base + prim_off + k) * PRIM_F4, A.vals[first + k]);
+                src.write(A.out_prims + (size_t)(prim_base + prim_off + k) * PRIM_F4, A.vals[pr[k]]);
             prim_off += pc;
         }
     }
@@ -312,30 +383,34 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
     o[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
 }
 
+// One wide node per task: follow the dynamic programme's decisions from the task's hierarchy node with a budget of 8 roots.
 template <int PRIM_F4, typename Source>
 __global__ void k_collapse(CollapseArgs A, Source src, const uint2* __restrict__ tasks_in, unsigned n_in, uint2* tasks_out) {
     unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_in) return;
-    const int n = A.n;
+    const Hier& H = A.H;
     const uint2 task = tasks_in[t];
     const int root = (int)task.x;
-    int cid[8]; int cnt = 2;
-    cid[0] = A.child[root].x; cid[1] = A.child[root].y;
-    while (cnt < 8) {
-        int best = -1; float bestA = -1.0f;
-        for (int c = 0; c < cnt; c++) {
-            int id = cid[c];
-            if (id >= n - 1) continue;
-            if (A.range[id].y - A.range[id].x + 1 <= MAX_LEAF) continue;
-            float a = box_area(A.nlo[id], A.nhi[id]);
-            if (a > bestA) { bestA = a; best = c; }
-        }
-        if (best < 0) break;
-        int id = cid[best];
-        cid[best] = A.child[id].x;
-        cid[cnt++] = A.child[id].y;
+    int cid[8]; bool leaf[8]; int cnt = 0;
+    int st_node[16], st_budget[16]; int sp = 0;
+    {
+        const int2 ch = H.child[root - H.n];
+        const int k = H.dec[(size_t)(root - H.n) * 8 + 7] & 0x7f;
+        st_node[sp] = ch.y; st_budget[sp++] = 8 - k;
+        st_node[sp] = ch.x; st_budget[sp++] = k;
     }
-    emit_node<PRIM_F4, Source>(A, src, cid, cnt, A.nlo[root], A.nhi[root], task.y, tasks_out);
+    while (sp) {
+        const int m = st_node[--sp]; int j = st_budget[sp];
+        if (m < H.n) { cid[cnt] = m; leaf[cnt++] = true; continue; }
+        const unsigned char* D = H.dec + (size_t)(m - H.n) * 8;
+        while (j >= 2 && j <= 7 && (D[j - 1] & 0x80u)) j--;        // C(m,j) = C(m,j-1)
+        if (j == 1) { cid[cnt] = m; leaf[cnt++] = (D[0] != 0); continue; }
+        const int k = D[j - 1] & 0x7f;
+        const int2 ch = H.child[m - H.n];
+        st_node[sp] = ch.y; st_budget[sp++] = j - k;
+        st_node[sp] = ch.x; st_budget[sp++] = k;
+    }
+    emit_node<PRIM_F4, Source>(A, src, cid, leaf, cnt, H.nlo[root], H.nhi[root], task.y, tasks_out);
 }
 
 // n <= MAX_LEAF: one node, one leaf child holding everything
@@ -380,32 +455,61 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
     uint4* d_nodes = (uint4*)nodes_s.p;
     float4* d_prims = (float4*)prims_s.p;
     BuildCounters h_ctr;
+    out->sah_cost = 0.0f;
 
     if (n <= MAX_LEAF) {
         k_single_node<PRIM_F4, Source><<<1, 32, 0, stream>>>(src, d_plo, d_phi, (int)n, d_nodes, d_prims, d_ctr);
     } else {
-        Scratch keys_a, keys_b, vals_a, vals_b, child_s, range_s, parent_s, flags_s, nlo_s, nhi_s, tasks_a, tasks_b, tmp_s;
+        Scratch keys_a, keys_b, vals_a, vals_b, child_s, cnt_s, cost_s, dec_s, nlo_s, nhi_s, cl_a, cl_b, nn_s, val_s, valid_s, pos_s,
+            tasks_a, tasks_b, tmp_s, tmp2_s;
         CKE(keys_a.alloc((size_t)n * 8)); CKE(keys_b.alloc((size_t)n * 8));
         CKE(vals_a.alloc((size_t)n * 4)); CKE(vals_b.alloc((size_t)n * 4));
-        CKE(child_s.alloc((size_t)n * 8)); CKE(range_s.alloc((size_t)n * 8));
-        CKE(parent_s.alloc((size_t)2 * n * 4)); CKE(flags_s.alloc((size_t)n * 4));
+        CKE(child_s.alloc((size_t)n * 8)); CKE(cnt_s.alloc((size_t)n * 4));
+        CKE(cost_s.alloc((size_t)n * 28)); CKE(dec_s.alloc((size_t)n * 8));
         CKE(nlo_s.alloc((size_t)2 * n * 16)); CKE(nhi_s.alloc((size_t)2 * n * 16));
+        CKE(cl_a.alloc((size_t)n * 4)); CKE(cl_b.alloc((size_t)n * 4)); CKE(nn_s.alloc((size_t)n * 4));
+        CKE(val_s.alloc((size_t)n * 4)); CKE(valid_s.alloc((size_t)n * 4)); CKE(pos_s.alloc((size_t)n * 4));
         CKE(tasks_a.alloc((size_t)n * 8)); CKE(tasks_b.alloc((size_t)n * 8));
-        size_t tmp_bytes = 0;
+        size_t tmp_bytes = 0, tmp2_bytes = 0;
         CKE(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
                                             (uint32_t*)vals_a.p, (uint32_t*)vals_b.p, (int)n, 0, 63, stream));
         CKE(tmp_s.alloc(tmp_bytes));
+        CKE(cub::DeviceScan::ExclusiveSum(nullptr, tmp2_bytes, (int*)valid_s.p, (int*)pos_s.p, (int)n, stream));
+        CKE(tmp2_s.alloc(tmp2_bytes));
         k_morton<<<grid(n), TB, 0, stream>>>(d_plo, d_phi, n, d_ctr, (unsigned long long*)keys_a.p, (uint32_t*)vals_a.p);
         CKE(cub::DeviceRadixSort::SortPairs(tmp_s.p, tmp_bytes, (unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
                                             (uint32_t*)vals_a.p, (uint32_t*)vals_b.p, (int)n, 0, 63, stream));
-        k_lbvh<<<grid(n - 1), TB, 0, stream>>>((unsigned long long*)keys_b.p, (int)n, (int2*)child_s.p, (int2*)range_s.p, (int*)parent_s.p);
-        CKE(cudaMemsetAsync(flags_s.p, 0, (size_t)n * 4, stream));
-        k_fit<<<grid(n), TB, 0, stream>>>(d_plo, d_phi, (uint32_t*)vals_b.p, (int)n, (int2*)child_s.p, (int*)parent_s.p,
-                                          (unsigned int*)flags_s.p, (float4*)nlo_s.p, (float4*)nhi_s.p, d_ctr);
+        Hier H;
+        H.nlo = (float4*)nlo_s.p; H.nhi = (float4*)nhi_s.p; H.child = (int2*)child_s.p; H.cnt = (int*)cnt_s.p;
+        H.cost = (float*)cost_s.p; H.dec = (unsigned char*)dec_s.p; H.n = (int)n;
+        int* cin = (int*)cl_a.p; int* cout = (int*)cl_b.p;
+        k_leaf_boxes<<<grid(n), TB, 0, stream>>>(d_plo, d_phi, (uint32_t*)vals_b.p, (int)n, H.nlo, H.nhi, cin, d_ctr);
+        int nc = (int)n;
+        while (nc > 1) {
+            k_ploc_nn<<<grid(nc), TB, 0, stream>>>(cin, nc, H.nlo, H.nhi, (int*)nn_s.p);
+            k_ploc_merge<<<grid(nc), TB, 0, stream>>>(cin, nc, (int*)nn_s.p, H, d_ctr, (int*)val_s.p, (int*)valid_s.p);
+            CKE(cub::DeviceScan::ExclusiveSum(tmp2_s.p, tmp2_bytes, (int*)valid_s.p, (int*)pos_s.p, nc, stream));
+            k_ploc_compact<<<grid(nc), TB, 0, stream>>>((int*)val_s.p, (int*)valid_s.p, (int*)pos_s.p, nc, cout);
+            CKE(cudaMemcpyAsync(&h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, stream));
+            CKE(cudaStreamSynchronize(stream));
+            const int merged = (int)h_ctr.hier_nodes;
+            const int nc_new = (int)n - merged;
+            if (nc_new >= nc) return cudaErrorUnknown;          // no progress: cannot happen (the closest pair is always mutual)
+            nc = nc_new;
+            int* t = cin; cin = cout; cout = t;
+        }
+        int root = 0;
+        CKE(cudaMemcpyAsync(&root, cin, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CKE(cudaStreamSynchronize(stream));
+        float root_cost[7];
+        CKE(cudaMemcpy(root_cost, H.cost + (size_t)(root - (int)n) * 7, sizeof root_cost, cudaMemcpyDeviceToHost));
+        float4 rl, rh;
+        CKE(cudaMemcpy(&rl, H.nlo + root, 16, cudaMemcpyDeviceToHost)); CKE(cudaMemcpy(&rh, H.nhi + root, 16, cudaMemcpyDeviceToHost));
+        const float ra = 2.0f * ((rh.x - rl.x) * (rh.y - rl.y) + (rh.y - rl.y) * (rh.z - rl.z) + (rh.z - rl.z) * (rh.x - rl.x));
+        out->sah_cost = ra > 0.0f ? root_cost[0] / ra : 0.0f;
         CollapseArgs A;
-        A.child = (int2*)child_s.p; A.range = (int2*)range_s.p; A.nlo = (float4*)nlo_s.p; A.nhi = (float4*)nhi_s.p;
-        A.vals = (uint32_t*)vals_b.p; A.n = (int)n; A.out_nodes = d_nodes; A.out_prims = d_prims; A.ctr = d_ctr;
-        uint2 root_task = make_uint2(0u, 0u);
+        A.H = H; A.vals = (uint32_t*)vals_b.p; A.out_nodes = d_nodes; A.out_prims = d_prims; A.ctr = d_ctr;
+        uint2 root_task = make_uint2((unsigned)root, 0u);
         CKE(cudaMemcpyAsync(tasks_a.p, &root_task, sizeof root_task, cudaMemcpyHostToDevice, stream));
         unsigned n_in = 1;
         uint2* tin = (uint2*)tasks_a.p; uint2* tout = (uint2*)tasks_b.p;

@@ -17,6 +17,7 @@ struct Bvh8 {
     uint32_t n_nodes = 0, n_prims = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // padded bounds of everything inside
     float build_ms = 0.0f;
+    float sah_cost = 0.0f;      // SAH cost of the wide tree relative to the root area (c_node = 1, c_prim = 0.3)
 };
 
 // BLAS over an indexed triangle list (vertex stride 28 B, position first).  Returns device allocations owned by the caller.

@@ -92,9 +92,10 @@ __device__ __forceinline__ bool tri_test(const RaySpace& r, float4 a, float4 b, 
         V = (float)(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
         W = (float)(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
     }
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const bool neg = (U < 0.0f) | (V < 0.0f) | (W < 0.0f);
+    const bool pos = (U > 0.0f) | (V > 0.0f) | (W > 0.0f);
     float det = (U + V) + W;
-    if (det == 0.0f) return false;
+    if ((neg & pos) | (det == 0.0f)) return false;
     float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
     float T = (U * Az + V * Bz) + W * Cz;
     float rcp = 1.0f / det;
