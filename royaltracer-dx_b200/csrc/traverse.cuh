@@ -30,6 +30,10 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     return d;
 }
 __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x >> (i * 8)) & 0xffu; }
+// byte i of x as the float 1 + q/256 (mantissa bits 15..22): full-rate integer ops instead of the quarter-rate I2F
+__device__ __forceinline__ float byte_as_unit_float(uint32_t x, int i) {
+    return __uint_as_float(0x3F800000u | (((x >> (i * 8)) & 0xffu) << 15));
+}
 
 struct RaySpace {          // the ray in the space currently traversed + derived constants
     float ox, oy, oz;
@@ -115,7 +119,9 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
     const float ax = __uint_as_float((e & 0xffu) << 23) * r.ix;
     const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * r.iy;
     const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * r.iz;
-    const float bx = (px - r.ox) * r.ix, by = (py - r.oy) * r.iy, bz = (pz - r.oz) * r.iz;
+    // plane = p + q * 2^e  ->  t = (1 + q/256) * (256 a) + (b - 256 a); the rounding of (b - 256 a) is 2^-16 of a grid cell
+    const float ax2 = ax * 256.0f, ay2 = ay * 256.0f, az2 = az * 256.0f;
+    const float bx = (px - r.ox) * r.ix - ax2, by = (py - r.oy) * r.iy - ay2, bz = (pz - r.oz) * r.iz - az2;
     const bool nx = !(r.octinv4 & 1u), ny = !(r.octinv4 & 2u), nz = !(r.octinv4 & 4u);
     uint32_t hitmask = 0;
 #pragma unroll
@@ -132,12 +138,12 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
         const uint32_t zn = nz ? qhiz : qloz, zf = nz ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            float t0x = __fmaf_rn((float)extract_byte(xn, j), ax, bx);
-            float t0y = __fmaf_rn((float)extract_byte(yn, j), ay, by);
-            float t0z = __fmaf_rn((float)extract_byte(zn, j), az, bz);
-            float t1x = __fmaf_rn((float)extract_byte(xf, j), ax, bx);
-            float t1y = __fmaf_rn((float)extract_byte(yf, j), ay, by);
-            float t1z = __fmaf_rn((float)extract_byte(zf, j), az, bz);
+            float t0x = __fmaf_rn(byte_as_unit_float(xn, j), ax2, bx);
+            float t0y = __fmaf_rn(byte_as_unit_float(yn, j), ay2, by);
+            float t0z = __fmaf_rn(byte_as_unit_float(zn, j), az2, bz);
+            float t1x = __fmaf_rn(byte_as_unit_float(xf, j), ax2, bx);
+            float t1y = __fmaf_rn(byte_as_unit_float(yf, j), ay2, by);
+            float t1z = __fmaf_rn(byte_as_unit_float(zf, j), az2, bz);
             float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
             if (tn <= tf) {

@@ -149,3 +149,53 @@ def test_accumulation_reset_on_camera_change(rtdx):
     ctx.render_pass(0, 1)
     assert ctx.read_accum()[..., 3].max() == 1.0
     ctx.close()
+
+
+def test_cuda_path_matches_committed_golden_fixtures(rtdx):
+    """The CUDA path against tests/golden/golden_kat.json (made by tests/golden/make_golden.py from the oracle) — no oracle
+    call at run time."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kat.json")) as f:
+        g = json.load(f)["cornell"]
+    W = H = g["size"]
+    sc = rtdx.scenes.cornell()
+    ctx, up = _upload(rtdx, sc, W, H, bounces=2, flags=rtdx.FLAG_JITTER | rtdx.FLAG_LAMBERT_ONLY, samples_per_pass=2)
+    ctx.reset_counters()
+    ctx.render_pass(0, g["spp"])
+    ctx.synchronize()
+    acc = ctx.read_accum()
+    cnt = ctx.counters()
+    assert cnt["closest_rays"] == g["closest_rays"] and cnt["shadow_rays"] == g["shadow_rays"]
+    assert [int(v) for v in acc.view(np.uint32).reshape(-1)] == g["accum_bits"]
+    hits = ctx.trace(rtdx.scenes.camera_rays(up["camera"], W, H))
+    assert [int(v) for v in hits["prim"]] == g["primary_prim"]
+    ctx.close()
+
+
+def test_full_size_properties_c2(rtdx):
+    """BASELINE config C2 at full size (1M triangles, 1920x1080, bounces 6): size-independent properties instead of an oracle
+    run — determinism (two renders of the same sample are bit-identical), sample counting, ray-count bound 5 + bounces per
+    path, any-hit == closest-exists on the primary rays, and linearity of the accumulation (pass 0 + pass 1 == both)."""
+    sc = rtdx.scenes.mesh_room(n=296)
+    W, H = 1920, 1080
+    ctx, up = _upload(rtdx, sc, W, H, bounces=6)
+    ctx.reset_counters()
+    ctx.render_pass(0, 1); ctx.synchronize()
+    a0 = ctx.read_accum(); c0 = ctx.counters()
+    assert (a0[..., 3] <= 1).all() and a0[..., 3].mean() > 0.999
+    assert c0["paths"] == W * H and c0["closest_rays"] + c0["shadow_rays"] <= c0["paths"] * (5 + 6)
+    ctx.reset_accum(); ctx.render_pass(0, 1); ctx.synchronize()
+    assert np.array_equal(ctx.read_accum().view(np.uint32), a0.view(np.uint32))            # deterministic
+    ctx.render_pass(1, 1); ctx.synchronize()
+    a01 = ctx.read_accum()
+    ctx.reset_accum(); ctx.render_pass(1, 1); ctx.synchronize()
+    a1 = ctx.read_accum()
+    assert np.array_equal((a0 + a1).view(np.uint32), a01.view(np.uint32))                  # accumulation is a plain running sum
+    rays = rtdx.scenes.camera_rays(up["camera"], W, H, step=4)
+    ch, ah = ctx.trace(rays), ctx.trace(rays, any_hit=True)
+    assert np.array_equal(ch["inst"] != rtdx.MISS, ah["inst"] != rtdx.MISS)
+    assert (ch["inst"] != rtdx.MISS).all()                                                  # closed room: every primary ray hits
+    img = ctx.read_output()
+    assert img.shape == (H, W, 4) and (img[..., 3] == 255).all()
+    ctx.close()
