@@ -5,19 +5,22 @@
 // idle lanes as soon as fewer than FETCH_THRESHOLD lanes are still traversing, so long-running incoherent rays do
 // not strand the other 31 lanes (B200 has no RT cores; warp-execution efficiency is the second-order term after
 // memory latency — see DESIGN.md §Kernels).
+#include <stdlib.h>
+
 #include "trace.h"
 #include "traverse.cuh"
 
 namespace rtx {
 
 #define TRACE_BLOCK 128
-#define FETCH_THRESHOLD 24   // refill the warp's idle lanes when fewer than this many lanes are still traversing
+#define FETCH_THRESHOLD 24     // refill the warp's idle lanes when fewer than this many lanes are still traversing
+#define POSTPONE_THRESHOLD 0   // park leaf primitives when fewer than this many lanes are testing them (0 = off)
 
 template <bool ANY_HIT, bool STATS>
 __global__ void __launch_bounds__(TRACE_BLOCK, 4)
 trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restrict__ d_tmax,
              const uint32_t* __restrict__ n_ptr, uint32_t n_fixed, unsigned int* __restrict__ cursor,
-             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st) {
+             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int postpone_th) {
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -48,10 +51,10 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
         const unsigned act = __ballot_sync(0xffffffffu, active);
         if (act == 0u) break;
         // ---- traverse until too few lanes are left (or to the end once the queue is drained)
-        const int threshold = exhausted ? 1 : FETCH_THRESHOLD;
+        const int threshold = exhausted ? 1 : fetch_th;
         do {
             if (active) {
-                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts)) {
+                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts, postpone_th)) {
                     active = false;
                     if (!ANY_HIT) hit_a[j] = make_float4(T.h.t, T.h.b1, T.h.b2, __uint_as_float(T.h.prim));
                     hit_inst[j] = T.h.inst;
@@ -89,13 +92,19 @@ cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d
                          cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    const int grid = num_sms() * 4 * 2;   // 2 waves of resident CTAs: tail balancing is done by the cursor
+    static int fetch_th = -1, postpone_th = -1, waves = -1;
+    if (fetch_th < 0) {   // tuning knobs (defaults are the measured optimum on C2, see profiles/)
+        const char* e = getenv("RTX_FETCH_TH"); fetch_th = e ? atoi(e) : FETCH_THRESHOLD;
+        e = getenv("RTX_POSTPONE_TH"); postpone_th = e ? atoi(e) : POSTPONE_THRESHOLD;
+        e = getenv("RTX_TRACE_WAVES"); waves = e ? atoi(e) : 2;
+    }
+    const int grid = num_sms() * 4 * waves;   // resident CTAs x waves: tail balancing is done by the cursor
     if (stats) {
-        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats);
-        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats);
+        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, postpone_th);
+        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, postpone_th);
     } else {
-        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr);
-        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr);
+        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, postpone_th);
+        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, postpone_th);
     }
     return cudaGetLastError();
 }

@@ -196,10 +196,12 @@ __device__ __forceinline__ void trav_init(Trav& T, const SceneAS& S, float4 o_tm
 // Returns true when the ray is finished.
 template <bool ANY_HIT, bool STATS>
 __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stack, unsigned int* c_nodes, unsigned int* c_tris,
-                                          unsigned int* c_insts) {
+                                          unsigned int* c_insts, int postpone_th) {
     uint2 G = T.G, Gt;
     int sp = T.sp;
+    bool fresh = false;
     if (G.y & 0xff000000u) {
+        fresh = true;
         const uint32_t bit = 31u - __clz(G.y);
         G.y &= ~(1u << bit);
         const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
@@ -220,6 +222,14 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
     }
 
     while (Gt.y != 0u) {
+        // Triangle postponing: when only a few lanes of the warp still have leaf primitives to test, park the group on the
+        // stack and go on with node tests; it is tested when popped (never parked twice), together with more lanes.
+        if (fresh && T.in_blas && (G.y & 0xff000000u) && __popc(__activemask()) < postpone_th) {
+            const uint2 keep = G;
+            RTX_PUSH(Gt);
+            G = keep;
+            break;
+        }
         const uint32_t bit = 31u - __clz(Gt.y);
         Gt.y &= ~(1u << bit);
         if (T.in_blas) {
