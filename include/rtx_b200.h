@@ -116,6 +116,19 @@ rtx_status rtx_get_counters(rtx_ctx*, rtx_counters* out);
 rtx_status rtx_reset_counters(rtx_ctx*);
 /* device time in ms of the traversal kernels / all kernels of the last rtx_render_pass (CUDA events on the ctx stream) */
 rtx_status rtx_last_pass_ms(rtx_ctx*, float* trace_ms, float* total_ms);
+/* the same per stage kind (needs RTX_OPT_STAGE_TIMING): ms_by_stage[RTX_STAGE_*] summed over the launches of the last pass */
+#define RTX_STAGE_GENERATE 0
+#define RTX_STAGE_CLOSEST 1
+#define RTX_STAGE_ANY 2
+#define RTX_STAGE_SHADE_PRIMARY 3
+#define RTX_STAGE_DI_FINISH 4
+#define RTX_STAGE_GI_STEP 5
+#define RTX_STAGE_SCATTER 6
+#define RTX_STAGE_FINALIZE 7
+#define RTX_STAGE_ACCUMULATE 8
+#define RTX_STAGE_SORT 9
+#define RTX_STAGE_COUNT 10
+rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stages, float* total_ms);
 /* runtime options.  RTX_OPT_TRACE_STATS: closest-hit traversals of rtx_render_pass also count nodes/triangles/instances
  * (instrumented kernel variant: for the roofline's B_ray, never for timed runs).  RTX_OPT_STAGE_TIMING: record CUDA events
  * around every traversal launch of a pass so that rtx_last_pass_ms can report the traversal share. */

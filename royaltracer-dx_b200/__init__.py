@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtx_b200.so")
+LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(HERE, "librtx_b200.so")   # the override is for A/B builds of the kernels
 HOST_LIB_PATH = os.path.join(HERE, "librtx_host.so")
 
 # ---------------------------------------------------------------------------------------------- POD layouts
@@ -36,6 +36,7 @@ assert camera_dt.itemsize == 512 and desc_dt.itemsize == 64 and ray_dt.itemsize 
 FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL = 1, 2, 4
 OPT_TRACE_STATS, OPT_STAGE_TIMING = 1, 2
 MISS = 0xFFFFFFFF
+STAGE_NAMES = ["generate", "closest", "any", "shade_primary", "di_finish", "gi_step", "scatter", "finalize", "accumulate", "sort"]
 
 
 class RtxConfig(C.Structure):
@@ -57,7 +58,7 @@ class RtxBlasInfo(C.Structure):
 ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model", "rtx_blas_info_get", "rtx_set_material_ids",
                "rtx_set_materials", "rtx_set_instances", "rtx_set_emissive_triangles", "rtx_set_camera", "rtx_render_pass",
                "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_accum_device_ptr", "rtx_trace",
-               "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_set_option", "rtx_debug_pixel"]
+               "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel"]
 HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut"]
 
 _lib = None
@@ -100,6 +101,7 @@ def load_library():
     lib.rtx_get_counters.argtypes = [vp, C.POINTER(RtxCounters)]
     lib.rtx_reset_counters.argtypes = [vp]
     lib.rtx_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.rtx_last_pass_stage_ms.argtypes = [vp, vp, u32, C.POINTER(C.c_float)]
     lib.rtx_debug_pixel.argtypes = [vp, u32, u32, vp]
     lib.rtx_set_option.argtypes = [vp, u32, u32]
     _lib = lib
@@ -304,6 +306,13 @@ class Context:
         a, b = C.c_float(), C.c_float()
         self._check(self.lib.rtx_last_pass_ms(self.handle, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_pass_stage_ms(self):
+        """{stage name: ms} of the last pass (needs OPT_STAGE_TIMING) and the pass total."""
+        k = np.zeros(len(STAGE_NAMES), dtype=np.float32)
+        t = C.c_float()
+        self._check(self.lib.rtx_last_pass_stage_ms(self.handle, _ptr(k), k.size, C.byref(t)))
+        return {n: float(v) for n, v in zip(STAGE_NAMES, k)}, t.value
 
     def set_option(self, option, value):
         self._check(self.lib.rtx_set_option(self.handle, option, int(value)))

@@ -428,21 +428,38 @@ extern "C" rtx_status rtx_reset_counters(rtx_ctx* c) {
     return RTX_OK;
 }
 
-extern "C" rtx_status rtx_last_pass_ms(rtx_ctx* c, float* trace_ms, float* total_ms) {
-    if (!c) return fail(RTX_ERR_ARG, "null context");
+static rtx_status stage_ms(rtx_ctx* c, float* by_kind, float* total) {
     if (!c->pass_timed) return fail(RTX_ERR_STATE, "rtx_last_pass_ms: no pass rendered yet");
     RTX_CK(cudaSetDevice(c->cfg.device));
     RTX_CK(cudaEventSynchronize(c->timing.ev[1]));
-    float t = 0.0f;
-    RTX_CK(cudaEventElapsedTime(&t, c->timing.ev[0], c->timing.ev[1]));
-    if (total_ms) *total_ms = t;
-    float tr = 0.0f;
-    for (int i = 0; i < c->timing.n_closest; i++) {
+    RTX_CK(cudaEventElapsedTime(total, c->timing.ev[0], c->timing.ev[1]));
+    for (int k = 0; k < SK_COUNT; k++) by_kind[k] = 0.0f;
+    for (int i = 0; i < c->timing.n_marks; i++) {
         float d = 0.0f;
-        RTX_CK(cudaEventElapsedTime(&d, c->timing.ev[2 + 2 * i], c->timing.ev[3 + 2 * i]));
-        tr += d;
+        cudaEvent_t next = (i + 1 < c->timing.n_marks) ? c->timing.ev[3 + i] : c->timing.ev[1];
+        RTX_CK(cudaEventElapsedTime(&d, c->timing.ev[2 + i], next));
+        by_kind[c->timing.kind[i]] += d;
     }
-    if (trace_ms) *trace_ms = tr;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_last_pass_ms(rtx_ctx* c, float* trace_ms, float* total_ms) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    float k[SK_COUNT], t = 0.0f;
+    rtx_status st = stage_ms(c, k, &t);
+    if (st != RTX_OK) return st;
+    if (total_ms) *total_ms = t;
+    if (trace_ms) *trace_ms = k[SK_CLOSEST];
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_last_pass_stage_ms(rtx_ctx* c, float* ms_by_stage, uint32_t n_stages, float* total_ms) {
+    if (!c || !ms_by_stage) return fail(RTX_ERR_ARG, "rtx_last_pass_stage_ms: null argument");
+    float k[SK_COUNT], t = 0.0f;
+    rtx_status st = stage_ms(c, k, &t);
+    if (st != RTX_OK) return st;
+    for (uint32_t i = 0; i < n_stages; i++) ms_by_stage[i] = i < (uint32_t)SK_COUNT ? k[i] : 0.0f;
+    if (total_ms) *total_ms = t;
     return RTX_OK;
 }
 

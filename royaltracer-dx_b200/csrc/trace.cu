@@ -13,14 +13,19 @@
 namespace rtx {
 
 #define TRACE_BLOCK 128
+#ifndef RTX_TRACE_MINB
+#define RTX_TRACE_MINB 4       // resident CTAs per SM the register budget is set for
+#endif
 #define FETCH_THRESHOLD 24     // refill the warp's idle lanes when fewer than this many lanes are still traversing
-#define POSTPONE_THRESHOLD 0   // park leaf primitives when fewer than this many lanes are testing them (0 = off)
+#ifndef RTX_FETCH_CHUNK
+#define RTX_FETCH_CHUNK 96     // rays a warp claims from the global cursor with one atomic
+#endif
 
 template <bool ANY_HIT, bool STATS>
-__global__ void __launch_bounds__(TRACE_BLOCK, 4)
+__global__ void __launch_bounds__(TRACE_BLOCK, RTX_TRACE_MINB)
 trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restrict__ d_tmax,
              const uint32_t* __restrict__ n_ptr, uint32_t n_fixed, unsigned int* __restrict__ cursor,
-             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int postpone_th) {
+             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th) {
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -29,32 +34,54 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     bool active = false;
     bool exhausted = (S.n_instances == 0u);
     uint32_t j = 0;
+    // the warp's private pool of claimed rays [pool_next, pool_end) and one chunk claimed ahead of need (its atomic
+    // is in flight while the warp traverses): all warp-uniform
+    uint32_t pool_next = 0, pool_end = 0, ahead = 0;
+    bool have_ahead = false;
     unsigned int c_nodes = 0, c_tris = 0, c_insts = 0;
 
     for (;;) {
-        // ---- refill idle lanes: one atomic per warp claims a run of consecutive rays
+        // ---- refill idle lanes from the pool
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted) {
-            const int leader = __ffs(idle) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!active) {
-                j = base + __popc(idle & lt_mask);
-                if (j < n) {
-                    trav_init(T, S, __ldg(o_tmin + j), __ldg(d_tmax + j));
-                    active = true;
+            uint32_t need = (uint32_t)__popc(idle);
+            const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
+            uint32_t take = min(need, pool_end - pool_next);
+            uint32_t mine = pool_next + rank;
+            pool_next += take;
+            if (take < need) {                                   // pool empty: switch to the chunk claimed ahead (or claim one now)
+                if (!have_ahead) { if (lane == 0) ahead = atomicAdd(cursor, (unsigned)RTX_FETCH_CHUNK); }
+                const uint32_t base = __shfl_sync(0xffffffffu, ahead, 0);
+                have_ahead = false;
+                if (base >= n) { exhausted = true; pool_next = pool_end = 0; need = take; }
+                else {
+                    pool_end = min(base + (uint32_t)RTX_FETCH_CHUNK, n);
+                    const uint32_t take2 = min(need - take, pool_end - base);
+                    if (rank >= take) mine = base + (rank - take);
+                    pool_next = base + take2;
+                    need = take + take2;
                 }
             }
-            if (base + __popc(idle) >= n) exhausted = true;
+            if (!active && rank < need) {
+                j = mine;
+                trav_init(T, S, __ldg(o_tmin + j), __ldg(d_tmax + j));
+                active = true;
+            }
+            if (!exhausted && !have_ahead && pool_end - pool_next < 32u) {   // claim the next chunk now, use it later
+                if (lane == 0) ahead = atomicAdd(cursor, (unsigned)RTX_FETCH_CHUNK);
+                have_ahead = true;
+            }
         }
         const unsigned act = __ballot_sync(0xffffffffu, active);
-        if (act == 0u) break;
+        if (act == 0u) {
+            if (exhausted) break;
+            continue;
+        }
         // ---- traverse until too few lanes are left (or to the end once the queue is drained)
         const int threshold = exhausted ? 1 : fetch_th;
         do {
             if (active) {
-                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts, postpone_th)) {
+                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts)) {
                     active = false;
                     if (!ANY_HIT) hit_a[j] = make_float4(T.h.t, T.h.b1, T.h.b2, __uint_as_float(T.h.prim));
                     hit_inst[j] = T.h.inst;
@@ -92,19 +119,18 @@ cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d
                          cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    static int fetch_th = -1, postpone_th = -1, waves = -1;
+    static int fetch_th = -1, waves = -1;
     if (fetch_th < 0) {   // tuning knobs (defaults are the measured optimum on C2, see profiles/)
         const char* e = getenv("RTX_FETCH_TH"); fetch_th = e ? atoi(e) : FETCH_THRESHOLD;
-        e = getenv("RTX_POSTPONE_TH"); postpone_th = e ? atoi(e) : POSTPONE_THRESHOLD;
-        e = getenv("RTX_TRACE_WAVES"); waves = e ? atoi(e) : 2;
+        e = getenv("RTX_TRACE_WAVES"); waves = e ? atoi(e) : 1;
     }
-    const int grid = num_sms() * 4 * waves;   // resident CTAs x waves: tail balancing is done by the cursor
+    const int grid = num_sms() * RTX_TRACE_MINB * waves;   // persistent: resident CTAs (x waves); the cursor balances the tail
     if (stats) {
-        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, postpone_th);
-        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, postpone_th);
+        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th);
+        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th);
     } else {
-        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, postpone_th);
-        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, postpone_th);
+        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th);
+        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th);
     }
     return cudaGetLastError();
 }

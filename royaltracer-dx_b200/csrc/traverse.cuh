@@ -10,6 +10,13 @@
 //   * any-hit returns as soon as one triangle is hit.
 // The ray/triangle test is the watertight edge-function test; its operation order is part of the contract
 // (hit IDs are compared bit-exactly against the CPU oracle).  Box tests only have to be conservative.
+//
+// Instruction-level notes (ncu, profiles/r01_trace_hotspots_*.txt): the kernel is issue-bound, so the inner loops
+// are written for instruction count and for the fma/alu pipe split of sm_100 —
+//   * quantised plane bytes become floats with ONE byte-permute each (1 + q*2^-15 in the mantissa), the small extra
+//     rounding this costs is covered by widening the slab interval by 2^-23 |A|;
+//   * the Woop axis permutation uses predicated selects from a one-hot mask (no branches, no register copies);
+//   * leaving a BLAS is detected by the stack depth (no sentinel entry, no pop loop).
 #pragma once
 #include "common.cuh"
 
@@ -24,22 +31,37 @@ __device__ unsigned int g_stack_overflow;
         else g_stack_overflow = 1u;                                   \
     } while (0)
 
+#ifndef RTX_CONV_MODE
+#define RTX_CONV_MODE 1     // 0: shift+or (1 + q/256), 1: byte permute (1 + q*2^-15), 2: fp16 pairs (1024 + q)
+#endif
+
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
     return d;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x >> (i * 8)) & 0xffu; }
-// byte i of x as the float 1 + q/256 (mantissa bits 15..22): full-rate integer ops instead of the quarter-rate I2F
-__device__ __forceinline__ float byte_as_unit_float(uint32_t x, int i) {
-    return __uint_as_float(0x3F800000u | (((x >> (i * 8)) & 0xffu) << 15));
+
+// byte i of x as a float that is affine in q (see RTX_CONV_MODE); the matching (scale, offset) are in plane_coeffs()
+template <int I>
+__device__ __forceinline__ float plane_byte(uint32_t x) {
+#if RTX_CONV_MODE == 0
+    return __uint_as_float(0x3F800000u | (((x >> (I * 8)) & 0xffu) << 15));     // 1 + q/256
+#else
+    return __uint_as_float(prmt(x, 0x3F800000u, 0x7604u | (I << 4)));            // 0x3F80qq00 = 1 + q*2^-15
+#endif
 }
 
 struct RaySpace {          // the ray in the space currently traversed + derived constants
     float ox, oy, oz;
     float ix, iy, iz;      // approximate reciprocal direction, clamped away from 0 (box tests only: conservative, not reproducible)
     float Sx, Sy, Sz;      // watertight shear constants (BLAS space only)
-    uint32_t k;            // kx | ky<<2 | kz<<4
+    uint32_t ksel;         // one-hot axis selectors: bit (3a + c) set iff k_a == c, a = 0 (kx), 1 (ky), 2 (kz)
     uint32_t octinv4;      // (dx>=0 | dy>=0 <<1 | dz>=0 <<2) * 0x01010101
 };
 
@@ -71,23 +93,49 @@ __device__ __forceinline__ void setup_tri(RaySpace& r, float dx, float dy, float
     uint32_t kx = (kz == 2u) ? 0u : kz + 1u, ky = (kx == 2u) ? 0u : kx + 1u;
     const float dkz = sel3(dx, dy, dz, kz);
     if (dkz < 0.0f) { const uint32_t t = kx; kx = ky; ky = t; }
-    r.k = kx | (ky << 2) | (kz << 4);
+    r.ksel = (1u << kx) | (8u << ky) | (64u << kz);
     r.Sz = 1.0f / dkz;
     r.Sx = sel3(dx, dy, dz, kx) * r.Sz;
     r.Sy = sel3(dx, dy, dz, ky) * r.Sz;
 }
 
+// (v[kx], v[ky], v[kz]) for the three vertices at once: 6 mask tests + 18 predicated selects, no branches.
+__device__ __forceinline__ void permute_axes(uint32_t ksel, float ax, float ay, float az, float bx, float by, float bz, float cx, float cy,
+                                             float cz, float& Ax, float& Ay, float& Az, float& Bx, float& By, float& Bz, float& Cx,
+                                             float& Cy, float& Cz) {
+    asm("{\n\t"
+        ".reg .pred x0, x1, y0, y1, z0, z1;\n\t"
+        ".reg .b32 m;\n\t"
+        ".reg .f32 t;\n\t"
+        "and.b32 m, %18, 1;   setp.ne.u32 x0, m, 0;\n\t"
+        "and.b32 m, %18, 2;   setp.ne.u32 x1, m, 0;\n\t"
+        "and.b32 m, %18, 8;   setp.ne.u32 y0, m, 0;\n\t"
+        "and.b32 m, %18, 16;  setp.ne.u32 y1, m, 0;\n\t"
+        "and.b32 m, %18, 64;  setp.ne.u32 z0, m, 0;\n\t"
+        "and.b32 m, %18, 128; setp.ne.u32 z1, m, 0;\n\t"
+        "selp.f32 t, %10, %11, x1; selp.f32 %0, %9, t, x0;\n\t"
+        "selp.f32 t, %10, %11, y1; selp.f32 %1, %9, t, y0;\n\t"
+        "selp.f32 t, %10, %11, z1; selp.f32 %2, %9, t, z0;\n\t"
+        "selp.f32 t, %13, %14, x1; selp.f32 %3, %12, t, x0;\n\t"
+        "selp.f32 t, %13, %14, y1; selp.f32 %4, %12, t, y0;\n\t"
+        "selp.f32 t, %13, %14, z1; selp.f32 %5, %12, t, z0;\n\t"
+        "selp.f32 t, %16, %17, x1; selp.f32 %6, %15, t, x0;\n\t"
+        "selp.f32 t, %16, %17, y1; selp.f32 %7, %15, t, y0;\n\t"
+        "selp.f32 t, %16, %17, z1; selp.f32 %8, %15, t, z0;\n\t"
+        "}"
+        : "=f"(Ax), "=f"(Ay), "=f"(Az), "=f"(Bx), "=f"(By), "=f"(Bz), "=f"(Cx), "=f"(Cy), "=f"(Cz)
+        : "f"(ax), "f"(ay), "f"(az), "f"(bx), "f"(by), "f"(bz), "f"(cx), "f"(cy), "f"(cz), "r"(ksel));
+}
+
 // Watertight ray/triangle test; identical operation order to oracle/rtx_oracle.cpp tri_test().
 __device__ __forceinline__ bool tri_test(const RaySpace& r, float4 a, float4 b, float4 c, float tmin, float tmax,
                                          float& t, float& b1, float& b2) {
-    const uint32_t kx = r.k & 3u, ky = (r.k >> 2) & 3u, kz = r.k >> 4;
-    float Ax_ = a.x - r.ox, Ay_ = a.y - r.oy, Az_ = a.z - r.oz;
-    float Bx_ = b.x - r.ox, By_ = b.y - r.oy, Bz_ = b.z - r.oz;
-    float Cx_ = c.x - r.ox, Cy_ = c.y - r.oy, Cz_ = c.z - r.oz;
-    float Akz = sel3(Ax_, Ay_, Az_, kz), Bkz = sel3(Bx_, By_, Bz_, kz), Ckz = sel3(Cx_, Cy_, Cz_, kz);
-    float Ax = sel3(Ax_, Ay_, Az_, kx) - r.Sx * Akz, Ay = sel3(Ax_, Ay_, Az_, ky) - r.Sy * Akz;
-    float Bx = sel3(Bx_, By_, Bz_, kx) - r.Sx * Bkz, By = sel3(Bx_, By_, Bz_, ky) - r.Sy * Bkz;
-    float Cx = sel3(Cx_, Cy_, Cz_, kx) - r.Sx * Ckz, Cy = sel3(Cx_, Cy_, Cz_, ky) - r.Sy * Ckz;
+    float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
+    permute_axes(r.ksel, a.x - r.ox, a.y - r.oy, a.z - r.oz, b.x - r.ox, b.y - r.oy, b.z - r.oz, c.x - r.ox, c.y - r.oy, c.z - r.oz,
+                 Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz);
+    float Ax = Akx - r.Sx * Akz, Ay = Aky - r.Sy * Akz;
+    float Bx = Bkx - r.Sx * Bkz, By = Bky - r.Sy * Bkz;
+    float Cx = Ckx - r.Sx * Ckz, Cy = Cky - r.Sy * Ckz;
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -119,9 +167,23 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
     const float ax = __uint_as_float((e & 0xffu) << 23) * r.ix;
     const float ay = __uint_as_float(((e >> 8) & 0xffu) << 23) * r.iy;
     const float az = __uint_as_float(((e >> 16) & 0xffu) << 23) * r.iz;
-    // plane = p + q * 2^e  ->  t = (1 + q/256) * (256 a) + (b - 256 a); the rounding of (b - 256 a) is 2^-16 of a grid cell
-    const float ax2 = ax * 256.0f, ay2 = ay * 256.0f, az2 = az * 256.0f;
+    // plane = p + q * 2^e  ->  t = F(q) * A + B with F(q) = 1 + q/S the float plane_byte() builds, A = S a, B = b - A.
+#if RTX_CONV_MODE == 0
+    const float SC = 256.0f;
+#else
+    const float SC = 32768.0f;
+#endif
+    const float ax2 = ax * SC, ay2 = ay * SC, az2 = az * SC;
     const float bx = (px - r.ox) * r.ix - ax2, by = (py - r.oy) * r.iy - ay2, bz = (pz - r.oz) * r.iz - az2;
+#if RTX_CONV_MODE == 0
+    // the rounding of (b - 256 a) is 2^-16 of a grid cell: inside the builder's padding
+    const float bxn = bx, bxf = bx, byn = by, byf = by, bzn = bz, bzf = bz;
+#else
+    // the rounding of (b - 2^15 a) is up to 2^-9 of a grid cell: widen the slab interval by 2^-23 |A| (= 2^-8 cell) instead
+    const float w = 1.1920929e-7f, fx = fabsf(ax2), fy = fabsf(ay2), fz = fabsf(az2);
+    const float bxn = __fmaf_rn(fx, -w, bx), bxf = __fmaf_rn(fx, w, bx), byn = __fmaf_rn(fy, -w, by), byf = __fmaf_rn(fy, w, by);
+    const float bzn = __fmaf_rn(fz, -w, bz), bzf = __fmaf_rn(fz, w, bz);
+#endif
     const bool nx = !(r.octinv4 & 1u), ny = !(r.octinv4 & 2u), nz = !(r.octinv4 & 4u);
     uint32_t hitmask = 0;
 #pragma unroll
@@ -136,20 +198,20 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
         const uint32_t xn = nx ? qhix : qlox, xf = nx ? qlox : qhix;
         const uint32_t yn = ny ? qhiy : qloy, yf = ny ? qloy : qhiy;
         const uint32_t zn = nz ? qhiz : qloz, zf = nz ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float t0x = __fmaf_rn(byte_as_unit_float(xn, j), ax2, bx);
-            float t0y = __fmaf_rn(byte_as_unit_float(yn, j), ay2, by);
-            float t0z = __fmaf_rn(byte_as_unit_float(zn, j), az2, bz);
-            float t1x = __fmaf_rn(byte_as_unit_float(xf, j), ax2, bx);
-            float t1y = __fmaf_rn(byte_as_unit_float(yf, j), ay2, by);
-            float t1z = __fmaf_rn(byte_as_unit_float(zf, j), az2, bz);
-            float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-            float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-            if (tn <= tf) {
-                hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
-            }
+#define RTX_CHILD(J)                                                                                         \
+        {                                                                                                    \
+            float t0x = __fmaf_rn(plane_byte<J>(xn), ax2, bxn);                                              \
+            float t0y = __fmaf_rn(plane_byte<J>(yn), ay2, byn);                                              \
+            float t0z = __fmaf_rn(plane_byte<J>(zn), az2, bzn);                                              \
+            float t1x = __fmaf_rn(plane_byte<J>(xf), ax2, bxf);                                              \
+            float t1y = __fmaf_rn(plane_byte<J>(yf), ay2, byf);                                              \
+            float t1z = __fmaf_rn(plane_byte<J>(zf), az2, bzf);                                              \
+            float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                                             \
+            float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                             \
+            if (tn <= tf) hitmask |= extract_byte(child_bits4, J) << extract_byte(bit_index4, J);            \
         }
+        RTX_CHILD(0) RTX_CHILD(1) RTX_CHILD(2) RTX_CHILD(3)
+#undef RTX_CHILD
     }
     return hitmask;
 }
@@ -171,37 +233,34 @@ __device__ __forceinline__ bool hit_better(float t, uint32_t inst, uint32_t prim
 struct Trav {
     RaySpace r;                 // current space
     float wox, woy, woz, wdx, wdy, wdz;   // world-space ray
-    float wix, wiy, wiz; uint32_t woct4;   // world-space box-test constants (restored when a BLAS is left)
     float tmin, tmax;
     HitRec h;
     const uint4* nodes; const float4* prims;
     uint2 G;
     uint32_t cur_inst;
     int sp;
-    bool in_blas;
+    int blas_sp;                // stack depth at which the current BLAS was entered; -1 while in the TLAS
 };
 
 __device__ __forceinline__ void trav_init(Trav& T, const SceneAS& S, float4 o_tmin, float4 d_tmax) {
     T.wox = o_tmin.x; T.woy = o_tmin.y; T.woz = o_tmin.z; T.wdx = d_tmax.x; T.wdy = d_tmax.y; T.wdz = d_tmax.z;
     T.tmin = o_tmin.w; T.tmax = d_tmax.w;
     setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
-    T.wix = T.r.ix; T.wiy = T.r.iy; T.wiz = T.r.iz; T.woct4 = T.r.octinv4;
     T.h.t = d_tmax.w; T.h.b1 = 0.0f; T.h.b2 = 0.0f; T.h.prim = 0xFFFFFFFFu; T.h.inst = 0xFFFFFFFFu;
     T.nodes = S.tlas_nodes; T.prims = S.inst_recs;
     T.G = make_uint2(0u, 0x80000000u);
-    T.cur_inst = 0; T.sp = 0; T.in_blas = false;
+    T.cur_inst = 0; T.sp = 0; T.blas_sp = -1;
 }
 
 // One traversal step: at most one node intersection, then the node's leaf primitives, then a pop.
 // Returns true when the ray is finished.
 template <bool ANY_HIT, bool STATS>
 __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stack, unsigned int* c_nodes, unsigned int* c_tris,
-                                          unsigned int* c_insts, int postpone_th) {
-    uint2 G = T.G, Gt;
+                                          unsigned int* c_insts) {
+    uint2 G = T.G;
+    uint32_t leaf_base, leaf_bits;
     int sp = T.sp;
-    bool fresh = false;
     if (G.y & 0xff000000u) {
-        fresh = true;
         const uint32_t bit = 31u - __clz(G.y);
         G.y &= ~(1u << bit);
         const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
@@ -213,76 +272,65 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
         if (STATS) (*c_nodes)++;
         const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t);
         G.x = n1.x;
-        Gt.x = n1.y;
         G.y = (hm & 0xff000000u) | (n0.w >> 24);
-        Gt.y = hm & 0x00ffffffu;
-    } else {
-        Gt = G;
+        leaf_base = n1.y;
+        leaf_bits = hm & 0x00ffffffu;
+    } else {                                   // a leaf group that was parked on the stack
+        leaf_base = G.x; leaf_bits = G.y;
         G = make_uint2(0u, 0u);
     }
 
-    while (Gt.y != 0u) {
-        // Triangle postponing: when only a few lanes of the warp still have leaf primitives to test, park the group on the
-        // stack and go on with node tests; it is tested when popped (never parked twice), together with more lanes.
-        if (fresh && T.in_blas && (G.y & 0xff000000u) && __popc(__activemask()) < postpone_th) {
-            const uint2 keep = G;
-            RTX_PUSH(Gt);
-            G = keep;
-            break;
-        }
-        const uint32_t bit = 31u - __clz(Gt.y);
-        Gt.y &= ~(1u << bit);
-        if (T.in_blas) {
-            const float4* tp = T.prims + (size_t)(Gt.x + bit) * 3;
+    if (T.blas_sp >= 0) {
+        while (leaf_bits != 0u) {
+            const uint32_t bit = 31u - __clz(leaf_bits);
+            leaf_bits &= ~(1u << bit);
+            const float4* tp = T.prims + (size_t)(leaf_base + bit) * 3;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (STATS) (*c_tris)++;
             float t, b1, b2;
             if (tri_test(T.r, a, b, c, T.tmin, T.tmax, t, b1, b2)) {
                 const uint32_t prim = __float_as_uint(a.w);
                 if (ANY_HIT) {
-                    T.h.t = t; T.h.b1 = b1; T.h.b2 = b2; T.h.prim = prim; T.h.inst = T.cur_inst;
+                    T.h.inst = T.cur_inst;
                     return true;
                 }
                 if (T.h.inst == 0xFFFFFFFFu || hit_better(t, T.cur_inst, prim, T.h)) {
                     T.h.t = t; T.h.b1 = b1; T.h.b2 = b2; T.h.prim = prim; T.h.inst = T.cur_inst;
                 }
             }
-        } else {
-            // instance leaf: enter the BLAS.  Save what is left of this level, then a sentinel.
-            const float4* ip = T.prims + (size_t)(Gt.x + bit) * 4;
-            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-            if (STATS) (*c_insts)++;
-            if (Gt.y) RTX_PUSH(Gt);
-            if (G.y & 0xff000000u) RTX_PUSH(G);
-            RTX_PUSH(make_uint2(0xffffffffu, 0u));
-            const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
-            const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
-            const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
-            const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
-            const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
-            const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
-            setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
-            setup_tri(T.r, tdx, tdy, tdz);
-            const BlasRef br = S.blas[__float_as_uint(r3.x)];
-            T.nodes = br.nodes; T.prims = br.tris;
-            T.cur_inst = __float_as_uint(r3.y);
-            T.in_blas = true;
-            G = make_uint2(0u, 0x80000000u);
-            break;
         }
+    } else if (leaf_bits != 0u) {
+        // instance leaf: enter the BLAS.  What is left of this level goes to the stack; the BLAS is left again when the
+        // stack is back at this depth.
+        const uint32_t bit = 31u - __clz(leaf_bits);
+        leaf_bits &= ~(1u << bit);
+        const float4* ip = T.prims + (size_t)(leaf_base + bit) * 4;
+        const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+        if (STATS) (*c_insts)++;
+        if (leaf_bits) RTX_PUSH(make_uint2(leaf_base, leaf_bits));
+        if (G.y & 0xff000000u) RTX_PUSH(G);
+        T.blas_sp = sp;
+        const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
+        const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
+        const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
+        const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
+        const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
+        const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
+        setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
+        setup_tri(T.r, tdx, tdy, tdz);
+        const BlasRef br = S.blas[__float_as_uint(r3.x)];
+        T.nodes = br.nodes; T.prims = br.tris;
+        T.cur_inst = __float_as_uint(r3.y);
+        G = make_uint2(0u, 0x80000000u);
     }
 
-    if ((G.y & 0xff000000u) == 0u) {
-        for (;;) {   // pop
-            if (sp == 0) { T.sp = 0; return true; }
-            G = stack[--sp];
-            if (G.x == 0xffffffffu && G.y == 0u) {   // sentinel: back to the TLAS / world space
-                T.r.ox = T.wox; T.r.oy = T.woy; T.r.oz = T.woz; T.r.ix = T.wix; T.r.iy = T.wiy; T.r.iz = T.wiz; T.r.octinv4 = T.woct4;
-                T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.in_blas = false;
-                continue;
-            }
-            break;
+    if ((G.y & 0xff000000u) == 0u) {           // pop
+        if (sp == T.blas_sp) {                 // the BLAS is exhausted: back to the TLAS / world space
+            setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
+            T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.blas_sp = -1;
         }
+        if (sp == 0) { T.sp = 0; return true; }
+        G = stack[--sp];
     }
     T.G = G; T.sp = sp;
     return false;

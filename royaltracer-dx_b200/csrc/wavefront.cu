@@ -544,51 +544,59 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     StateView st{B.state, n};
     const unsigned grid = (n + WF_BLOCK - 1) / WF_BLOCK;
     uint64_t L = 0;
-    T->n_closest = 0; T->n_shadow = 0;
-    int ev_next = 2;
-    int shadow_ev[4]; int n_shadow_ev = 0;
-    auto closest = [&](const RayQueue& q) -> cudaError_t {
-        const bool timed = T->stage_timing && ev_next + 2 <= WAVE_MAX_EVENTS - 4;
-        if (timed) CKE(cudaEventRecord(T->ev[ev_next], stream));
-        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, false, T->stats, stream)); L++;
-        if (timed) { CKE(cudaEventRecord(T->ev[ev_next + 1], stream)); ev_next += 2; T->n_closest++; }
+    T->n_marks = 0;
+    auto mark = [&](StageKind k) -> cudaError_t {       // per-launch CUDA events (RTX_OPT_STAGE_TIMING only)
+        if (T->stage_timing && T->n_marks + 2 < WAVE_MAX_EVENTS) {
+            T->kind[T->n_marks] = (unsigned char)k;
+            CKE(cudaEventRecord(T->ev[2 + T->n_marks], stream));
+            T->n_marks++;
+        }
+        L++;
         return cudaSuccess;
+    };
+    auto closest = [&](const RayQueue& q) -> cudaError_t {
+        CKE(mark(SK_CLOSEST));
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, false, T->stats, stream);
     };
     auto shadow = [&](const RayQueue& q, float* vis) -> cudaError_t {
-        const bool timed = T->stage_timing && n_shadow_ev + 2 <= 4;
-        if (timed) CKE(cudaEventRecord(T->ev[WAVE_MAX_EVENTS - 4 + n_shadow_ev], stream));
-        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream)); L++;
-        if (timed) { CKE(cudaEventRecord(T->ev[WAVE_MAX_EVENTS - 4 + n_shadow_ev + 1], stream)); n_shadow_ev += 2; T->n_shadow++; }
-        k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(q.count, q.pid, B.hit_inst, vis); L++;
+        CKE(mark(SK_ANY));
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream));
+        CKE(mark(SK_SCATTER));
+        k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(q.count, q.pid, B.hit_inst, vis);
         return cudaSuccess;
     };
-    (void)shadow_ev;
     CKE(cudaMemsetAsync(B.counts, 0, 128 * 4, stream));
     // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
     RayQueue q0 = B.q[0], q1 = B.q[1], sdi = B.sq[0], sgi = B.sq[1];
     q0.count = B.counts + 0; q1.count = B.counts + 1; sdi.count = B.counts + 2; sgi.count = B.counts + 3;
     CKE(cudaEventRecord(T->ev[0], stream));
-    k_generate<<<grid, WF_BLOCK, 0, stream>>>(st, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi, B.ray_counters); L++;
+    CKE(mark(SK_GENERATE));
+    k_generate<<<grid, WF_BLOCK, 0, stream>>>(st, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi, B.ray_counters);
     CKE(closest(q0));
-    k_shade_primary<<<grid, WF_BLOCK, 0, stream>>>(st, S, q0, B.hit_a, B.hit_inst, q1, B.ray_counters); L++;
+    CKE(mark(SK_SHADE_PRIMARY));
+    k_shade_primary<<<grid, WF_BLOCK, 0, stream>>>(st, S, q0, B.hit_a, B.hit_inst, q1, B.ray_counters);
     CKE(closest(q1));
     RayQueue qa = B.q[0]; qa.count = B.counts + 4;
-    k_di_finish<<<grid, WF_BLOCK, 0, stream>>>(st, S, q1, B.hit_a, B.hit_inst, sdi, qa, B.ray_counters); L++;
+    CKE(mark(SK_DI_FINISH));
+    k_di_finish<<<grid, WF_BLOCK, 0, stream>>>(st, S, q1, B.hit_a, B.hit_inst, sdi, qa, B.ray_counters);
     CKE(shadow(sdi, B.vis_di));                 // DI visibility (connect); hit_inst is reused by the next closest trace
     CKE(closest(qa));
     int cur = 0;
     RayQueue qin = qa;
     for (uint32_t iter = 0; iter <= S.bounces; iter++) {
         RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
-        k_gi_step<<<grid, WF_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters); L++;
+        CKE(mark(SK_GI_STEP));
+        k_gi_step<<<grid, WF_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
         if (iter < S.bounces) {
             CKE(closest(qout));
             qin = qout; cur ^= 1;
         }
     }
     CKE(shadow(sgi, B.vis_gi));
-    k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters); L++;
-    k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum); L++;
+    CKE(mark(SK_FINALIZE));
+    k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters);
+    CKE(mark(SK_ACCUMULATE));
+    k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
     CKE(cudaEventRecord(T->ev[1], stream));
     CKE(cudaGetLastError());
     if (launches) *launches += L;

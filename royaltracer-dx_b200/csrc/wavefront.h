@@ -52,10 +52,12 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
 void wave_free(WaveBuffers* B);
 
 #define WAVE_MAX_EVENTS 96
+// stage kinds of rtx_last_pass_stage_ms (include/rtx_b200.h RTX_STAGE_*)
+enum StageKind { SK_GENERATE = 0, SK_CLOSEST, SK_ANY, SK_SHADE_PRIMARY, SK_DI_FINISH, SK_GI_STEP, SK_SCATTER, SK_FINALIZE, SK_ACCUMULATE, SK_SORT, SK_COUNT };
 struct PassTiming {
-    cudaEvent_t ev[WAVE_MAX_EVENTS] = {};   // [0],[1] bracket the pass; pairs from [2] bracket closest-hit traversal launches,
-    int n_closest = 0;                 // then pairs bracketing any-hit launches
-    int n_shadow = 0;
+    cudaEvent_t ev[WAVE_MAX_EVENTS] = {};   // [0],[1] bracket the pass; with stage_timing, ev[2+i] is recorded before launch i
+    unsigned char kind[WAVE_MAX_EVENTS] = {};
+    int n_marks = 0;
     bool stage_timing = false;
     TraceStats* stats = nullptr;       // non-null: use the counting traversal variant
 };
