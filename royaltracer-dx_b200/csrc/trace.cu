@@ -14,11 +14,11 @@ namespace rtx {
 
 #define TRACE_BLOCK 128
 #ifndef RTX_TRACE_MINB
-#define RTX_TRACE_MINB 4       // resident CTAs per SM the register budget is set for
+#define RTX_TRACE_MINB 6       // resident CTAs per SM the register budget is set for
 #endif
-#define FETCH_THRESHOLD 24     // refill the warp's idle lanes when fewer than this many lanes are still traversing
+#define FETCH_THRESHOLD 20     // refill the warp's idle lanes when fewer than this many lanes are still traversing
 #ifndef RTX_FETCH_CHUNK
-#define RTX_FETCH_CHUNK 96     // rays a warp claims from the global cursor with one atomic
+#define RTX_FETCH_CHUNK 32     // rays a warp claims from the global cursor with one atomic
 #endif
 
 template <bool ANY_HIT, bool STATS>

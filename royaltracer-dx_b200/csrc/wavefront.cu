@@ -22,6 +22,9 @@ namespace rtx {
     } while (0)
 
 #define WF_BLOCK 128
+#ifndef RTX_GI_MINB
+#define RTX_GI_MINB 8       // resident CTAs per SM the register budget of k_gi_step is set for
+#endif
 
 struct StateView {
     float4* base; uint32_t n;
@@ -273,7 +276,7 @@ __device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_l
 // ---- stage: one step of the indirect path (Path_Sampler_v7.hlsl:54-269 + Sampler_v7.hlsl:436-504).
 // iter == 0 consumes the hit of the initial indirect ray; iter >= 1 consumes the BSDF ray of loop iteration iter-1.
 // If the path goes on and iter < bounces it runs iteration `iter`'s NEE candidates and emits its BSDF ray.
-__global__ void __launch_bounds__(WF_BLOCK, 4)
+__global__ void __launch_bounds__(WF_BLOCK, RTX_GI_MINB)
 k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
           RayQueue q_shadow, RayQueue qout, uint32_t iter, unsigned long long* ray_counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
