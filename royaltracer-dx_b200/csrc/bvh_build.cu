@@ -130,7 +130,9 @@ __global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict
 //   C_inner(m) = A_m * c_node + C_dist(m,8),  C_dist(m,j) = min_k C(left,k) + C(right,j-k),  C_leaf(m) = A_m * P_m * c_prim (P_m <= 3)
 #define PLOC_RADIUS 16
 #define C_NODE 1.0f
+#ifndef C_PRIM
 #define C_PRIM 0.3f
+#endif
 
 struct Hier {
     float4* nlo; float4* nhi;       // boxes of all 2n-1 nodes

@@ -24,6 +24,11 @@ ctx.upload_scene(sc)
 for p in range(3):
     ctx.render_pass(p, 1)
 ctx.synchronize()
+ctx.reset_counters(); ctx.set_option(rtdx.OPT_TRACE_STATS, 1)
+ctx.render_pass(0, 1); ctx.synchronize()
+s0 = ctx.counters(); ctx.set_option(rtdx.OPT_TRACE_STATS, 0)
+nc = max(s0["closest_rays"], 1)
+stats = "N/ray node %.2f tri %.2f inst %.2f" % (s0["nodes_visited"] / nc, s0["tris_tested"] / nc, s0["instances_entered"] / nc)
 ctx.set_option(rtdx.OPT_STAGE_TIMING, 1)
 ctx.reset_counters()
 acc, tot = {}, 0.0
@@ -37,4 +42,4 @@ c = ctx.counters()
 rays = c["closest_rays"] + c["shadow_rays"]
 tag = a.tag or os.environ.get("RTX_B200_LIB", "default")
 print("%-28s pass %.3f ms  %.0f Mrays/s | " % (tag, tot / a.passes, rays / tot / 1e3) +
-      "  ".join("%s %.3f" % (n, v / a.passes) for n, v in acc.items() if v > 0), flush=True)
+      "  ".join("%s %.3f" % (n, v / a.passes) for n, v in acc.items() if v > 0) + " | " + stats, flush=True)
