@@ -137,6 +137,9 @@ rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stage
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);
+/* self-test of the device arithmetic (csrc/dmath.cuh): compares every hand-scheduled fast path with the IEEE-754
+ * operation it restates over ALL 2^32 binary32 bit patterns on the device.  mismatches_out[0] = d_rsqrt vs 1/sqrt. */
+rtx_status rtx_selftest_dmath(rtx_ctx*, uint64_t* mismatches_out, uint32_t n_out);
 
 #ifdef __cplusplus
 }

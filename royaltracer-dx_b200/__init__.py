@@ -58,7 +58,8 @@ class RtxBlasInfo(C.Structure):
 ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model", "rtx_blas_info_get", "rtx_set_material_ids",
                "rtx_set_materials", "rtx_set_instances", "rtx_set_emissive_triangles", "rtx_set_camera", "rtx_render_pass",
                "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_accum_device_ptr", "rtx_trace",
-               "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel"]
+               "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel",
+               "rtx_selftest_dmath"]
 HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut"]
 
 _lib = None
@@ -104,6 +105,7 @@ def load_library():
     lib.rtx_last_pass_stage_ms.argtypes = [vp, vp, u32, C.POINTER(C.c_float)]
     lib.rtx_debug_pixel.argtypes = [vp, u32, u32, vp]
     lib.rtx_set_option.argtypes = [vp, u32, u32]
+    lib.rtx_selftest_dmath.argtypes = [vp, vp, u32]
     _lib = lib
     return lib
 
@@ -316,6 +318,11 @@ class Context:
 
     def set_option(self, option, value):
         self._check(self.lib.rtx_set_option(self.handle, option, int(value)))
+
+    def selftest_dmath(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self.lib.rtx_selftest_dmath(self.handle, _ptr(out), 8))
+        return {"rsqrt": int(out[0]), "div3": int(out[1])}
 
     def debug_pixel(self, x, y):
         out = np.zeros(64, dtype=np.float32)

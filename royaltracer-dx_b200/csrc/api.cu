@@ -471,6 +471,15 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     return RTX_OK;
 }
 
+extern "C" rtx_status rtx_selftest_dmath(rtx_ctx* c, uint64_t* out, uint32_t n_out) {
+    if (!c || !out || n_out == 0) return fail(RTX_ERR_ARG, "rtx_selftest_dmath: bad argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    unsigned long long h[8] = {0};
+    RTX_CK(wave_selftest_dmath(c->stream, h, 8));
+    for (uint32_t i = 0; i < n_out; i++) out[i] = i < 8 ? (uint64_t)h[i] : 0;
+    return RTX_OK;
+}
+
 extern "C" rtx_status rtx_debug_pixel(rtx_ctx* c, uint32_t x, uint32_t y, float* out64) {
     if (!c || !out64 || !c->wb_ready) return fail(RTX_ERR_ARG, "rtx_debug_pixel: bad argument");
     if (x >= c->cfg.width || y >= c->cfg.height) return fail(RTX_ERR_ARG, "rtx_debug_pixel: pixel out of range");

@@ -60,7 +60,7 @@ __device__ __forceinline__ MatOpt load_matopt(const SceneData& S, uint32_t id, f
 }
 
 // shaders/Common_v7.hlsl:119-138
-__device__ __forceinline__ float RandomFloat(uint2& seed) {
+__device__ __forceinline__ uint2 tea4_body(uint2 seed) {
     uint32_t v0 = seed.x, v1 = seed.y, sum = 0u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -68,8 +68,16 @@ __device__ __forceinline__ float RandomFloat(uint2& seed) {
         v0 += ((v1 << 4) + 0xA341316Cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xC8013EA4u);
         v1 += ((v0 << 4) + 0xAD90777Du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7E95761Eu);
     }
-    seed.x = v0; seed.y = v1;
-    return (float)v0 / 4294967296.0f;
+    return make_uint2(v0, v1);
+}
+#ifdef RTX_TEA_NOINLINE
+static __device__ __noinline__ uint2 tea4(uint2 seed) { return tea4_body(seed); }
+#else
+__device__ __forceinline__ uint2 tea4(uint2 seed) { return tea4_body(seed); }
+#endif
+__device__ __forceinline__ float RandomFloat(uint2& seed) {
+    seed = tea4(seed);
+    return (float)seed.x / 4294967296.0f;
 }
 // shaders/Pass_init_di_v7.hlsl:63-77, uint(time) := global sample index
 __device__ __forceinline__ uint2 init_seed(uint32_t x, uint32_t y, uint32_t pass, uint32_t sample) {
@@ -229,6 +237,19 @@ __device__ __forceinline__ uint32_t SelectSamplingStrategy(const SceneData& S, c
     if (r <= p_s) { if (mat.Pr < 0.04f) return 0; return 1; }
     return 0;
 }
+// the two halves of SelectSamplingStrategy, for call sites that select twice at the same shading point
+// (Path_Sampler_v7.hlsl:118,196): p_s depends on (material, outgoing, normal) only.
+__device__ __forceinline__ float StrategyPs(const SceneData& S, const MatOpt& mat, f3 outgoing, f3 normal) {
+    if (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) return -1.0f;          // r <= p_s never holds: always strategy 0
+    float cosTheta = dot3(normal, outgoing);
+    f3 fr = SchlickFresnel(mat.Ks, cosTheta);
+    return fminf(1.0f, ((fr.x + fr.y) + fr.z) / 3.0f + mat.Pm);
+}
+__device__ __forceinline__ uint32_t SelectWithPs(float p_s, const MatOpt& mat, uint2& seed) {
+    float r = RandomFloat(seed);
+    if (r <= p_s) { if (mat.Pr < 0.04f) return 0; return 1; }
+    return 0;
+}
 // :74-88
 __device__ __forceinline__ f3 SampleBRDF(uint32_t strategy, const MatOpt& mat, f3 outgoing, f3 normal, uint2& seed) {
     if (strategy == 0) return RandomUnitVectorInHemisphere(normal, seed);
@@ -256,6 +277,90 @@ __device__ __forceinline__ float CombinedP(const SceneData& S, const MatOpt& mat
     float P1 = SafeMultiply1(p_d, BRDF_PDF_Lambertian(normal, incidence));
     float P2 = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) ? 0.0f : SafeMultiply1(p_s, BRDF_PDF_GGX(mat, normal, incidence, outgoing));
     return P1 + P2;
+}
+
+// ---- the combined lobe with its shading-point invariants hoisted.
+// CombinedF / CombinedP above are evaluated 5 times per path vertex (4 NEE candidates + the BSDF ray) with the same
+// (material, normal, outgoing): N, V, N.V, the Smith term of V, G1, the D_GGX constants, the ESS energy factor and the
+// Lambert lobe do not depend on the light direction.  LobeCtx computes them once; lobe_FP() then evaluates exactly the
+// expression trees of EvaluateBRDF_GGX / BRDF_PDF_GGX / the Lambert lobe on those values (same operations on the same
+// operands => bit-identical to the un-hoisted form, which tests/test_gpu_parity.py checks against the oracle).
+struct LobeCtx {
+    f3 normal;              // raw shading normal (the Lambert pdf uses it un-normalised)
+    f3 N, V;                // normalize3(normal), normalize3(outgoing)
+    f3 Ks, essScale;        // mat.Ks ; 1 + Ks*kms, kms = (1-Ess)/Ess (GGX_v7.hlsl:196-199)
+    f3 F1;                  // SafeMultiply(p_d, Kd/PI)
+    float NdotV, NdotV4;    // N.V ; 4*N.V
+    float a2D, a2Dm1;       // D_GGX: alpha^2 with alpha = Pr*Pr in fp32 ; alpha^2 - 1
+    float a2G, oma2G;       // Smith: alpha^2 with alpha = half(Pr*Pr) ; 1 - alpha^2
+    float sV, G1;           // sqrt(a2G + ((1-a2G) N.V) N.V) ; (2 N.V)/(sV + N.V)
+    float p_d, p_s;
+    bool lambert_only;
+};
+// N = normalize3(normal) and V = normalize3(outgoing) supplied by the caller (call sites that build two contexts at one
+// vertex share N, and often already hold V)
+__device__ __forceinline__ LobeCtx make_lobe_ctx_nv(const SceneData& S, const MatOpt& mat, f3 normal, f3 N, f3 V, float p_d, float p_s) {
+    LobeCtx c;
+    c.normal = normal; c.p_d = p_d; c.p_s = p_s;
+    c.lambert_only = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) != 0u;
+    c.F1 = SafeMultiply(p_d, EvaluateBRDF_Lambertian(mat));
+    c.Ks = mat.Ks;
+    if (!c.lambert_only) {
+        c.N = N; c.V = V;
+        c.NdotV = dot3(c.N, c.V);
+        c.NdotV4 = 4.0f * c.NdotV;
+        const float alphaD = mat.Pr * mat.Pr;
+        c.a2D = alphaD * alphaD; c.a2Dm1 = c.a2D - 1.0f;
+        const float alphaG = hmul(mat.Pr, mat.Pr);
+        c.a2G = alphaG * alphaG; c.oma2G = 1.0f - c.a2G;
+        c.sV = sqrtf(c.a2G + (c.oma2G * c.NdotV) * c.NdotV);
+        c.G1 = (2.0f * c.NdotV) / (c.sV + c.NdotV);
+        const float Ess = ESS_LUT(S, mat, c.NdotV);
+        const float kms = (1.0f - Ess) / Ess;
+        c.essScale = mk3(1.0f + mat.Ks.x * kms, 1.0f + mat.Ks.y * kms, 1.0f + mat.Ks.z * kms);
+    }
+    return c;
+}
+__device__ __forceinline__ LobeCtx make_lobe_ctx(const SceneData& S, const MatOpt& mat, f3 normal, f3 outgoing, float p_d, float p_s) {
+    const bool lo = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) != 0u;
+    return make_lobe_ctx_nv(S, mat, normal, lo ? normal : normalize3(normal), lo ? outgoing : normalize3(outgoing), p_d, p_s);
+}
+// F = CombinedF(...), P = CombinedP(...) (scaled == false) or CombinedP_scaled(..., a, b) for one incidence direction.
+template <bool WANT_F, bool WANT_P>
+__device__ __forceinline__ void lobe_FP(const LobeCtx& c, f3 incidence, bool scaled, float a, float b, f3& F, float& P) {
+    f3 F2 = mk3(0, 0, 0); float P2 = 0.0f;
+    if (!c.lambert_only) {
+        const f3 L = normalize3(-incidence);
+        const f3 H = normalize3(c.V + L);
+        const float NdotH = dot3(c.N, H);
+        const float denomD = (NdotH * NdotH) * c.a2Dm1 + 1.0f;
+        const float D = c.a2D / ((RTX_PI_REF * denomD) * denomD);                // D_GGX
+        if (WANT_F) {
+            const float NdotL = dot3(c.N, L), VdotH = dot3(c.V, H);
+            const f3 Fr = SchlickFresnel(c.Ks, VdotH);
+            const float denomA = c.NdotV * sqrtf(c.a2G + (c.oma2G * NdotL) * NdotL);
+            const float denomB = NdotL * c.sV;
+            const float G = ((2.0f * NdotL) * c.NdotV) / (denomA + denomB);      // G2_SmithGGX
+            const float denominator = c.NdotV4 * NdotL;
+            f3 spec = mk3(0, 0, 0);
+            if (!(denominator < RTX_EPS)) {
+                spec = (((Fr * D) * G) / denominator) * c.essScale;
+                if (any_nan_inf(spec)) spec = mk3(0, 0, 0);
+            }
+            F2 = SafeMultiply(c.p_s, spec);
+        }
+        if (WANT_P) {
+            float pdf = (c.G1 * D) / c.NdotV4;                                    // BRDF_PDF_GGX (NdotV*4 == 4*NdotV)
+            if (scaled) pdf = (pdf * a) / b;
+            P2 = SafeMultiply1(c.p_s, pdf);
+        }
+    }
+    if (WANT_F) F = c.F1 + F2;
+    if (WANT_P) {
+        float pl = BRDF_PDF_Lambertian(c.normal, incidence);
+        if (scaled) pl = (pl * a) / b;
+        P = SafeMultiply1(c.p_d, pl) + P2;
+    }
 }
 
 // ---- ClosestHit, shaders/Hit_v7.hlsl:12-61 (area is not carried: nothing on the E0 path reads payload.area)

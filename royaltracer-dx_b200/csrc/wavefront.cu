@@ -22,8 +22,11 @@ namespace rtx {
     } while (0)
 
 #define WF_BLOCK 128
+#ifndef RTX_GI_BLOCK
+#define RTX_GI_BLOCK 384    // CTA size of k_gi_step: 2 x 384 threads per SM at 85 registers measured best (profiles/)
+#endif
 #ifndef RTX_GI_MINB
-#define RTX_GI_MINB 8       // resident CTAs per SM the register budget of k_gi_step is set for
+#define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
 
 struct StateView {
@@ -95,8 +98,10 @@ __device__ __forceinline__ bool UpdateReservoir(f3& rx, f3& rn, f3& rL, float& w
 }
 
 // SampleLightNEE with useVisibility=false, shaders/Sampler_v7.hlsl:273-396 (call site :677-693)
+// `lobe` = make_lobe_ctx(material, normal, on = normalize3(outgoing), CalculateStrategyProbabilities(material, on, normal)):
+// the part of :348-374 that is the same for every candidate of one shading point.
 __device__ __forceinline__ void SampleLightNEE(const SceneData& S, float& pdf_light, float& pdf_bsdf, float& p_hat, uint2& seed, f3 worldOrigin,
-                                               f3 normal, f3 outgoing, const MatOpt& material, f3& emission, f3& x2, f3& n2) {
+                                               f3 normal, const LobeCtx& lobe, f3& emission, f3& x2, f3& n2) {
     LightSample ls;
     SampleLightPoint(S, worldOrigin, seed, ls);
     x2 = ls.point; n2 = ls.normal_l;
@@ -104,11 +109,8 @@ __device__ __forceinline__ void SampleLightNEE(const SceneData& S, float& pdf_li
     float cos_theta_y = dot3(ls.normal_l, -ls.L_norm);
     float G = fmaxf((cos_theta_y * cos_theta_x) / ls.dist2, RTX_EPS);
     emission = ls.emission;
-    float p_d, p_s;
-    f3 on = normalize3(outgoing);
-    CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
-    f3 brdf_light = CombinedF(S, material, normal, -ls.L_norm, on, p_d, p_s);
-    float P = CombinedP_scaled(S, material, normal, -ls.L_norm, on, p_d, p_s, cos_theta_y, ls.dist2);
+    f3 brdf_light; float P;
+    lobe_FP<true, true>(lobe, -ls.L_norm, true, cos_theta_y, ls.dist2, brdf_light, P);
     p_hat = length3((ls.emission * brdf_light) * G);
     pdf_light = fmaxf(RTX_EPS, ls.pdf_l);
     pdf_bsdf = P;
@@ -140,9 +142,13 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
                 const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, payload.hitNormal, seed);
                 f3 rx = mk3(0, 0, 0), rn = mk3(0, 0, 0), rL = mk3(0, 0, 0); float w_sum = 0.0f;
                 const float fM1 = (float)S.nee_samples_di, fM2 = 1.0f;
+                const f3 on = normalize3(outgoing);
+                float p_d, p_s;
+                CalculateStrategyProbabilities(S, mat, on, payload.hitNormal, p_d, p_s);
+                const LobeCtx lobe = make_lobe_ctx(S, mat, payload.hitNormal, on, p_d, p_s);
                 for (uint32_t i = 0; i < S.nee_samples_di; i++) {
                     float pdf_light = 0.0f, pdf_bsdf = 0.0f, p_hat = 0.0f; f3 emission, x2, n2;
-                    SampleLightNEE(S, pdf_light, pdf_bsdf, p_hat, seed, payload.hitPosition, payload.hitNormal, outgoing, mat, emission, x2, n2);
+                    SampleLightNEE(S, pdf_light, pdf_bsdf, p_hat, seed, payload.hitPosition, payload.hitNormal, lobe, emission, x2, n2);
                     float mi = pdf_light / (fM1 * pdf_light + fM2 * pdf_bsdf);
                     float wi = (mi * p_hat) / pdf_light;
                     if (p_hat > 0.0f) UpdateReservoir(rx, rn, rL, w_sum, wi, x2, n2, emission, seed);
@@ -200,8 +206,14 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
                 float p_d, p_s;
                 f3 on = normalize3(o);
                 CalculateStrategyProbabilities(S, mat, on, hitNormal, p_d, p_s);
-                f3 brdf = CombinedF(S, mat, hitNormal, -sample, on, p_d, p_s);
-                float pdf_bsdf = CombinedP_scaled(S, mat, hitNormal, -sample, o, p_d, p_s, cos_theta, dist2);
+                // F sees V = normalize3(on), the pdf sees V = normalize3(o) = on (Sampler_v7.hlsl:248-261)
+                const bool lo = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) != 0u;
+                const f3 N = lo ? hitNormal : normalize3(hitNormal);
+                const LobeCtx lobeF = make_lobe_ctx_nv(S, mat, hitNormal, N, lo ? on : normalize3(on), p_d, p_s);
+                const LobeCtx lobeP = make_lobe_ctx_nv(S, mat, hitNormal, N, on, p_d, p_s);
+                f3 brdf, unusedF; float pdf_bsdf, unusedP;
+                lobe_FP<true, false>(lobeF, -sample, false, 1.0f, 1.0f, brdf, unusedP);
+                lobe_FP<false, true>(lobeP, -sample, true, cos_theta, dist2, unusedF, pdf_bsdf);
                 float ndot = dot3(hitNormal, sample);
                 float p_hat = length3((((brdf * emission) * ndot) * cos_theta) / dist2);
                 float mi = pdf_bsdf / ((float)S.nee_samples_di * pdf_light + 1.0f * pdf_bsdf);
@@ -248,8 +260,9 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
 }
 
 // SampleLightNEE_GI with useVisibility=false, Sampler_v7.hlsl:508-647 (call site Path_Sampler_v7.hlsl:133-151)
+// `lobe` = make_lobe_ctx(material, normal, on = normalize3(outgoing), CalculateStrategyProbabilities(material, on, normal))
 __device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_light, float& pdf_bsdf, f3& x2_pos, uint2& seed, f3 origin, f3 normal,
-                                                f3 outgoing, f3 acc_l, float acc_pdf, f3& throughput, f3& emission, const MatOpt& material) {
+                                                const LobeCtx& lobe, f3 acc_l, float acc_pdf, f3& throughput, f3& emission) {
     LightSample ls;
     SampleLightPoint(S, origin, seed, ls);
     x2_pos = ls.point;
@@ -258,11 +271,8 @@ __device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_l
     float cos_theta_y = fabsf(dot3(ls.normal_l, -ls.L_norm));
     if (cos_theta_y < RTX_EPS) cos_theta_y = 0.0f;
     float G = cos_theta_x;
-    float p_d, p_s;
-    f3 on = normalize3(outgoing);
-    CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
-    f3 brdf_light = CombinedF(S, material, normal, -ls.L_norm, on, p_d, p_s);
-    float P = CombinedP(S, material, normal, -ls.L_norm, on, p_d, p_s);
+    f3 brdf_light; float P;
+    lobe_FP<true, true>(lobe, -ls.L_norm, false, 1.0f, 1.0f, brdf_light, P);
     if (cos_theta_y > 0.0f) pdf_light = (fmaxf(RTX_EPS, ls.pdf_l) * ls.dist2) / cos_theta_y;
     pdf_bsdf = P;
     acc_pdf *= pdf_light;
@@ -276,7 +286,8 @@ __device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_l
 // ---- stage: one step of the indirect path (Path_Sampler_v7.hlsl:54-269 + Sampler_v7.hlsl:436-504).
 // iter == 0 consumes the hit of the initial indirect ray; iter >= 1 consumes the BSDF ray of loop iteration iter-1.
 // If the path goes on and iter < bounces it runs iteration `iter`'s NEE candidates and emits its BSDF ray.
-__global__ void __launch_bounds__(WF_BLOCK, RTX_GI_MINB)
+template <bool ITER0>       // two instantiations: the hit-consuming halves differ, and the kernel is I-cache bound
+__global__ void __launch_bounds__(RTX_GI_BLOCK, RTX_GI_MINB)
 k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
           RayQueue q_shadow, RayQueue qout, uint32_t iter, unsigned long long* ray_counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,13 +317,14 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             ClosestHit(S, origin, sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
             f3 ke_full;
             const MatOpt hm = load_matopt(S, sp.materialID, &ke_full);
-            if (iter == 0u) {
+            if (ITER0) {
                 if (!(length3(ke_full) > 0.0f)) {                   // Path_Sampler_v7.hlsl:55-98
                     const f3 incoming = normalize3(-sample);
                     float p_d, p_s;
                     CalculateStrategyProbabilities(S, material, outgoing, normal, p_d, p_s);
-                    const f3 F = CombinedF(S, material, normal, incoming, outgoing, p_d, p_s);
-                    const float P = CombinedP(S, material, normal, incoming, outgoing, p_d, p_s);
+                    const LobeCtx lobe = make_lobe_ctx(S, material, normal, outgoing, p_d, p_s);
+                    f3 F; float P;
+                    lobe_FP<true, true>(lobe, incoming, false, 1.0f, 1.0f, F, P);
                     const float NdotL = dot3(normal, sample);
                     acc_pdf *= P;
                     acc_f = acc_f * (F * NdotL);
@@ -324,8 +336,14 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 float p_d, p_s;
                 const f3 on = normalize3(outgoing);
                 CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
-                const f3 brdf = CombinedF(S, material, normal, -sample, on, p_d, p_s);
-                const float pdf_bsdf = CombinedP(S, material, normal, -sample, outgoing, p_d, p_s);
+                // F sees V = normalize3(on), the pdf sees V = normalize3(outgoing) = on (Sampler_v7.hlsl:443-456)
+                const bool lo = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) != 0u;
+                const f3 N = lo ? normal : normalize3(normal);
+                const LobeCtx lobeF = make_lobe_ctx_nv(S, material, normal, N, lo ? on : normalize3(on), p_d, p_s);
+                const LobeCtx lobeP = make_lobe_ctx_nv(S, material, normal, N, on, p_d, p_s);
+                f3 brdf, unusedF; float pdf_bsdf, unusedP;
+                lobe_FP<true, false>(lobeF, -sample, false, 1.0f, 1.0f, brdf, unusedP);
+                lobe_FP<false, true>(lobeP, -sample, false, 1.0f, 1.0f, unusedF, pdf_bsdf);
                 const float NdotL = dot3(normal, sample);
                 const bool emitter = (hm.Ke.x != 0.0f || hm.Ke.y != 0.0f || hm.Ke.z != 0.0f);
                 acc_pdf *= pdf_bsdf;
@@ -359,12 +377,21 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             }
         }
         if (cont && iter < S.bounces) {                             // Path_Sampler_v7.hlsl:114-225 (iteration `iter`)
-            uint32_t strategy = SelectSamplingStrategy(S, material, outgoing, normal, seed);
+            const float ps_sel = StrategyPs(S, material, outgoing, normal);     // both selections of this vertex see the same p_s
+            uint32_t strategy = SelectWithPs(ps_sel, material, seed);
+            LobeCtx lobe;
+            const f3 Nn = normalize3(normal);
+            if (S.nee_samples > 0u) {
+                const f3 on = normalize3(outgoing);
+                float p_d, p_s;
+                CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
+                lobe = make_lobe_ctx_nv(S, material, normal, Nn, normalize3(on), p_d, p_s);
+            }
             for (uint32_t k = 0; k < S.nee_samples; k++) {
                 float pdf_light = 1.0f, pdf_bsdf = 1.0f;
                 f3 throughput_NEE = mk3(1, 1, 1), emission_NEE = mk3(0, 0, 0), x2;
-                f3 contribution = SampleLightNEE_GI(S, pdf_light, pdf_bsdf, x2, seed, origin, normal, outgoing, acc_f, acc_pdf,
-                                                    throughput_NEE, emission_NEE, material);
+                f3 contribution = SampleLightNEE_GI(S, pdf_light, pdf_bsdf, x2, seed, origin, normal, lobe, acc_f, acc_pdf,
+                                                    throughput_NEE, emission_NEE);
                 float mi = pdf_light / (fnee * pdf_light + pdf_bsdf);
                 f3 E_reconnection = ((acc_fr * mi) * emission_NEE) * throughput_NEE;
                 f3 E_path = mi * contribution;
@@ -373,11 +400,11 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 w_sum += wi;
                 if (RandomFloat(seed) < wi / w_sum) {
                     E3 = q16v(E_reconnection);
-                    x1s = origin + RTX_S_BIAS * normalize3(normal);
+                    x1s = origin + RTX_S_BIAS * Nn;
                     x2s = x2;
                 }
             }
-            strategy = SelectSamplingStrategy(S, material, outgoing, normal, seed);
+            strategy = SelectWithPs(ps_sel, material, seed);
             const f3 s2 = SampleBRDF(strategy, material, outgoing, normal, seed);
             emit = true; ro = origin; rd = s2;
         } else {
@@ -589,7 +616,9 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     for (uint32_t iter = 0; iter <= S.bounces; iter++) {
         RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
         CKE(mark(SK_GI_STEP));
-        k_gi_step<<<grid, WF_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
+        const unsigned ggrid = (n + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
+        if (iter == 0u) k_gi_step<true><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
+        else k_gi_step<false><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
         if (iter < S.bounces) {
             CKE(closest(qout));
             qin = qout; cur ^= 1;
@@ -610,6 +639,30 @@ cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream,
     k_resolve<<<(n_pixels + 255) / 256, 256, 0, stream>>>(B.accum, n_pixels, (uchar4*)B.output);
     if (launches) *launches += 1;
     return cudaGetLastError();
+}
+
+// ---- rtx_selftest_dmath: every binary32 bit pattern through the fast path and through the IEEE operations it restates
+__global__ void k_selftest_dmath(unsigned long long* bad) {
+    unsigned long long n_rsqrt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const float x = __uint_as_float((uint32_t)i);
+        if (__float_as_uint(d_rsqrt(x)) != __float_as_uint(1.0f / sqrtf(x))) n_rsqrt++;
+    }
+    if (n_rsqrt) atomicAdd(&bad[0], n_rsqrt);
+}
+cudaError_t wave_selftest_dmath(cudaStream_t stream, unsigned long long* host_out, uint32_t n_out) {
+    unsigned long long* d = nullptr;
+    CKE(cudaMalloc((void**)&d, 8 * sizeof(unsigned long long)));
+    CKE(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), stream));
+    k_selftest_dmath<<<148 * 8, 256, 0, stream>>>(d);
+    unsigned long long h[8];
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    for (uint32_t i = 0; i < n_out && i < 8; i++) host_out[i] = h[i];
+    return cudaSuccess;
 }
 
 cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uint32_t y, cudaStream_t stream, float* host_out64) {

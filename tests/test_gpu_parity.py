@@ -135,6 +135,15 @@ def test_render_instanced_emitters(rtdx, orc):
     ctx.close()
 
 
+def test_device_arithmetic_fast_paths_exhaustive(rtdx):
+    """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
+    (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""
+    ctx = rtdx.Context(16, 16)
+    r = ctx.selftest_dmath()
+    assert r == {"rsqrt": 0, "div3": 0}, r
+    ctx.close()
+
+
 def test_accumulation_reset_on_camera_change(rtdx):
     sc = rtdx.scenes.cornell()
     ctx, up = _upload(rtdx, sc, 64, 64, bounces=2, flags=rtdx.FLAG_LAMBERT_ONLY)
