@@ -42,9 +42,21 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--side", type=int, default=296, help="cube-sphere side: 12*side^2 triangles (296 -> 1,051,392)")
     ap.add_argument("--bounces", type=int, default=6)
-    ap.add_argument("--cpu-step", type=int, default=6, help="pixel subsampling of the CPU baseline (every n-th pixel in x and y)")
+    ap.add_argument("--cpu-step", type=int, default=2, help="pixel subsampling of the CPU baseline (every n-th pixel in x and y)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json, written by
+    tools/ncu_traffic.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        return float(t["kernels"][kernel]["dram_bytes_per_launch"]), t.get("source", "")
+    except Exception:
+        return None, ""
 
 
 def peaks():
@@ -66,7 +78,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -278,8 +290,10 @@ def main():
         peak, peak_src = peaks()
         n_launch = (args.bounces + 3) * args.steps      # closest-hit traversal launches in the instrumented K steps
         achieved = (cnt_t["closest_rays"] * b_ray) / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        traffic, traffic_src = measured_traffic("trace_kernel<closest>")
         roofline = {"bound": "hbm", "kernel": "trace_kernel<closest>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, dram read+write bytes per launch (profiles/traffic.json <- %s)" % traffic_src,
+                    "algorithmic_bytes_per_launch": cnt_t["closest_rays"] * b_ray / n_launch, "peak_source": peak_src,
                     "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri, "instances_per_ray": n_inst,
                     "launches": n_launch, "avg_launch_ms": trace_ms / n_launch, "rays_per_launch": cnt_t["closest_rays"] / n_launch, "trace_share_of_step": trace_ms / pass_ms if pass_ms else None,
                     "note": "BVH (%.1f MB) is L2-resident at this scene size; HBM peak is the conservative denominator (SURVEY.md §8d)" % (sum(b["bytes"] for b in blas) / 1e6)}
