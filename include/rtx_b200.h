@@ -50,6 +50,7 @@ typedef struct { float t, u, v; uint32_t prim; uint32_t inst; } rtx_hit;      /*
 #define RTX_FLAG_JITTER          1u  /* 2 RandomFloat draws before anything else (legacy include/RayGen.hlsl:84-85) */
 #define RTX_FLAG_LAMBERT_ONLY    2u  /* strategy probabilities forced to (1,0) (BASELINE config C1) */
 #define RTX_FLAG_SORT_MATERIAL   4u  /* bin shading queues by material id */
+#define RTX_FLAG_RESTIR          8u  /* allocate the reservoir / sample buffers u2..u7 (rdn/Renderer.cpp:1331-1577) for rtx_render_frame */
 
 /* Compile-time #defines of shaders/Common_v7.hlsl:1-28 that BASELINE configs vary, as runtime fields. */
 typedef struct {
@@ -100,6 +101,14 @@ rtx_status rtx_set_camera(rtx_ctx*, const rtx_camera_params*);
 /* replaces the DispatchRays sequence (rdn/Renderer.cpp:611-673): renders samples [first_sample, first_sample+n_samples)
  * of every pixel with estimator E0 and accumulates them (gPermanentData).  Asynchronous on the context stream. */
 rtx_status rtx_render_pass(rtx_ctx*, uint32_t first_sample, uint32_t n_samples);
+/* One frame of the reference's dispatch sequence (rdn/Renderer.cpp:611-673): DispatchRays RayGen (pass 1, 1 spp, sample
+ * index = frame_index) -> RayGen2 (temporal reuse against last frame's reservoirs, reprojected with prevView/prevProjection
+ * of rtx_set_camera and prevObjectToWorld of rtx_set_instances) -> RayGen3 (spatial reuse, final shade, accumulation).
+ * Needs RTX_FLAG_RESTIR and samples_per_pass == 1.  rtx_reset_restir zero-fills the reservoir history. */
+rtx_status rtx_render_frame(rtx_ctx*, uint32_t frame_index);
+rtx_status rtx_reset_restir(rtx_ctx*);
+/* debug: the *_last reservoir / sample buffers after a frame, 40 floats per pixel (layout: csrc/restir.cu k_restir_dump) */
+rtx_status rtx_read_restir(rtx_ctx*, float* out40_per_pixel);
 rtx_status rtx_reset_accum(rtx_ctx*);
 rtx_status rtx_synchronize(rtx_ctx*);
 /* gPermanentData (u1): float4 per pixel, row-major; gOutput slice 0 (u0): RGBA8 */

@@ -61,6 +61,11 @@ def lib():
         L.orc_render.argtypes = [vp, C.POINTER(OrcConfig), vp, u32, u32, u32, vp, C.POINTER(OrcCounters), C.c_int]
         L.orc_render_rows.argtypes = [vp, C.POINTER(OrcConfig), vp, u32, u32, u32, u32, u32, vp, C.POINTER(OrcCounters), C.c_int]
         L.orc_resolve.argtypes = [vp, u32, vp]
+        L.orc_frames_create.argtypes = [u32, u32]
+        L.orc_frames_create.restype = vp
+        L.orc_frames_destroy.argtypes = [vp]
+        L.orc_render_frame.argtypes = [vp, C.POINTER(OrcConfig), vp, u32, vp, vp, C.POINTER(OrcCounters), C.c_int]
+        L.orc_frames_dump.argtypes = [vp, vp]
         L.orc_kat_rng.argtypes = [u32, u32, u32, vp, vp]
         L.orc_kat_seed.argtypes = [u32, u32, u32, u32, vp]
         L.orc_kat_sincos.argtypes = [vp, u32, vp, vp]
@@ -94,7 +99,8 @@ class OracleScene:
         L.orc_set_material_ids(self.h, _p(ids), ids.size)
         mats = np.ascontiguousarray(scene.materials)
         L.orc_set_materials(self.h, _p(mats), mats.size)
-        mids = np.ascontiguousarray(np.array([i[0] for i in scene.instances], dtype=np.uint32))
+        self._model_ids = [i[0] for i in scene.instances]
+        mids = np.ascontiguousarray(np.array(self._model_ids, dtype=np.uint32))
         pr = np.ascontiguousarray(props)
         L.orc_set_instances(self.h, _p(mids), _p(pr), mids.size)
         lt = np.ascontiguousarray(lights)
@@ -151,6 +157,32 @@ class OracleScene:
         [t.join() for t in ts]
         tot = {k: sum(getattr(ct, k) for ct in ctrs) for k, _ in OrcCounters._fields_}
         return accum, tot
+
+    def set_props(self, props):
+        """OnUpdate: new per-instance matrices (UpdateInstancePropertiesBuffer); rebuilds the oracle's instance boxes."""
+        mids = np.ascontiguousarray(np.array(self._model_ids, dtype=np.uint32))
+        pr = np.ascontiguousarray(props)
+        self.L.orc_set_instances(self.h, _p(mids), _p(pr), mids.size)
+        self.L.orc_build(self.h)
+
+    def new_frames(self, width, height):
+        return C.c_void_p(self.L.orc_frames_create(width, height))
+
+    def free_frames(self, frames):
+        self.L.orc_frames_destroy(frames)
+
+    def render_frame(self, cam, width, height, frame_index, frames, accum, bounces=3, nee_samples=4, nee_samples_di=4, flags=0, mode=1):
+        """One frame of the reference's 3-pass sequence (pass 1 + temporal + spatial reuse); accum is updated in place."""
+        cfg = OrcConfig(width, height, bounces, nee_samples, nee_samples_di, flags)
+        ctr = OrcCounters()
+        c = np.ascontiguousarray(cam)
+        self.L.orc_render_frame(self.h, C.byref(cfg), _p(c), frame_index, frames, _p(accum), C.byref(ctr), mode)
+        return {k: getattr(ctr, k) for k, _ in OrcCounters._fields_}
+
+    def dump_frames(self, frames, width, height):
+        out = np.zeros((height, width, 40), dtype=np.float32)
+        self.L.orc_frames_dump(frames, _p(out))
+        return out
 
     def debug_pixel(self, cam, width, height, x, y, sample, bounces=3, nee_samples=4, nee_samples_di=4, flags=0, mode=1):
         cfg = OrcConfig(width, height, bounces, nee_samples, nee_samples_di, flags)

@@ -899,6 +899,7 @@ struct PixelDebug {
     f3 cam_o, cam_d; uint32_t hit_inst, hit_prim; float hit_t;
     uint32_t mID; f3 x1, n1;
     ReservoirDI rdi; ReservoirGI rgi; float p_hat; f3 C; uint32_t seed_end[2]; f3 acc_L;
+    uint32_t kind; f3 L1;       // 0 = miss, 1 = primary hit on an emitter (L1 = half3 Ke), 2 = sampled
 };
 
 // Pass_init_di_v7.hlsl:48-190 followed by the E0 final shade (Pass_spat_di_v7.hlsl:334-372 with no neighbours)
@@ -923,7 +924,11 @@ inline f3 RenderSample(const Ctx& c, const orc_camera& cam, uint32_t x, uint32_t
     orc_material fm = fetch_material(*c.S, mID);
     MatOpt matOpt = make_matopt(fm, mID);
     if (dbg) { dbg->mID = mID; dbg->x1 = payload.hitPosition; dbg->n1 = payload.hitNormal; }
-    if (length3(mk3(fm.Ke[0], fm.Ke[1], fm.Ke[2])) > 0.0f) return matOpt.Ke;       // :103-106,132 ; D5 (L1 is half3)
+    if (length3(mk3(fm.Ke[0], fm.Ke[1], fm.Ke[2])) > 0.0f) {                       // :103-106,132 ; D5 (L1 is half3)
+        if (dbg) { dbg->kind = 1; dbg->L1 = matOpt.Ke; }
+        return matOpt.Ke;
+    }
+    if (dbg) dbg->kind = 2;
     ReservoirDI reservoir; memset(&reservoir, 0, sizeof reservoir);
     ReservoirGI reservoir_GI; memset(&reservoir_GI, 0, sizeof reservoir_GI);
     f3 o = -direction;
@@ -949,6 +954,254 @@ inline f3 RenderSample(const Ctx& c, const orc_camera& cam, uint32_t x, uint32_t
     f3 Cc = Cdi + f_gi * reservoir_GI.W;
     if (dbg) { dbg->rdi = reservoir; dbg->rgi = reservoir_GI; dbg->p_hat = p_hat; dbg->C = Cc; dbg->seed_end[0] = seed[0]; dbg->seed_end[1] = seed[1]; dbg->acc_L = acc_L; }
     return Cc;
+}
+
+// ============================================================================================ ReSTIR reuse
+// Passes 2 and 3 of the reference's frame: shaders/Pass_temp_di_v7.hlsl:46-204 (RayGen2), shaders/Pass_spat_di_v7.hlsl:46-464
+// (RayGen3), shaders/MIS_v7.hlsl, include/MIS_GI_v6.hlsl, shaders/Common_v7.hlsl:203-350, shaders/Sampler_v7.hlsl:738-785.
+// Per-pixel buffers are indexed linearly (MapPixelID is a storage order only, F3).
+struct SData { f3 x1; uint32_t mID; f3 L1; f3 n1; f3 o; uint32_t objID; uint32_t kind; };   // Reservoir_v7.hlsl:2-11; mID is uint16_t
+
+// GetP_Hat / GetP_Hat_GI (Sampler_v7.hlsl:163-181).  Deviation D6': the visibility ray is traced only when the unshadowed
+// value is > 0 (the product with V is 0 or NaN otherwise, whatever V is) — this also defines the ray count.
+inline float GetP_Hat(const Ctx& c, f3 x1, f3 n1, f3 x2, f3 n2, f3 L2, f3 o, const MatOpt& m, bool use_visibility) {
+    float f_g = LinearizeVector(ReconnectDI(c, x1, n1, x2, n2, L2, o, m));
+    float v = 1.0f;
+    if (use_visibility && f_g > 0.0f) { f3 d = x2 - x1; v = VisibilityCheck(c, x1, n1, normalize3(d), length3(d)); }
+    return f_g * v;
+}
+inline f3 GetP_Hat_GI(const Ctx& c, f3 x1, f3 n1, f3 x2, f3 n2, f3 L2, f3 o, const MatOpt& m, bool use_visibility) {
+    f3 f_g = ReconnectGI(c, x1, n1, x2, n2, L2, o, m);
+    float v = 1.0f;
+    if (use_visibility && LinearizeVector(f_g) > 0.0f) { f3 d = x2 - x1; v = VisibilityCheck(c, x1, n1, normalize3(d), length3(d)); }
+    return f_g * v;
+}
+inline float GetW(float w_sum, float p_hat) { return p_hat > EPS ? w_sum / p_hat : 0.0f; }           // :183-195
+// Common_v7.hlsl:268-283, 286-307; length(half3) compared with 0 = "any component non-zero" (D10)
+inline bool nz3(f3 v) { return v.x != 0.0f || v.y != 0.0f || v.z != 0.0f; }
+inline bool RejectDistance(f3 x1, f3 x2, f3 camPos, float threshold) {
+    float d1 = length3(x1 - camPos), d2 = length3(x2 - camPos);
+    float rel = fabsf(d1 - d2) / fmaxf(d1, d2);
+    return rel > threshold;
+}
+inline bool RejectJacobian(float J, float threshold) { return J > threshold || J < 1.0f / threshold || isnan1(J) || isinf1(J); }
+inline bool IsValidReservoir(const ReservoirDI& r) { return length3(r.n2) > 0.0f && nz3(r.L2) && r.w_sum > 0.0f && r.M > 0u; }
+inline bool IsValidReservoir_GI(const ReservoirGI& r) { return r.w_sum > 0.0f && r.M > 0u; }
+// Common_v7.hlsl:326-345
+inline float Jacobian_Reconnection(const SData& r, const SData& q, f3 x2q, f3 n2q) {
+    f3 vq = x2q - q.x1, vr = x2q - r.x1;
+    float cosPhi2q = fabsf(dot3(normalize3(-vq), normalize3(n2q)));
+    float cosPhi2r = fabsf(dot3(normalize3(-vr), normalize3(n2q)));
+    float len2_vq = dot3(vq, vq), len2_vr = dot3(vr, vr);
+    return (cosPhi2q / cosPhi2r) * (len2_vr / len2_vq);
+}
+// Common_v7.hlsl:203-244 (pow(u, spatial_exponent = 1) is the identity); returns the pixel
+inline void GetRandomPixelCircleWeighted(uint32_t radius, uint32_t w, uint32_t h, uint32_t x, uint32_t y, uint32_t seed[2], int& px, int& py) {
+    int newX, newY;
+    do {
+        float u = RandomFloat(seed);
+        float r = (float)radius * u;
+        float angle = RandomFloat(seed) * 6.2831853f;
+        float sn, cs; d_sincos(angle, &sn, &cs);
+        int offsetX = (int)(cs * r), offsetY = (int)(sn * r);
+        newX = (int)x + offsetX; newY = (int)y + offsetY;
+        while (newX < 0 || newX >= (int)w) { if (newX < 0) newX = -newX; else newX = 2 * (int)w - newX - 2; }
+        while (newY < 0 || newY >= (int)h) { if (newY < 0) newY = -newY; else newY = 2 * (int)h - newY - 2; }
+    } while (newX == (int)x && newY == (int)y);
+    px = newX; py = newY;
+}
+// Sampler_v7.hlsl:738-785.  D11: a reprojection that lands outside the image is "no candidate" (the reference only tests
+// for the (-1,-1) sentinel and lets other out-of-range coordinates alias through MapPixelID / read out of bounds).
+inline bool GetBestReprojectedPixel(const orc_scene& S, const orc_camera& cam, f3 worldPos, uint32_t w, uint32_t h, uint32_t objID, int& px, int& py) {
+    if (objID >= S.instances.size()) return false;
+    const orc_instance_props& ip = S.instances[objID].p;
+    f4 lp = mul44(ip.objectToWorldInverse, worldPos.x, worldPos.y, worldPos.z, 1.0f);
+    f4 pw = mul44(ip.prevObjectToWorld, lp.x, lp.y, lp.z, lp.w);
+    f4 vp = mul44(cam.prevView, pw.x, pw.y, pw.z, pw.w);
+    f4 cp = mul44(cam.prevProjection, vp.x, vp.y, vp.z, vp.w);
+    if (cp.w <= 0.0f) return false;
+    float ndcx = cp.x / cp.w, ndcy = cp.y / cp.w;
+    float uvx = ndcx * 0.5f + 0.5f, uvy = ndcy * 0.5f + 0.5f;
+    uvy = 1.0f - uvy;
+    float fx = rintf(uvx * (float)w), fy = rintf(uvy * (float)h);      // round(): to nearest even
+    if (!(fx >= 0.0f && fx < (float)w && fy >= 0.0f && fy < (float)h)) return false;
+    px = (int)fx; py = (int)fy;
+    return true;
+}
+inline MatOpt matopt_of(const orc_scene& S, uint32_t mID) { return make_matopt(fetch_material(S, mID), mID); }
+inline uint32_t mcap(uint32_t cap, uint32_t M) { return M < cap ? M : cap; }
+
+}  // namespace
+struct orc_frames {
+    uint32_t w = 0, h = 0;
+    std::vector<ReservoirDI> cur, last;
+    std::vector<ReservoirGI> gcur, glast;
+    std::vector<SData> scur, slast;
+};
+namespace {
+
+// RayGen2, Pass_temp_di_v7.hlsl:46-204
+void TemporalPixel(const Ctx& c, const orc_camera& cam, orc_frames& F, uint32_t x, uint32_t y, uint32_t frame) {
+    const uint32_t W = F.w, H = F.h, pix = y * W + x;
+    ReservoirDI rc = F.cur[pix]; ReservoirGI gc = F.gcur[pix]; const SData sc = F.scur[pix];
+    if (sc.kind != 2u) return;
+    f4 o4 = mul44(cam.viewI, 0.0f, 0.0f, 0.0f, 1.0f);
+    const f3 init_orig = mk3(o4.x, o4.y, o4.z);
+    uint32_t seed[2]; init_seed(x, y, 2u, frame, seed);
+    int px, py;
+    if (!GetBestReprojectedPixel(*c.S, cam, sc.x1, W, H, sc.objID, px, py)) return;
+    const uint32_t tp = (uint32_t)py * W + (uint32_t)px;
+    const ReservoirDI rl = F.last[tp]; const ReservoirGI gl = F.glast[tp]; const SData sl = F.slast[tp];
+    const bool okDI = !nz3(sl.L1) && IsValidReservoir(rl) && !RejectDistance(sc.x1, sl.x1, init_orig, 0.1f) &&
+                      (rl.x2.x != 0.0f && rl.x2.y != 0.0f && rl.x2.z != 0.0f) && sl.mID == sc.mID;
+    const bool okGI = !nz3(sl.L1) && !(gl.w_sum > 5.0f) && !RejectDistance(sc.x1, sl.x1, init_orig, 0.1f) &&
+                      IsValidReservoir_GI(gl) && sl.mID == sc.mID;
+    const MatOpt m = matopt_of(*c.S, sc.mID);
+    const uint32_t CAP = 16u;
+    if (okDI) {
+        const float cM = (float)mcap(CAP, rc.M), nM = (float)mcap(CAP, rl.M);
+        const float M_sum = cM + nM;
+        float mi_c = cM / M_sum;                                                    // MIS_v7.hlsl:63-71
+        { float m_num = cM, m_den = m_num + (M_sum - cM); if (m_den > 0.0f) mi_c += (nM / M_sum) * (m_num / m_den); }
+        float mi_t = 0.0f;                                                          // :73-80
+        { float m_num = M_sum - cM, m_den = m_num + cM; if (m_den > 0.0f) mi_t = ((nM / M_sum) * m_num) / m_den; }
+        if (length3(rl.n2) == 0.0f) { mi_c = 1.0f; mi_t = 0.0f; }
+        float w_c = (mi_c * GetP_Hat(c, sc.x1, sc.n1, rc.x2, rc.n2, rc.L2, sc.o, m, false)) * rc.W;
+        float w_t = (mi_t * GetP_Hat(c, sc.x1, sc.n1, rl.x2, rl.n2, rl.L2, sc.o, m, true)) * rl.W;
+        rc.M = mcap(CAP, rc.M); rc.w_sum = w_c;
+        rc.M += mcap(CAP, rl.M);
+        UpdateReservoir(rc, w_t, rl.x2, rl.n2, rl.L2, seed);
+        float p_hat = GetP_Hat(c, sc.x1, sc.n1, rc.x2, rc.n2, rc.L2, sc.o, m, false);
+        rc.W = GetW(rc.w_sum, p_hat);
+    }
+    if (okGI) {
+        const float cM = (float)mcap(CAP, gc.M), nM = (float)mcap(CAP, gl.M);
+        const float M_sum = cM + nM;
+        float mi_c = cM / M_sum;                                                    // MIS_GI_v6.hlsl:79-95
+        { float m_num = cM, m_den = m_num + (M_sum - cM); if (m_den > 0.0f) mi_c += (nM / M_sum) * (m_num / m_den); }
+        float mi_t = 0.0f;                                                          // :97-112
+        { float m_num = M_sum - cM, m_den = m_num + cM; if (m_den > 0.0f) mi_t = ((nM / M_sum) * m_num) / m_den; }
+        f3 f_c = GetP_Hat_GI(c, sc.x1, sc.n1, gc.xn, gc.nn, gc.E3, sc.o, m, false);
+        float w_c = (mi_c * LinearizeVector(f_c)) * gc.W;
+        f3 f_t = GetP_Hat_GI(c, sc.x1, sc.n1, gl.xn, gl.nn, gl.E3, sc.o, m, true);
+        float w_t = (mi_t * LinearizeVector(f_t)) * gl.W;
+        gc.M = mcap(CAP, gc.M); gc.w_sum = w_c;
+        gc.M += mcap(CAP, gl.M);
+        UpdateReservoir_GI(gc, w_t, gl.xn, gl.nn, gl.E3, seed);
+        gc.W = GetW(gc.w_sum, LinearizeVector(GetP_Hat_GI(c, sc.x1, sc.n1, gc.xn, gc.nn, gc.E3, sc.o, m, false)));
+    }
+    F.cur[pix] = rc; F.gcur[pix] = gc;
+}
+
+// RayGen3, Pass_spat_di_v7.hlsl:46-464 up to the accumulation; returns the frame's radiance sample of the pixel
+f3 SpatialPixel(const Ctx& c, const orc_camera& cam, orc_frames& F, uint32_t x, uint32_t y, uint32_t frame) {
+    const uint32_t W = F.w, H = F.h, pix = y * W + x;
+    const SData sc = F.scur[pix];
+    if (sc.kind == 0u) { F.last[pix] = ReservoirDI(); F.glast[pix] = ReservoirGI(); F.slast[pix] = sc; return mk3(0, 0, 0); }   // D1
+    if (sc.kind == 1u) return sc.L1;                            // :458-463, accumulated (D5); the *_last buffers keep their old contents
+    f4 o4 = mul44(cam.viewI, 0.0f, 0.0f, 0.0f, 1.0f);
+    const f3 init_orig = mk3(o4.x, o4.y, o4.z);
+    uint32_t seed[2]; init_seed(x, y, 3u, frame, seed);
+    const MatOpt m = matopt_of(*c.S, sc.mID);
+    const uint32_t NC = 3u, TRIES = 9u, CAP = 128u;
+    uint32_t candDI[3], candGI[3]; uint32_t nDI = 0, nGI = 0;
+    float M_sum_DI = (float)mcap(CAP, F.cur[pix].M), M_sum_GI = (float)mcap(CAP, F.gcur[pix].M);
+    for (uint32_t attempt = 0; attempt < TRIES && nDI < NC; attempt++) {                            // :105-134
+        int px, py; GetRandomPixelCircleWeighted(20u, W, H, x, y, seed, px, py);
+        const uint32_t r = (uint32_t)py * W + (uint32_t)px;
+        const SData& sr = F.scur[r];
+        bool ok = !(dot3(sc.n1, sr.n1) < 0.9f) && !RejectDistance(sc.x1, sr.x1, init_orig, 0.1f) && IsValidReservoir(F.cur[r]) &&
+                  !nz3(sr.L1) && sr.kind == 2u && sr.mID == sc.mID;
+        if (ok) { candDI[nDI++] = r; M_sum_DI += (float)mcap(CAP, F.cur[r].M); }
+    }
+    for (uint32_t attempt = 0; attempt < TRIES && nGI < NC; attempt++) {                            // :144-186
+        int px, py; GetRandomPixelCircleWeighted(20u, W, H, x, y, seed, px, py);
+        const uint32_t r = (uint32_t)py * W + (uint32_t)px;
+        const SData& sr = F.scur[r]; const ReservoirGI& gr = F.gcur[r];
+        bool ok = m.Pr > 0.3f && !RejectDistance(sc.x1, sr.x1, init_orig, 0.1f) &&
+                  !(dot3(normalize3(gr.xn - sc.x1), sc.n1) < 0.0f) && !(gr.w_sum > 5.0f) && IsValidReservoir_GI(gr) &&
+                  !RejectJacobian(Jacobian_Reconnection(sr, sc, gr.xn, gr.nn), 5.0f) && !nz3(sr.L1) && sr.kind == 2u && sr.mID == sc.mID;
+        if (ok) { candGI[nGI++] = r; M_sum_GI += (float)mcap(CAP, gr.M); }
+    }
+    ReservoirDI rc = F.cur[pix]; ReservoirGI gc = F.gcur[pix];
+    const ReservoirDI can = rc; const ReservoirGI cang = gc;
+    // GenPairwiseMIS_canonical, MIS_v7.hlsl:2-37
+    float mi_c;
+    {
+        float c_M_min = (float)mcap(CAP, can.M), c_M_max = M_sum_DI - c_M_min;
+        float p_c = GetP_Hat(c, sc.x1, sc.n1, can.x2, can.n2, can.L2, sc.o, m, false);
+        float c_m_num = c_M_min * p_c;
+        mi_c = c_M_min / M_sum_DI;
+        for (uint32_t j = 0; j < nDI; j++) {
+            const SData& sn = F.scur[candDI[j]];
+            float n_M_min = (float)mcap(CAP, F.cur[candDI[j]].M);
+            float p_from = GetP_Hat(c, sn.x1, sn.n1, can.x2, can.n2, can.L2, sn.o, m, true);
+            float m_den = c_m_num + (c_M_max * p_from);
+            if (m_den > 0.0f) mi_c += (n_M_min / M_sum_DI) * (c_m_num / m_den);
+        }
+    }
+    float w_c = (mi_c * GetP_Hat(c, sc.x1, sc.n1, can.x2, can.n2, can.L2, sc.o, m, false)) * can.W;
+    // GenPairwiseMIS_canonical_GI, MIS_GI_v6.hlsl:2-40
+    float mi_c_gi;
+    {
+        float c_M_min = (float)mcap(CAP, cang.M), c_M_max = M_sum_GI - c_M_min;
+        float p_c = LinearizeVector(GetP_Hat_GI(c, sc.x1, sc.n1, cang.xn, cang.nn, cang.E3, sc.o, m, false));
+        float c_m_num = c_M_min * p_c;
+        float m_c = c_M_min / M_sum_GI;
+        for (uint32_t j = 0; j < nGI; j++) {
+            const SData& sn = F.scur[candGI[j]];
+            float n_M_min = (float)mcap(CAP, F.gcur[candGI[j]].M);
+            float j_gi = Jacobian_Reconnection(sc, sn, cang.xn, cang.nn);
+            float p_from = LinearizeVector(GetP_Hat_GI(c, sn.x1, sn.n1, cang.xn, cang.nn, cang.E3, sn.o, m, true)) * j_gi;
+            float m_den = c_m_num + (c_M_max * p_from);
+            if (m_den > 0.0f) m_c += (n_M_min / M_sum_GI) * (c_m_num / m_den);
+        }
+        mi_c_gi = fminf(fmaxf(m_c, 0.0f), 1.0f);
+    }
+    f3 f_c = GetP_Hat_GI(c, sc.x1, sc.n1, cang.xn, cang.nn, cang.E3, sc.o, m, false);
+    float w_c_gi = (mi_c_gi * LinearizeVector(f_c)) * cang.W;
+    rc.M = mcap(CAP, can.M); rc.w_sum = w_c;
+    gc.M = mcap(CAP, cang.M); gc.w_sum = w_c_gi;
+    for (uint32_t v = 0; v < nDI; v++) {                                                            // :252-290
+        const uint32_t sp = candDI[v]; const SData& sn = F.scur[sp]; const ReservoirDI& rn = F.cur[sp];
+        float mi_s = 0.0f;                                                                          // MIS_v7.hlsl:40-61
+        {
+            float c_M_min = (float)mcap(CAP, can.M);
+            float p_c = GetP_Hat(c, sc.x1, sc.n1, can.x2, can.n2, can.L2, sc.o, m, false);
+            float p_from = GetP_Hat(c, sn.x1, sn.n1, can.x2, can.n2, can.L2, sn.o, m, false);
+            float m_num = (M_sum_DI - c_M_min) * p_from;
+            float m_den = m_num + (c_M_min * p_c);
+            if (m_den > 0.0f) mi_s = ((float)mcap(CAP, rn.M) / M_sum_DI) * (m_num / m_den);
+        }
+        float w_s = (mi_s * GetP_Hat(c, sc.x1, sc.n1, rn.x2, rn.n2, rn.L2, sc.o, m, false)) * rn.W;
+        rc.M += mcap(CAP, rn.M);
+        UpdateReservoir(rc, w_s, rn.x2, rn.n2, rn.L2, seed);
+    }
+    for (uint32_t v = 0; v < nGI; v++) {                                                            // :293-341
+        const uint32_t sp = candGI[v]; const SData& sn = F.scur[sp]; const ReservoirGI& gn = F.gcur[sp];
+        float mi_s = 0.0f;                                                                          // MIS_GI_v6.hlsl:43-76
+        {
+            float c_M_min = (float)mcap(CAP, cang.M);
+            float p_c = LinearizeVector(GetP_Hat_GI(c, sc.x1, sc.n1, cang.xn, cang.nn, cang.E3, sc.o, m, false));
+            float j = Jacobian_Reconnection(sc, sn, cang.xn, cang.nn);
+            float p_from = LinearizeVector(GetP_Hat_GI(c, sn.x1, sn.n1, cang.xn, cang.nn, cang.E3, sn.o, m, false)) * j;
+            float m_num = (M_sum_GI - c_M_min) * p_from;
+            float m_den = m_num + (c_M_min * p_c);
+            if (m_den > 0.0f) mi_s = fminf(fmaxf(((float)mcap(CAP, gn.M) / M_sum_GI) * (m_num / m_den), 0.0f), 1.0f);
+        }
+        float j_gi = Jacobian_Reconnection(sn, sc, gn.xn, gn.nn);
+        f3 f_gi = GetP_Hat_GI(c, sc.x1, sc.n1, gn.xn, gn.nn, gn.E3, sc.o, m, true);
+        float w_s = ((mi_s * LinearizeVector(f_gi)) * gn.W) * j_gi;
+        if (j_gi != 0.0f) { gc.M += mcap(CAP, gn.M); UpdateReservoir_GI(gc, w_s, gn.xn, gn.nn, gn.E3, seed); }
+    }
+    float p_hat = GetP_Hat(c, sc.x1, sc.n1, rc.x2, rc.n2, rc.L2, sc.o, m, true);                    // :343-353
+    rc.W = GetW(rc.w_sum, p_hat);
+    f3 accumulation = ReconnectDI(c, sc.x1, sc.n1, rc.x2, rc.n2, rc.L2, sc.o, m) * rc.W;
+    f3 f_fin = GetP_Hat_GI(c, sc.x1, sc.n1, gc.xn, gc.nn, gc.E3, sc.o, m, false);                   // :367-381
+    gc.W = GetW(gc.w_sum, LinearizeVector(f_fin));
+    accumulation = accumulation + f_fin * gc.W;
+    F.last[pix] = rc; F.glast[pix] = gc; F.slast[pix] = sc;                                         // :434-436
+    return accumulation;
 }
 
 // shaders/Common_v7.hlsl:353-376
@@ -1040,6 +1293,61 @@ void orc_render_rows(orc_scene* s, const orc_config* cfg, const orc_camera* cam,
                 if (!any_nan_inf(C)) { px[0] += C.x; px[1] += C.y; px[2] += C.z; px[3] += 1.0f; }
             }
         }
+}
+
+orc_frames* orc_frames_create(uint32_t w, uint32_t h) {
+    orc_frames* F = new orc_frames(); F->w = w; F->h = h;
+    const size_t n = (size_t)w * h;
+    ReservoirDI zr; memset(&zr, 0, sizeof zr); ReservoirGI zg; memset(&zg, 0, sizeof zg); SData zs; memset(&zs, 0, sizeof zs);
+    F->cur.assign(n, zr); F->last.assign(n, zr); F->gcur.assign(n, zg); F->glast.assign(n, zg); F->scur.assign(n, zs); F->slast.assign(n, zs);
+    return F;
+}
+void orc_frames_destroy(orc_frames* F) { delete F; }
+
+// One frame of the reference's dispatch sequence (rdn/Renderer.cpp:611-673): RayGen (pass 1) for every pixel, RayGen2
+// (temporal reuse), RayGen3 (spatial reuse, final shade, accumulation F20).  uint(time) := frame_index (D2).
+void orc_render_frame(orc_scene* s, const orc_config* cfg, const orc_camera* cam, uint32_t frame_index, orc_frames* F, float* accum,
+                      orc_counters* counters, int trace_mode) {
+    orc_counters local; memset(&local, 0, sizeof local);
+    Ctx c; c.S = s; c.cfg = *cfg; c.C = counters ? counters : &local; c.mode = trace_mode;
+    const uint32_t W = cfg->width, H = cfg->height;
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            PixelDebug d; memset(&d, 0, sizeof d); d.hit_inst = 0xFFFFFFFFu;
+            RenderSample(c, *cam, x, y, frame_index, &d);
+            const size_t pix = (size_t)y * W + x;
+            ReservoirDI zr; memset(&zr, 0, sizeof zr); ReservoirGI zg; memset(&zg, 0, sizeof zg); SData sd; memset(&sd, 0, sizeof sd);
+            sd.kind = d.kind;
+            if (d.kind == 1u) { sd.mID = d.mID & 0xFFFFu; sd.L1 = d.L1; sd.objID = d.hit_inst; }       // Pass_init_di_v7.hlsl:129-137
+            if (d.kind == 2u) {
+                sd.x1 = d.x1; sd.n1 = normalize3(d.n1); sd.o = -d.cam_d; sd.mID = d.mID & 0xFFFFu; sd.objID = d.hit_inst;   // :161-164
+                zr = d.rdi; zg = d.rgi;
+            }
+            F->cur[pix] = zr; F->gcur[pix] = zg; F->scur[pix] = sd;
+        }
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) TemporalPixel(c, *cam, *F, x, y, frame_index);
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            f3 C = SpatialPixel(c, *cam, *F, x, y, frame_index);
+            float* px = accum + 4 * ((size_t)y * W + x);
+            if (!any_nan_inf(C)) { px[0] += C.x; px[1] += C.y; px[2] += C.z; px[3] += 1.0f; }      // Pass_spat_di_v7.hlsl:388-404
+        }
+}
+
+// the *_last buffers after a frame, 40 floats per pixel:
+// [0..3] x2,w_sum [4..7] n2,W [8..10] L2 [11] M | [12..15] xn,w_sum [16..19] nn,W [20..22] E3 [23] M |
+// [24..26] x1 [27] mID [28..30] n1 [31] objID [32..34] o [35] kind [36..38] L1
+void orc_frames_dump(const orc_frames* F, float* out) {
+    const size_t n = (size_t)F->w * F->h;
+    for (size_t i = 0; i < n; i++) {
+        float* o = out + 40 * i; memset(o, 0, 40 * sizeof(float));
+        const ReservoirDI& r = F->last[i]; const ReservoirGI& g = F->glast[i]; const SData& s = F->slast[i];
+        auto put3 = [&](int k, f3 v) { o[k] = v.x; o[k + 1] = v.y; o[k + 2] = v.z; };
+        put3(0, r.x2); o[3] = r.w_sum; put3(4, r.n2); o[7] = r.W; put3(8, r.L2); o[11] = (float)r.M;
+        put3(12, g.xn); o[15] = g.w_sum; put3(16, g.nn); o[19] = g.W; put3(20, g.E3); o[23] = (float)g.M;
+        put3(24, s.x1); o[27] = (float)s.mID; put3(28, s.n1); o[31] = (float)s.objID; put3(32, s.o); o[35] = (float)s.kind; put3(36, s.L1);
+    }
 }
 
 void orc_resolve(const float* accum, uint32_t n_pixels, uint8_t* rgba8) {

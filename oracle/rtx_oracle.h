@@ -71,6 +71,14 @@ void orc_render(orc_scene*, const orc_config*, const orc_camera*, uint32_t first
 /* same, rows [y0, y1) only; disjoint row ranges may run concurrently on several host threads */
 void orc_render_rows(orc_scene*, const orc_config*, const orc_camera*, uint32_t first_sample, uint32_t n_samples,
                      uint32_t step, uint32_t y0, uint32_t y1, float* accum, orc_counters* counters, int trace_mode);
+/* The reference's whole frame: pass 1 (RayGen) + temporal reuse (RayGen2) + spatial reuse, final
+ * shade and accumulation (RayGen3).  orc_frames holds the per-pixel reservoir / sample buffers u2..u7 (current and last). */
+typedef struct orc_frames orc_frames;
+orc_frames* orc_frames_create(uint32_t width, uint32_t height);
+void        orc_frames_destroy(orc_frames*);
+void orc_render_frame(orc_scene*, const orc_config*, const orc_camera*, uint32_t frame_index, orc_frames*, float* accum,
+                      orc_counters* counters, int trace_mode);
+void orc_frames_dump(const orc_frames*, float* out40_per_pixel);   /* the *_last buffers, layout in rtx_oracle.cpp */
 /* F20 output: sRGB(sum/n) -> RGBA8 */
 void orc_resolve(const float* accum, uint32_t n_pixels, uint8_t* rgba8);
 

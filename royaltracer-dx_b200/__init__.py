@@ -33,7 +33,7 @@ hit_dt = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("
 assert vertex_dt.itemsize == 28 and material_dt.itemsize == 128 and props_dt.itemsize == 384 and light_dt.itemsize == 80
 assert camera_dt.itemsize == 512 and desc_dt.itemsize == 64 and ray_dt.itemsize == 32 and hit_dt.itemsize == 20
 
-FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL = 1, 2, 4
+FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL, FLAG_RESTIR = 1, 2, 4, 8
 OPT_TRACE_STATS, OPT_STAGE_TIMING = 1, 2
 MISS = 0xFFFFFFFF
 STAGE_NAMES = ["generate", "closest", "any", "shade_primary", "di_finish", "gi_step", "scatter", "finalize", "accumulate", "sort"]
@@ -59,7 +59,7 @@ ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model"
                "rtx_set_materials", "rtx_set_instances", "rtx_set_emissive_triangles", "rtx_set_camera", "rtx_render_pass",
                "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_accum_device_ptr", "rtx_trace",
                "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel",
-               "rtx_selftest_dmath"]
+               "rtx_selftest_dmath", "rtx_render_frame", "rtx_reset_restir", "rtx_read_restir"]
 HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut"]
 
 _lib = None
@@ -106,6 +106,9 @@ def load_library():
     lib.rtx_debug_pixel.argtypes = [vp, u32, u32, vp]
     lib.rtx_set_option.argtypes = [vp, u32, u32]
     lib.rtx_selftest_dmath.argtypes = [vp, vp, u32]
+    lib.rtx_render_frame.argtypes = [vp, u32]
+    lib.rtx_reset_restir.argtypes = [vp]
+    lib.rtx_read_restir.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -264,6 +267,18 @@ class Context:
 
     def render_pass(self, first_sample, n_samples):
         self._check(self.lib.rtx_render_pass(self.handle, first_sample, n_samples))
+
+    def render_frame(self, frame_index):
+        """The reference's 3-pass frame (RayGen, RayGen2, RayGen3); the context needs FLAG_RESTIR."""
+        self._check(self.lib.rtx_render_frame(self.handle, frame_index))
+
+    def reset_restir(self):
+        self._check(self.lib.rtx_reset_restir(self.handle))
+
+    def read_restir(self):
+        out = np.zeros((self.height, self.width, 40), dtype=np.float32)
+        self._check(self.lib.rtx_read_restir(self.handle, _ptr(out)))
+        return out
 
     def reset_accum(self):
         self._check(self.lib.rtx_reset_accum(self.handle))

@@ -5,6 +5,7 @@
 #include <mutex>
 #include <vector>
 
+#include "restir.h"
 #include "trace.h"
 #include "wavefront.h"
 
@@ -35,6 +36,7 @@ struct rtx_ctx {
     rtx_light_triangle* d_lights = nullptr; uint32_t n_lights = 0;
     rtx_camera_params cam; bool have_cam = false;
     WaveBuffers wb; bool wb_ready = false;
+    RestirBuffers rs; bool rs_ready = false;
     float4* d_trace_o = nullptr; float4* d_trace_d = nullptr; float4* d_trace_ha = nullptr; uint32_t* d_trace_hi = nullptr;
     rtx_hit* d_trace_out = nullptr; uint32_t trace_cap = 0;
     TraceStats* d_stats = nullptr;
@@ -90,6 +92,7 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     free_bvh(&c->tlas);
     free_tables(c);
     if (c->wb_ready) wave_free(&c->wb);
+    if (c->rs_ready) restir_free(&c->rs);
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -267,6 +270,60 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
         done += spp;
     }
     c->pass_timed = true;
+    return RTX_OK;
+}
+
+static rtx_status ensure_restir(rtx_ctx* c) {
+    if (!(c->cfg.flags & RTX_FLAG_RESTIR)) return fail(RTX_ERR_STATE, "ReSTIR entry point on a context created without RTX_FLAG_RESTIR");
+    if (c->cfg.samples_per_pass != 1) return fail(RTX_ERR_STATE, "RTX_FLAG_RESTIR needs samples_per_pass == 1 (one sample per frame, as the reference)");
+    if (c->rs_ready) return RTX_OK;
+    RTX_CK(restir_alloc(&c->rs, c->cfg.width, c->cfg.height));
+    RTX_CK(restir_clear(c->rs, c->stream));
+    c->rs_ready = true;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
+    if (!c) return fail(RTX_ERR_ARG, "rtx_render_frame: null context");
+    if (!c->have_cam) return fail(RTX_ERR_STATE, "rtx_render_frame: camera not set");
+    if (!c->n_instances || !c->tlas.nodes) return fail(RTX_ERR_STATE, "rtx_render_frame: no instances");
+    if (!c->d_materials || !c->d_material_ids) return fail(RTX_ERR_STATE, "rtx_render_frame: materials not set");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if (!c->d_lights && (st = rtx_set_emissive_triangles(c, nullptr, 0)) != RTX_OK) return st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    if ((st = ensure_restir(c)) != RTX_OK) return st;
+    SceneData S;
+    S.models = c->d_model_refs; S.inst_model = c->d_inst_model; S.props = c->d_props;
+    S.material_ids = c->d_material_ids; S.n_material_ids = c->n_material_ids;
+    S.materials = c->d_materials; S.n_materials = c->n_materials;
+    S.lights = c->d_lights;
+    S.cfg_flags = c->cfg.flags; S.bounces = c->cfg.bounces; S.nee_samples = c->cfg.nee_samples; S.nee_samples_di = c->cfg.nee_samples_di;
+    S.width = c->cfg.width; S.height = c->cfg.height;
+    const SceneAS AS = make_as(c);
+    c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
+    RTX_CK(wave_render_pass(c->wb, S, AS, frame_index, 1, c->stream, &c->launches, &c->timing, false));     // RayGen
+    RTX_CK(restir_store_pass1(c->rs, c->wb, S, c->stream, &c->launches));
+    RTX_CK(restir_reuse_passes(c->rs, c->wb, S, AS, frame_index, c->stream, &c->launches));                 // RayGen2, RayGen3
+    c->pass_timed = true;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_reset_restir(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_restir(c)) != RTX_OK) return st;
+    RTX_CK(restir_clear(c->rs, c->stream));
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_read_restir(rtx_ctx* c, float* out) {
+    if (!c || !out) return fail(RTX_ERR_ARG, "rtx_read_restir: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_restir(c)) != RTX_OK) return st;
+    RTX_CK(restir_dump(c->rs, c->stream, out));
     return RTX_OK;
 }
 

@@ -12,6 +12,7 @@
 // arrays (wavefront.h); queue slots are claimed with one atomic per warp (ballot + popc compaction).
 #include "trace.h"
 #include "wavefront.h"
+#include "wave_dev.cuh"
 
 namespace rtx {
 
@@ -28,32 +29,6 @@ namespace rtx {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
-
-struct StateView {
-    float4* base; uint32_t n;
-    __device__ __forceinline__ float4& at(int plane, uint32_t pid) const { return base[(size_t)plane * n + pid]; }
-};
-
-__device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
-__device__ __forceinline__ float4 f4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
-__device__ __forceinline__ float4 f4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }
-
-// Warp-level queue compaction: one atomicAdd per warp claims a contiguous run of slots.  Must be reached by all 32 lanes.
-__device__ __forceinline__ void push_ray(const RayQueue& q, bool emit, f3 o, float tmin, f3 d, float tmax, uint32_t pid) {
-    const unsigned mask = __ballot_sync(0xffffffffu, emit);
-    if (mask == 0u) return;
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if ((int)lane == leader) base = atomicAdd(q.count, (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (emit) {
-        const unsigned slot = base + __popc(mask & ((1u << lane) - 1u));
-        q.o_tmin[slot] = f4(o, tmin);
-        q.d_tmax[slot] = f4(d, tmax);
-        q.pid[slot] = pid;
-    }
-}
 
 // camera ray, shaders/Pass_init_di_v7.hlsl:59,80-95
 __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t W, uint32_t H, uint32_t x, uint32_t y, float jx, float jy,
@@ -135,7 +110,9 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
             f3 ke_full;
             const MatOpt mat = load_matopt(S, payload.materialID, &ke_full);
             if (length3(ke_full) > 0.0f) {                          // :103-106 ; L1 = half3(Ke) (deviation D5: accumulated)
-                st.at(SP_RESULT, pid) = f4(mat.Ke, 0.0f);
+                st.at(SP_RESULT, pid) = f4(mat.Ke, 3.0f);          // .w: 0 miss, 3 emitter, 1 sampled (2 once finalized)
+                st.at(SP_X1, pid) = f4u(mk3(0, 0, 0), payload.materialID);
+                st.at(SP_DI_L2, pid) = f4u(mk3(0, 0, 0), inst);
             } else {
                 uint2 seed = make_uint2(__float_as_uint(st.at(SP_N1, pid).w), __float_as_uint(st.at(SP_O, pid).w));
                 const f3 outgoing = -d;
@@ -160,7 +137,7 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
                 st.at(SP_O, pid) = f4u(outgoing, seed.y);
                 st.at(SP_DI_X2, pid) = f4(rx, w_sum);
                 st.at(SP_DI_N2, pid) = f4(rn, 0.0f);
-                st.at(SP_DI_L2, pid) = f4(rL, 0.0f);
+                st.at(SP_DI_L2, pid) = f4u(rL, inst);              // .w: primary-hit instance (SampleData::objID)
                 st.at(SP_RESULT, pid) = make_float4(0, 0, 0, 1.0f);
             }
         }
@@ -186,7 +163,8 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
         const MatOpt mat = load_matopt(S, mID, nullptr);
         float4 b0 = st.at(SP_DI_X2, pid);
-        f3 rx = xyz(b0), rn = xyz(st.at(SP_DI_N2, pid)), rL = xyz(st.at(SP_DI_L2, pid)); float w_sum = b0.w;
+        const float4 b2 = st.at(SP_DI_L2, pid);
+        f3 rx = xyz(b0), rn = xyz(st.at(SP_DI_N2, pid)), rL = xyz(b2); float w_sum = b0.w;
         const f3 sample = xyz(qin.d_tmax[j]);
         const uint32_t inst = hit_inst[j];
         if (inst != 0xFFFFFFFFu) {                                  // miss => materials[MISS] reads 0 => p_hat = 0
@@ -235,7 +213,7 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         }
         st.at(SP_DI_X2, pid) = f4(rx, w_sum);
         st.at(SP_DI_N2, pid) = f4(rn, f_g);
-        st.at(SP_DI_L2, pid) = f4(rL, 0.0f);
+        st.at(SP_DI_L2, pid) = f4(rL, b2.w);
         st.at(SP_DI_R, pid) = f4(rdi, 0.0f);
         // SamplePathSimple step 1: Path_Sampler_v7.hlsl:24-52
         const f3 outgoing = normalize3(o);
@@ -303,7 +281,9 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         float4 c0 = st.at(SP_GI_XN, pid), c1 = st.at(SP_GI_NN, pid);
         f3 xn = xyz(c0), nn = xyz(c1), E3 = xyz(st.at(SP_GI_E3, pid));
         float w_sum = c0.w, acc_pdf = c1.w;
-        f3 x1s = xyz(st.at(SP_SH1, pid)), x2s = xyz(st.at(SP_SH2, pid));
+        const float4 sh2 = st.at(SP_SH2, pid);
+        f3 x1s = xyz(st.at(SP_SH1, pid)), x2s = xyz(sh2);
+        float gi_has = sh2.w;                                       // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
         float4 a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
         uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
         MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
@@ -369,7 +349,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                     float wi = length3(E_path);
                     if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
                     w_sum += wi;
-                    if (RandomFloat(seed) < wi / w_sum) { E3 = q16v(E_reconnection); }   // UpdateReservoir_GI; (xn, nn) are the path's
+                    if (RandomFloat(seed) < wi / w_sum) { E3 = q16v(E_reconnection); gi_has = 1.0f; }   // UpdateReservoir_GI; (xn, nn) are the path's
                 } else if (!emitter) {
                     origin = sp.hitPosition; material = hm; outgoing = -sample; normal = sp.hitNormal;
                     cont = true;
@@ -399,7 +379,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
                 w_sum += wi;
                 if (RandomFloat(seed) < wi / w_sum) {
-                    E3 = q16v(E_reconnection);
+                    E3 = q16v(E_reconnection); gi_has = 1.0f;
                     x1s = origin + RTX_S_BIAS * Nn;
                     x2s = x2;
                 }
@@ -425,7 +405,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         st.at(SP_GI_NN, pid) = f4(nn, acc_pdf);
         st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
         st.at(SP_SH1, pid) = f4(x1s, 0.0f);
-        st.at(SP_SH2, pid) = f4(x2s, 0.0f);
+        st.at(SP_SH2, pid) = f4(x2s, gi_has);
         st.at(SP_N1, pid) = make_float4(a1.x, a1.y, a1.z, __uint_as_float(seed.x));
         st.at(SP_O, pid) = make_float4(a2.x, a2.y, a2.z, __uint_as_float(seed.y));
     }
@@ -441,7 +421,7 @@ k_finalize(StateView st, SceneData S, const float* __restrict__ vis_di, const fl
     if (p == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
     if (p >= st.n) return;
     const float4 res = st.at(SP_RESULT, p);
-    if (res.w == 0.0f) return;
+    if (res.w != 1.0f) return;
     const float4 a0 = st.at(SP_X1, p);
     const f3 x1 = xyz(a0), hitNormal = xyz(st.at(SP_N1, p)), o = xyz(st.at(SP_O, p));
     const MatOpt mat = load_matopt(S, __float_as_uint(a0.w), nullptr);
@@ -461,7 +441,7 @@ k_finalize(StateView st, SceneData S, const float* __restrict__ vis_di, const fl
     st.at(SP_GI_XN, p) = make_float4(c0.x, c0.y, c0.z, w_sum_gi);
     st.at(SP_DI_R, p) = f4(rdi, W);
     st.at(SP_GI_E3, p).w = W_GI;
-    st.at(SP_DI_L2, p).w = p_hat;
+    st.at(SP_SH1, p).w = p_hat;
 }
 
 // ---- F20 accumulation, Pass_spat_di_v7.hlsl:383-404: drop non-finite samples, sum += C, n += 1 (samples in index order)
@@ -506,7 +486,7 @@ __global__ void k_debug_pixel(StateView st, uint32_t p, const float* vis_di, con
     put3(16, b0); out[19] = b0.w; put3(20, b1); out[23] = b3.w; put3(24, b2);
     const float4 c0 = st.at(SP_GI_XN, p), c1 = st.at(SP_GI_NN, p), c2 = st.at(SP_GI_E3, p);
     put3(27, c0); out[30] = c0.w; put3(31, c1); out[34] = c2.w; put3(35, c2);
-    out[38] = b2.w;
+    out[38] = st.at(SP_SH1, p).w;
     put3(39, st.at(SP_RESULT, p));
     out[42] = a1.w; out[43] = a2.w;
     out[49] = st.at(SP_RESULT, p).w; out[50] = vis_di[p]; out[51] = vis_gi[p]; out[52] = b1.w;
@@ -567,7 +547,7 @@ k_scatter_vis(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ p
 }
 
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
-                             uint64_t* launches, PassTiming* T) {
+                             uint64_t* launches, PassTiming* T, bool accumulate) {
     const uint32_t npx = S.width * S.height;
     const uint32_t n = npx * spp;
     if (n > B.n_paths) return cudaErrorInvalidValue;
@@ -627,8 +607,10 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     CKE(shadow(sgi, B.vis_gi));
     CKE(mark(SK_FINALIZE));
     k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters);
-    CKE(mark(SK_ACCUMULATE));
-    k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
+    if (accumulate) {       // E0: the pass's samples go straight to gPermanentData; the ReSTIR frame accumulates after RayGen3
+        CKE(mark(SK_ACCUMULATE));
+        k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
+    }
     CKE(cudaEventRecord(T->ev[1], stream));
     CKE(cudaGetLastError());
     if (launches) *launches += L;
