@@ -30,6 +30,21 @@ acc, ctr = osc.render(cam, W, H, 0, 4, bounces=2, flags=3)
 hits = osc.trace(rtdx.scenes.camera_rays(cam, W, H), mode=0)
 g["cornell"] = {"size": W, "spp": 4, "closest_rays": ctr["closest_rays"], "shadow_rays": ctr["shadow_rays"],
                 "accum_bits": [int(v) for v in acc.view(np.uint32).reshape(-1)], "primary_prim": [int(v) for v in hits["prim"]]}
+# ReSTIR frames: 3 frames of the 3-pass sequence, static camera, GGX allowed
+import zlib  # noqa: E402
+W2, H2 = 32, 24
+props, descs, lights, cam2 = host_inputs(rtdx, sc, W2, H2)
+fr = osc.new_frames(W2, H2)
+acc2 = np.zeros((H2, W2, 4), dtype=np.float32)
+tot = {"closest_rays": 0, "shadow_rays": 0}
+for f_i in range(3):
+    c = osc.render_frame(cam2, W2, H2, f_i, fr, acc2, bounces=2)
+    tot["closest_rays"] += c["closest_rays"]; tot["shadow_rays"] += c["shadow_rays"]
+dump = osc.dump_frames(fr, W2, H2)
+g["restir"] = {"width": W2, "height": H2, "frames": 3, "bounces": 2, "closest_rays": tot["closest_rays"], "shadow_rays": tot["shadow_rays"],
+               "accum_bits": [int(v) for v in acc2.view(np.uint32).reshape(-1)],
+               "reservoir_crc32": int(zlib.crc32(np.ascontiguousarray(dump).view(np.uint8).tobytes())),
+               "M_di_sum": int(dump[..., 11].sum()), "M_gi_sum": int(dump[..., 23].sum())}
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_kat.json"), "w") as f:
     json.dump(g, f)
 print("wrote golden_kat.json", len(json.dumps(g)), "bytes")

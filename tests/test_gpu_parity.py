@@ -261,6 +261,26 @@ def test_cuda_path_matches_committed_golden_fixtures(rtdx):
     ctx.close()
 
 
+def test_restir_cuda_path_matches_committed_golden(rtdx):
+    """3 ReSTIR frames on the engine against tests/golden/golden_kat.json["restir"] — no oracle call at run time."""
+    import json
+    import os
+    import zlib
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kat.json")) as f:
+        g = json.load(f)["restir"]
+    W, H = g["width"], g["height"]
+    ctx, up = _upload(rtdx, rtdx.scenes.cornell(), W, H, bounces=g["bounces"], flags=rtdx.FLAG_RESTIR)
+    ctx.reset_counters()
+    for f in range(g["frames"]):
+        ctx.render_frame(f)
+    ctx.synchronize()
+    cnt = ctx.counters()
+    assert cnt["closest_rays"] == g["closest_rays"] and cnt["shadow_rays"] == g["shadow_rays"]
+    assert [int(v) for v in ctx.read_accum().view(np.uint32).reshape(-1)] == g["accum_bits"]
+    assert int(zlib.crc32(np.ascontiguousarray(ctx.read_restir()).view(np.uint8).tobytes())) == g["reservoir_crc32"]
+    ctx.close()
+
+
 def test_full_size_properties_c2(rtdx):
     """BASELINE config C2 at full size (1M triangles, 1920x1080, bounces 6): size-independent properties instead of an oracle
     run — determinism (two renders of the same sample are bit-identical), sample counting, ray-count bound 5 + bounces per

@@ -270,6 +270,65 @@ def test_oracle_matches_committed_golden_vectors(rtdx, orc):
     assert [int(v) for v in hits["prim"]] == g["cornell"]["primary_prim"]
 
 
+def _restir_oracle_run(rtdx, orc, W, H, n_frames, bounces=2):
+    sc = rtdx.scenes.cornell()
+    props, descs, lights, cam = host_inputs(rtdx, sc, W, H)
+    osc = orc.OracleScene(sc, props, lights)
+    fr = osc.new_frames(W, H)
+    acc = np.zeros((H, W, 4), dtype=np.float32)
+    tot = {"closest_rays": 0, "shadow_rays": 0}
+    dumps = []
+    for f in range(n_frames):
+        c = osc.render_frame(cam, W, H, f, fr, acc, bounces=bounces)
+        tot["closest_rays"] += c["closest_rays"]; tot["shadow_rays"] += c["shadow_rays"]
+        dumps.append(osc.dump_frames(fr, W, H).copy())
+    osc.free_frames(fr)
+    return osc, cam, acc, tot, dumps
+
+
+def test_restir_oracle_matches_committed_golden(rtdx, orc):
+    """the oracle's 3-pass frame (RayGen, RayGen2, RayGen3) against the committed fixture."""
+    import zlib
+    with open(GOLDEN) as f:
+        g = json.load(f)["restir"]
+    _, _, acc, tot, dumps = _restir_oracle_run(rtdx, orc, g["width"], g["height"], g["frames"], g["bounces"])
+    assert tot["closest_rays"] == g["closest_rays"] and tot["shadow_rays"] == g["shadow_rays"]
+    assert [int(v) for v in acc.view(np.uint32).reshape(-1)] == g["accum_bits"]
+    assert int(zlib.crc32(np.ascontiguousarray(dumps[-1]).view(np.uint8).tobytes())) == g["reservoir_crc32"]
+
+
+def test_restir_oracle_invariants(rtdx, orc):
+    """Closed-form properties the reference source fixes for the reuse passes:
+    * frame 0 has no history (zero-filled *_last buffers are invalid reservoirs): its temporal pass changes nothing, so M <= 1 + 3
+      spatial candidates of M = 1 (Pass_temp_di_v7.hlsl:88-107, Common_v7.hlsl:307-322);
+    * the confidence M of a DI reservoir never exceeds spatial cap arithmetic: min(16, M) + min(16, M_last) after RayGen2, and after
+      RayGen3 at most 4 * 32 (Pass_temp_di_v7.hlsl:117,135-142; Pass_spat_di_v7.hlsl:95,129);
+    * with a static camera every sampled pixel reprojects onto itself (Sampler_v7.hlsl:738-785), so M grows frame over frame;
+    * emitter pixels bypass reuse and deliver half3(Ke) (Pass_spat_di_v7.hlsl:458-463); every pixel gets exactly one sample per frame."""
+    W, H, N = 40, 32, 4
+    osc, cam, acc, tot, dumps = _restir_oracle_run(rtdx, orc, W, H, N)
+    kind = dumps[-1][..., 35]
+    M = [d[..., 11] for d in dumps]
+    sampled = kind == 2
+    assert sampled.sum() > 0.3 * W * H
+    assert M[0][sampled].max() <= 4 and M[0][sampled].min() >= 1
+    for f in range(1, N):
+        assert M[f][sampled].mean() > M[f - 1][sampled].mean()          # history is reused
+        assert M[f].max() <= 4 * 32
+    assert (acc[..., 3] == N).all()
+    assert np.isfinite(acc).all()
+    # E0 (no reuse) and the ReSTIR estimate agree on the image mean within Monte-Carlo noise
+    e0, _ = osc.render(cam, W, H, 0, N, bounces=2)
+    m_restir, m_e0 = acc[..., :3][sampled].mean(), e0[..., :3][sampled].mean()
+    assert abs(m_restir - m_e0) < 0.25 * m_e0, (m_restir, m_e0)
+    # the pairwise-MIS weights of the temporal pass sum to 1 (MIS_v7.hlsl:63-80)
+    for cM, nM in [(1, 1), (1, 16), (7, 16), (16, 16)]:
+        Ms = np.float32(cM + nM)
+        mc = np.float32(cM) / Ms + (np.float32(nM) / Ms) * (np.float32(cM) / (np.float32(cM) + (Ms - np.float32(cM))))
+        mt = ((np.float32(nM) / Ms) * (Ms - np.float32(cM))) / ((Ms - np.float32(cM)) + np.float32(cM))
+        assert abs(float(mc + mt) - 1.0) < 1e-6
+
+
 def test_e0_estimator_sanity(rtdx, orc):
     """The E0 image of the Cornell box: emitter pixels carry half3(Ke), walls are lit (finite, non-negative), ray counts
     obey the per-path bound 5 + bounces."""

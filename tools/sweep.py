@@ -104,6 +104,35 @@ def c3():
     ctx.close()
 
 
+def restir(width=1920, height=1080, side=296, bounces=3, frames=8):
+    """The reference's own frame (3 DispatchRays: RayGen, RayGen2, RayGen3) on the C2 scene at the reference's defaults
+    (1920x1080, bounces 3): ms/frame and Mrays/s, next to the E0 pass (pass 1 + accumulate only) on the same context."""
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    sc = rtdx.scenes.mesh_room(n=side)
+    ctx = rtdx.Context(width, height, bounces=bounces, flags=rtdx.FLAG_RESTIR, stream=stream.cuda_stream)
+    ctx.upload_scene(sc)
+    out = {"config": "restir_frame", "scene": sc.name, "triangles": sc.n_triangles(), "width": width, "height": height, "bounces": bounces}
+    for mode in ("e0_pass", "restir_frame"):
+        step = (lambda f: ctx.render_pass(f, 1)) if mode == "e0_pass" else (lambda f: ctx.render_frame(f))
+        for f in range(3):
+            step(f)
+        ctx.synchronize(); ctx.reset_counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in range(frames):
+            step(3 + f)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / frames
+        c = ctx.counters()
+        rays = (c["closest_rays"] + c["shadow_rays"]) / frames
+        out[mode] = {"ms": ms, "rays_per_frame": rays, "Mrays_per_s": rays / ms / 1e3, "closest_rays": c["closest_rays"] / frames,
+                     "shadow_rays": c["shadow_rays"] / frames}
+    d = ctx.read_restir()
+    out["M_di_mean"] = float(d[..., 11].mean()); out["M_gi_mean"] = float(d[..., 23].mean())
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
 def bounce_rays(rays_t, hits_t, gen):
     """incoherent class: cosine-hemisphere bounces from the primary hits (seed 7), built with torch on the device."""
     o, d = rays_t[:, 0:3], rays_t[:, 4:7]
@@ -187,6 +216,8 @@ if __name__ == "__main__":
         c1()
     elif which == "c3":
         c3()
+    elif which == "restir":
+        restir()
     else:
         sizes = [int(float(x)) for x in sys.argv[2:]] or [10_000, 100_000, 1_000_000, 10_000_000, 50_000_000]
         c5(sizes)
