@@ -60,7 +60,8 @@ ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model"
                "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_accum_device_ptr", "rtx_trace",
                "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel",
                "rtx_selftest_dmath", "rtx_render_frame", "rtx_reset_restir", "rtx_read_restir"]
-HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut"]
+HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut",
+                "rdx_obj_load", "rdx_obj_free", "rdx_obj_error", "rdx_obj_counts", "rdx_obj_copy"]
 
 _lib = None
 _host = None
@@ -129,6 +130,13 @@ def load_host_library():
     h.rdx_camera_params.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     h.rdx_camera_params.restype = None
     h.rdx_generate_ess_lut.argtypes = [vp, u32]
+    h.rdx_obj_load.argtypes = [C.c_char_p, u32, C.c_char_p, u32]
+    h.rdx_obj_load.restype = vp
+    h.rdx_obj_free.argtypes = [vp]
+    h.rdx_obj_error.argtypes = [vp]
+    h.rdx_obj_error.restype = C.c_char_p
+    h.rdx_obj_counts.argtypes = [vp, vp]
+    h.rdx_obj_copy.argtypes = [vp, vp, vp, vp, vp]
     h.rdx_generate_ess_lut.restype = None
     _host = h
     return h
@@ -180,6 +188,25 @@ def camera_params(eye, center, up, aspect, fovy_deg=60.0, zn=0.1, zf=1000.0):
     e, c, u = (np.ascontiguousarray(np.asarray(v, dtype=np.float32)) for v in (eye, center, up))
     h.rdx_camera_params(_ptr(e), _ptr(c), _ptr(u), fovy_deg, aspect, zn, zf, _ptr(cam))
     return cam
+
+
+def load_obj(path, material_offset=0, mtl_dir=None, lut_seed=12345):
+    """src/Util/ObjLoader.h:393-495 (ObjLoader::loadObjFile): OBJ/MTL -> vertices (de-duplicated by position), indices, one global
+    material id per face-vertex, and this model's material block [default, mtl...]."""
+    h = load_host_library()
+    hd = C.c_void_p(h.rdx_obj_load(os.fsencode(path), material_offset, os.fsencode(mtl_dir) if mtl_dir else None, lut_seed))
+    try:
+        err = h.rdx_obj_error(hd)
+        if err:
+            raise RtxError("load_obj: " + err.decode())
+        cnt = np.zeros(4, dtype=np.uint32)
+        h.rdx_obj_counts(hd, _ptr(cnt))
+        v = np.zeros(int(cnt[0]), dtype=vertex_dt); idx = np.zeros(int(cnt[1]), dtype=np.uint32)
+        mids = np.zeros(int(cnt[2]), dtype=np.uint32); mats = np.zeros(int(cnt[3]), dtype=material_dt)
+        h.rdx_obj_copy(hd, _ptr(v), _ptr(idx), _ptr(mids), _ptr(mats))
+    finally:
+        h.rdx_obj_free(hd)
+    return {"vertices": v, "indices": idx, "material_ids": mids, "materials": mats}
 
 
 def generate_ess_lut(materials, seed=12345):

@@ -4,7 +4,7 @@ entry 0 of the material list = the loader's default material, src/Util/ObjLoader
 """
 import numpy as np
 
-from . import generate_ess_lut, material_dt, ray_dt, vertex_dt, xmmatrix_from_colvec
+from . import generate_ess_lut, load_obj, material_dt, ray_dt, vertex_dt, xmmatrix_from_colvec
 
 
 class SceneDesc:
@@ -36,6 +36,35 @@ class SceneDesc:
 
     def n_triangles(self):
         return sum(self.models[i]["indices"].size // 3 for i, _ in self.instances)
+
+
+def from_obj_files(paths, transforms=None, name="obj"):
+    """Renderer::LoadAssets / CreateVB over a model list (rdn/Renderer.cpp:362-370,1973-2072): every OBJ becomes one model
+    (one BLAS) with one instance; material blocks and material-id ranges accumulate across models exactly as materialOffset /
+    materialVertexOffset do.  transforms: column-vector 4x4 per model (default identity)."""
+    sc = SceneDesc(); sc.name = name
+    mats = []
+    for k, path in enumerate(paths):
+        off_mat = sum(m.size for m in mats)
+        o = load_obj(path, material_offset=off_mat)
+        off_ids = int(sc.material_ids.size)
+        v = o["vertices"].copy()
+        v["normal_material"][:, 3] = np.float32(off_ids)       # the reference's float smuggling; the ABI takes the uint
+        sc.material_ids = np.concatenate([sc.material_ids, o["material_ids"]])
+        sc.models.append({"vertices": v, "indices": o["indices"], "material_id_offset": off_ids})
+        mats.append(o["materials"])
+        sc.add_instance(k, None if transforms is None else transforms[k])
+    sc.materials = np.concatenate(mats)
+    return sc
+
+
+def reference_scene(asset_dir):
+    """The reference's only scene: garage.obj + monke.obj (rdn/Renderer.cpp:363), instance 1 rotated by 1.57 rad about y every
+    frame (:444-449), default camera (:47-48)."""
+    import os
+    rot = np.eye(4); rot[:3, :3] = _rot_y(np.float32(1.57))        # XMMatrixRotationAxis({0,1,0}, 1.57f), column-vector form
+    return from_obj_files([os.path.join(asset_dir, "garage.obj"), os.path.join(asset_dir, "monke.obj")], [np.eye(4), rot],
+                          name="garage+monke")
 
 
 def default_material():

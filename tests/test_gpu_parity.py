@@ -281,6 +281,37 @@ def test_restir_cuda_path_matches_committed_golden(rtdx):
     ctx.close()
 
 
+def test_reference_asset_scene_matches_committed_golden(rtdx):
+    """The reference's own scene (garage.obj + monke.obj, ingested by this repo's loader into tests/golden/reference_scene.npz)
+    on the engine: E0 render, primary hit ids and 3 ReSTIR frames against the oracle's committed outputs — no oracle call."""
+    import json
+    import os
+    import zlib
+    from util import load_scene_npz
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "reference_scene_golden.json")) as f:
+        g = json.load(f)
+    sc = load_scene_npz(rtdx, os.path.join(here, "reference_scene.npz"))
+    W, H = g["width"], g["height"]
+    ctx, up = _upload(rtdx, sc, W, H, bounces=g["bounces"], flags=rtdx.FLAG_RESTIR)
+    ctx.reset_counters()
+    ctx.render_pass(0, g["e0"]["spp"]); ctx.synchronize()
+    cnt = ctx.counters()
+    assert (cnt["closest_rays"], cnt["shadow_rays"]) == (g["e0"]["closest_rays"], g["e0"]["shadow_rays"])
+    assert int(zlib.crc32(ctx.read_accum().view(np.uint8).tobytes())) == g["e0"]["accum_crc32"]
+    hits = ctx.trace(rtdx.scenes.camera_rays(up["camera"], W, H))
+    assert [int(v) for v in hits["inst"]] == g["primary"]["inst"] and [int(v) for v in hits["prim"]] == g["primary"]["prim"]
+    ctx.reset_accum(); ctx.reset_counters()
+    for f in range(g["restir"]["frames"]):
+        ctx.render_frame(f)
+    ctx.synchronize()
+    cnt = ctx.counters()
+    assert (cnt["closest_rays"], cnt["shadow_rays"]) == (g["restir"]["closest_rays"], g["restir"]["shadow_rays"])
+    assert int(zlib.crc32(ctx.read_accum().view(np.uint8).tobytes())) == g["restir"]["accum_crc32"]
+    assert int(zlib.crc32(np.ascontiguousarray(ctx.read_restir()).view(np.uint8).tobytes())) == g["restir"]["reservoir_crc32"]
+    ctx.close()
+
+
 def test_full_size_properties_c2(rtdx):
     """BASELINE config C2 at full size (1M triangles, 1920x1080, bounces 6): size-independent properties instead of an oracle
     run — determinism (two renders of the same sample are bit-identical), sample counting, ray-count bound 5 + bounces per

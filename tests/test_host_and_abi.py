@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from util import host_inputs
+from util import host_inputs, load_scene_npz
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -196,3 +196,92 @@ def test_two_rank_sample_partition_and_reduce(rtdx, orc, tmp_path):
     # and it equals the 1-GPU image up to fp32 summation order
     one, _ = osc.render(cam, W, H, 0, 4, bounces=2, flags=3)
     assert (total[..., 3] == 4).all() and np.allclose(total, one, rtol=1e-5, atol=1e-6)
+
+
+# ---- OBJ/MTL ingest (src/Util/ObjLoader.h:393-495) ------------------------------------------------------
+OBJ_TEXT = """# synthetic
+mtllib t.mtl
+o A
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+v 0 0 1
+v 2 0 0
+v 2 3 0
+vn 0 0 1
+vn 0 1 0
+f 1//1 2//1 3//1
+usemtl red
+f 1//2 2//2 3//2 4//2
+usemtl glow
+f -3 -2 -1
+usemtl nosuch
+f 1 2 5
+f 1 6 7 4
+"""
+MTL_TEXT = """newmtl red
+Kd 0.8 0.1 0.1
+Ks 0.5 0.5 0.5
+d 0.75
+Pr 0.4
+Pm 1.0
+Ps 0.125
+Pc 0.25
+Ni 1.45
+newmtl glow
+Kd 1 1 1
+Ke 4 5 6
+Tr 0.25
+Pr 1.0
+"""
+
+
+def test_obj_loader_follows_the_reference_loader(rtdx, tmp_path):
+    (tmp_path / "t.obj").write_text(OBJ_TEXT); (tmp_path / "t.mtl").write_text(MTL_TEXT)
+    o = rtdx.load_obj(str(tmp_path / "t.obj"), material_offset=5)
+    m = o["materials"]
+    assert m.size == 3                                              # [default, red, glow]
+    assert tuple(m["Kd"][0]) == (1, 1, 1, 1) and tuple(m["Ks"][0]) == (1, 1, 1) and tuple(m["Pr_Pm_Ps_Pc"][0]) == (1, 0, 0, 0)
+    assert (m["LUT"][0] == 0).all()                                 # the default material never gets a LUT (ObjLoader.h:415-417)
+    assert np.allclose(m["Kd"][1], (0.8, 0.1, 0.1, 0.75)) and np.allclose(m["Pr_Pm_Ps_Pc"][1], (0.4, 1.0, 0.125, 0.25))
+    assert m["Ni"][1] == 1.0                                        # Ni is not taken from the MTL (Material ctor, Vertex.h:14-23)
+    assert np.allclose(m["Ke"][2], (4, 5, 6)) and np.isclose(m["Kd"][2][3], 0.75)      # Tr = 1 - d
+    assert (m["LUT"][1] > 0).all() and (m["LUT"][2] > 0).all()
+    # faces: tri (no usemtl -> default), quad (red) split along the shorter diagonal, tri with negative indices (glow),
+    # tri with an unknown usemtl (-> default), quad 1 6 7 4 whose diagonal 6-4 is shorter than 1-7
+    ids = o["material_ids"].reshape(-1, 3)
+    assert (ids[:, 0] == ids[:, 1]).all() and (ids[:, 1] == ids[:, 2]).all()
+    assert [int(v) for v in ids[:, 0]] == [5, 6, 6, 7, 5, 5, 5]     # offset 5: default = 5, red = 6, glow = 7
+    idx = o["indices"].reshape(-1, 3)
+    assert idx.shape[0] == 7
+    v = o["vertices"]
+    assert v.size == 7                                              # de-duplicated by position only
+    assert tuple(v["normal_material"][0][:3]) == (0, 0, 1)          # first normal seen for position 1 wins (Vertex.h:32-34,48)
+    p = v["position"][idx]
+    assert np.allclose(p[1], [[0, 0, 0], [1, 0, 0], [0, 1, 0]]) and np.allclose(p[2], [[1, 0, 0], [1, 1, 0], [0, 1, 0]])   # unit quad: diag 0-2 == 1-3 -> [0,1,3],[1,2,3]
+    assert np.allclose(p[3], [[0, 0, 1], [2, 0, 0], [2, 3, 0]])     # f -3 -2 -1
+    assert np.allclose(p[5], [[0, 0, 0], [2, 0, 0], [0, 1, 0]]) and np.allclose(p[6], [[2, 0, 0], [2, 3, 0], [0, 1, 0]])
+    assert (v["normal_material"][4][:3] == 0).all()                 # position 5 never had a normal: (0,0,0) (:470-476)
+    with pytest.raises(rtdx.RtxError):
+        rtdx.load_obj(str(tmp_path / "missing.obj"))
+
+
+def test_reference_scene_fixture_is_what_the_loader_produces(rtdx):
+    """tests/golden/reference_scene.npz = this repo's ingest of the reference's garage.obj + monke.obj.  Where the reference tree
+    is mounted (build container) the loader is re-run and compared; everywhere, the known facts of the asset are checked
+    (1254 + 967 triangles, 32 emissive triangles with Ke = 5, bbox (-10,-0.055,-5)..(10,4,5))."""
+    sc = load_scene_npz(rtdx, os.path.join(ROOT, "tests", "golden", "reference_scene.npz"))
+    assert [m["indices"].size // 3 for m in sc.models] == [1254, 967]
+    counts = np.bincount(sc.material_ids) // 3
+    assert [int(c) for c in counts] == [0, 268, 954, 32, 0, 967]    # [default, black_walls, floor, lights, default, Material.001]
+    assert tuple(sc.materials["Ke"][3]) == (5, 5, 5) and rtdx.collect_emissive_triangles(sc).size == 32
+    pos = sc.models[0]["vertices"]["position"]
+    assert np.allclose(pos.min(0), (-10, -0.054948, -5)) and np.allclose(pos.max(0), (10, 4, 5))
+    assert (sc.models[1]["vertices"]["normal_material"][:, :3] == 0).all()      # monke.obj has no normals
+    ref_dir = "/root/reference/Pathtracer/include"
+    if os.path.exists(os.path.join(ref_dir, "garage.obj")):
+        live = rtdx.scenes.reference_scene(ref_dir)
+        for a, b in zip(live.models, sc.models):
+            assert np.array_equal(a["vertices"], b["vertices"]) and np.array_equal(a["indices"], b["indices"])
+        assert np.array_equal(live.material_ids, sc.material_ids) and live.materials.tobytes() == sc.materials.tobytes()

@@ -345,3 +345,30 @@ def test_e0_estimator_sanity(rtdx, orc):
     assert img.max() == 15.0                                        # a pixel looking straight at the emitter (Ke = 15, exact in half)
     assert 0.02 < img[24:, 8:40].mean() < 2.0                        # floor region is lit
     assert ctr["closest_rays"] + ctr["shadow_rays"] <= ctr["paths"] * (5 + 2)
+
+
+def test_oracle_on_the_reference_asset_scene_matches_golden(rtdx, orc):
+    """The oracle on the reference's own scene (garage.obj + monke.obj through this repo's ingest, tests/golden/reference_scene.npz):
+    E0 render, primary hit ids and 3 ReSTIR frames against tests/golden/reference_scene_golden.json."""
+    import zlib
+    from util import load_scene_npz
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "reference_scene_golden.json")) as f:
+        g = json.load(f)
+    sc = load_scene_npz(rtdx, os.path.join(here, "reference_scene.npz"))
+    W, H = g["width"], g["height"]
+    props, descs, lights, cam = host_inputs(rtdx, sc, W, H)
+    assert lights.size == g["n_lights"] and sc.n_triangles() == g["triangles"]
+    osc = orc.OracleScene(sc, props, lights)
+    acc, ctr = osc.render(cam, W, H, 0, g["e0"]["spp"], bounces=g["bounces"])
+    assert (ctr["closest_rays"], ctr["shadow_rays"]) == (g["e0"]["closest_rays"], g["e0"]["shadow_rays"])
+    assert int(zlib.crc32(acc.view(np.uint8).tobytes())) == g["e0"]["accum_crc32"]
+    hits = osc.trace(rtdx.scenes.camera_rays(cam, W, H), mode=1)
+    assert [int(v) for v in hits["inst"]] == g["primary"]["inst"] and [int(v) for v in hits["prim"]] == g["primary"]["prim"]
+    fr = osc.new_frames(W, H); acc2 = np.zeros((H, W, 4), dtype=np.float32); tot = [0, 0]
+    for f in range(g["restir"]["frames"]):
+        c = osc.render_frame(cam, W, H, f, fr, acc2, bounces=g["bounces"])
+        tot[0] += c["closest_rays"]; tot[1] += c["shadow_rays"]
+    assert tot == [g["restir"]["closest_rays"], g["restir"]["shadow_rays"]]
+    assert int(zlib.crc32(acc2.view(np.uint8).tobytes())) == g["restir"]["accum_crc32"]
+    assert int(zlib.crc32(np.ascontiguousarray(osc.dump_frames(fr, W, H)).view(np.uint8).tobytes())) == g["restir"]["reservoir_crc32"]

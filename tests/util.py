@@ -36,3 +36,25 @@ def compare_hits(gpu, ref):
         "v": int((bits(gpu["v"][hit]) != bits(ref["v"][hit])).sum()),
     }
     return r
+
+
+def save_scene_npz(path, sc):
+    """A scenes.SceneDesc as plain arrays (fixture form of an ingested OBJ scene)."""
+    d = {"n_models": np.int32(len(sc.models)), "material_ids": sc.material_ids, "materials": sc.materials,
+         "inst_model": np.array([i[0] for i in sc.instances], dtype=np.int32), "inst_xm": np.stack([i[1] for i in sc.instances]),
+         "camera": np.array([sc.eye, sc.center, sc.up], dtype=np.float64)}
+    for k, m in enumerate(sc.models):
+        d["v%d" % k] = m["vertices"]; d["i%d" % k] = m["indices"]; d["o%d" % k] = np.int64(m["material_id_offset"])
+    np.savez_compressed(path, **d)
+
+
+def load_scene_npz(rtdx, path):
+    z = np.load(path)
+    sc = rtdx.scenes.SceneDesc(); sc.name = "npz"
+    for k in range(int(z["n_models"])):
+        sc.models.append({"vertices": z["v%d" % k], "indices": z["i%d" % k], "material_id_offset": int(z["o%d" % k])})
+    sc.material_ids = z["material_ids"]; sc.materials = z["materials"]
+    sc.instances = [(int(m), np.ascontiguousarray(x, dtype=np.float32)) for m, x in zip(z["inst_model"], z["inst_xm"])]
+    cam = z["camera"]
+    sc.eye, sc.center, sc.up = tuple(cam[0]), tuple(cam[1]), tuple(cam[2])
+    return sc
