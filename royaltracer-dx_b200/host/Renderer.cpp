@@ -1,5 +1,6 @@
 // Renderer.cpp — see Renderer.h.  Host-side preparation of the hot path's inputs, written against the C ABI.
 #include "Renderer.h"
+#include "ObjLoader.h"
 
 #include <math.h>
 #include <string.h>
@@ -271,6 +272,13 @@ uint32_t Renderer::CreateVB(const std::vector<rtx_vertex>& vertices, const std::
     m_models.push_back(std::move(m));
     return (uint32_t)m_models.size() - 1;
 }
+// CreateVB(std::string name), rdn/Renderer.cpp:1973-2072: loadObjFile appends this model's material block to the global list
+uint32_t Renderer::CreateVB(const std::string& obj_path) {
+    ObjModel o = loadObjFile(obj_path, (uint32_t)m_materials.size());
+    if (!o.error.empty()) throw std::logic_error("CreateVB: " + o.error);
+    m_materials.insert(m_materials.end(), o.materials.begin(), o.materials.end());
+    return CreateVB(o.vertices, o.indices, o.material_ids);
+}
 uint32_t Renderer::AddInstance(uint32_t model, const XMMATRIX& o2w) { m_instances.push_back({model, o2w}); return (uint32_t)m_instances.size() - 1; }
 void Renderer::SetInstanceTransform(uint32_t i, const XMMATRIX& o2w) { m_instances.at(i).second = o2w; }
 void Renderer::SetCamera(const float eye[3], const float center[3], const float up[3]) {
@@ -331,6 +339,11 @@ void Renderer::OnUpdate() {
 void Renderer::OnRender(uint32_t first_sample, uint32_t n_samples) {
     Check(rtx_render_pass(m_ctx, first_sample, n_samples), "rtx_render_pass");
     Check(rtx_synchronize(m_ctx), "rtx_synchronize");          // WaitForPreviousFrame, Renderer.cpp:717-735
+}
+// PopulateCommandList's three DispatchRays (RayGen, RayGen2, RayGen3), rdn/Renderer.cpp:611-673; needs flags |= RTX_FLAG_RESTIR
+void Renderer::OnRenderFrame(uint32_t frame_index) {
+    Check(rtx_render_frame(m_ctx, frame_index), "rtx_render_frame");
+    Check(rtx_synchronize(m_ctx), "rtx_synchronize");
 }
 void Renderer::ReadAccumulation(std::vector<float>& out) { out.resize((size_t)m_width * m_height * 4); Check(rtx_read_accum(m_ctx, out.data()), "rtx_read_accum"); }
 void Renderer::ReadOutput(std::vector<uint8_t>& out) { out.resize((size_t)m_width * m_height * 4); Check(rtx_read_output(m_ctx, out.data()), "rtx_read_output"); }

@@ -56,6 +56,9 @@ public:
     void OnInit();                       // uploads, BLAS/TLAS builds, light list, buffers
     void OnUpdate();                     // camera CB + instance properties (+ TLAS refit)
     void OnRender(uint32_t first_sample, uint32_t n_samples);
+    void OnRenderFrame(uint32_t frame_index);   // the reference's full frame incl. ReSTIR reuse (flags |= RTX_FLAG_RESTIR)
+    // CreateVB(std::string) of the reference: OBJ/MTL ingest through ObjLoader.h, materials appended to the global list
+    uint32_t CreateVB(const std::string& obj_path);
     void ReadAccumulation(std::vector<float>& rgba32f);
     void ReadOutput(std::vector<uint8_t>& rgba8);
 
