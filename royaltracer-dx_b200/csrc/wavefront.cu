@@ -267,10 +267,12 @@ __device__ __forceinline__ f3 SampleLightNEE_GI(const SceneData& S, float& pdf_l
 template <bool ITER0>       // two instantiations: the hit-consuming halves differ, and the kernel is I-cache bound
 __global__ void __launch_bounds__(RTX_GI_BLOCK, RTX_GI_MINB)
 k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
-          RayQueue q_shadow, RayQueue qout, uint32_t iter, unsigned long long* ray_counters) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+          RayQueue q_shadow, RayQueue qout, uint32_t iter, unsigned long long* ray_counters, const uint32_t* __restrict__ perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = *qin.count;
-    if (j == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
+    if (i == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
+    // RTX_FLAG_SORT_MATERIAL: queue entries are visited in material-binned order (perm), otherwise in queue order
+    const uint32_t j = (perm != nullptr && i < n) ? perm[i] : i;
     bool emit = false, emit_sh = false; uint32_t pid = 0;
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
@@ -492,6 +494,52 @@ __global__ void k_debug_pixel(StateView st, uint32_t p, const float* vis_di, con
     out[49] = st.at(SP_RESULT, p).w; out[50] = vis_di[p]; out[51] = vis_gi[p]; out[52] = b1.w;
 }
 
+// ---- RTX_FLAG_SORT_MATERIAL: bin the entries of a traced queue by the material of their hit (counting sort, 16 bins) so
+// that the warps of the next shading kernel see one material class each.  Measured on C2: every
+// material runs the same combined-lobe code, so the coherence gained is small and does not pay for the binning passes.
+#define WF_NBIN 16
+__device__ __forceinline__ uint32_t hit_material_bin(const SceneData& S, uint32_t inst, uint32_t prim) {
+    if (inst == 0xFFFFFFFFu) return WF_NBIN - 1;
+    const ModelRef M = S.models[S.inst_model[inst]];
+    const uint32_t mslot = 3u * prim + M.mat_offset;
+    const uint32_t mID = mslot < S.n_material_ids ? __ldg(&S.material_ids[mslot]) : 0u;
+    return mID < WF_NBIN - 2 ? mID : WF_NBIN - 2;
+}
+__global__ void __launch_bounds__(WF_BLOCK)
+k_bin_count(SceneData S, const uint32_t* __restrict__ n_ptr, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
+            unsigned char* __restrict__ keys, uint32_t* __restrict__ bins) {
+    __shared__ uint32_t h[WF_NBIN];
+    if (threadIdx.x < WF_NBIN) h[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < *n_ptr) {
+        const uint32_t k = hit_material_bin(S, hit_inst[j], __float_as_uint(hit_a[j].w));
+        keys[j] = (unsigned char)k;
+        atomicAdd(&h[k], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < WF_NBIN && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void k_bin_scan(uint32_t* bins) {       // bins[0..15] counts -> bins[16..31] running cursors (exclusive prefix)
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < WF_NBIN; k++) { bins[WF_NBIN + k] = run; run += bins[k]; bins[k] = 0u; }
+    }
+}
+__global__ void __launch_bounds__(WF_BLOCK)
+k_bin_scatter(const uint32_t* __restrict__ n_ptr, const unsigned char* __restrict__ keys, uint32_t* __restrict__ bins, uint32_t* __restrict__ perm) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = j < *n_ptr;
+    const uint32_t k = live ? keys[j] : 0xffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, k);          // one atomic per distinct bin per warp
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (live && (int)lane == leader) base = atomicAdd(&bins[WF_NBIN + k], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) perm[base + __popc(peers & ((1u << lane) - 1u))] = j;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static cudaError_t alloc_queue(RayQueue* q, uint32_t n) {
     CKE(cudaMalloc((void**)&q->o_tmin, (size_t)n * 16));
@@ -527,13 +575,16 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
     CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
     CKE(cudaMalloc((void**)&B->debug, 64 * 4));
+    CKE(cudaMalloc((void**)&B->perm, (size_t)n * 4));
+    CKE(cudaMalloc((void**)&B->bin_keys, (size_t)n));
+    CKE(cudaMalloc((void**)&B->bins, 2 * WF_NBIN * 4));
     return cudaSuccess;
 }
 
 void wave_free(WaveBuffers* B) {
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
-    void* ptrs[] = {B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug};
+    void* ptrs[] = {B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
     for (void* p : ptrs) if (p) cudaFree(p);
     *B = WaveBuffers();
 }
@@ -595,10 +646,20 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     RayQueue qin = qa;
     for (uint32_t iter = 0; iter <= S.bounces; iter++) {
         RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
-        CKE(mark(SK_GI_STEP));
         const unsigned ggrid = (n + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
-        if (iter == 0u) k_gi_step<true><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
-        else k_gi_step<false><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters);
+        const uint32_t* perm = nullptr;
+        if (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) {
+            CKE(mark(SK_SORT));
+            CKE(cudaMemsetAsync(B.bins, 0, 2 * WF_NBIN * 4, stream));
+            k_bin_count<<<grid, WF_BLOCK, 0, stream>>>(S, qin.count, B.hit_a, B.hit_inst, B.bin_keys, B.bins);
+            k_bin_scan<<<1, 32, 0, stream>>>(B.bins);
+            k_bin_scatter<<<grid, WF_BLOCK, 0, stream>>>(qin.count, B.bin_keys, B.bins, B.perm);
+            L += 2;
+            perm = B.perm;
+        }
+        CKE(mark(SK_GI_STEP));
+        if (iter == 0u) k_gi_step<true><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters, perm);
+        else k_gi_step<false><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters, perm);
         if (iter < S.bounces) {
             CKE(closest(qout));
             qin = qout; cur ^= 1;

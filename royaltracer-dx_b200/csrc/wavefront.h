@@ -46,6 +46,7 @@ struct WaveBuffers {
     uint8_t* output = nullptr;         // gOutput slice 0
     rtx_camera_params* cam = nullptr;  // b0 (device copy)
     float* debug = nullptr;            // 64 floats
+    uint32_t* perm = nullptr; unsigned char* bin_keys = nullptr; uint32_t* bins = nullptr;   // RTX_FLAG_SORT_MATERIAL scratch
 };
 
 cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp);

@@ -214,6 +214,16 @@ def test_restir_moving_camera_and_instances_bit_exact(rtdx, orc):
     _restir_frames(rtdx, orc, sc, 80, 64, 3, 0, [(None, moved(t)) for t in range(3)])
 
 
+def test_material_sorted_queues_do_not_change_the_image(rtdx, orc):
+    """RTX_FLAG_SORT_MATERIAL bins every shading queue by hit material before k_gi_step; each path draws its own random numbers,
+    so the image, the reservoirs and the ray counts are bit-identical to the unsorted run (and to the oracle)."""
+    sc = rtdx.scenes.mesh_room(n=24)
+    ctx, gpu, cnt, ref, octr = _render_both(rtdx, orc, sc, 96, 64, 2, 6, rtdx.FLAG_SORT_MATERIAL)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (cnt, octr)
+    assert (bits(gpu) != bits(ref)).sum() == 0
+    ctx.close()
+
+
 def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
     (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""

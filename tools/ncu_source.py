@@ -28,6 +28,9 @@ def line_map(cubin, mangled):
     return m
 
 
+WHICH = 0
+
+
 def main(rep, kre, cubin, mangled, top=40, sass=False):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     blocks, cur = [], None
@@ -42,7 +45,7 @@ def main(rep, kre, cubin, mangled, top=40, sass=False):
                 cur["rows"].append(row)
     lm = line_map(cubin, mangled)
     blocks = [x for x in blocks if re.search(kre, x["name"])]
-    b = blocks[0]
+    b = blocks[WHICH]
     h = b["hdr"]
     col = {n: i for i, n in enumerate(h)}
 
@@ -91,5 +94,8 @@ def main(rep, kre, cubin, mangled, top=40, sass=False):
 
 
 if __name__ == "__main__":
-    a = [x for x in sys.argv[1:] if x != "--sass"]
+    for x in sys.argv[1:]:
+        if x.startswith("--which="):
+            WHICH = int(x.split("=")[1])
+    a = [x for x in sys.argv[1:] if x != "--sass" and not x.startswith("--which=")]
     main(a[0], a[1], a[2], a[3], int(a[4]) if len(a) > 4 else 40, "--sass" in sys.argv)
