@@ -253,9 +253,19 @@ def main():
     value = rays_all / (ms * 1e-3) / 1e6
 
     # ---- end to end through the C ABI with host buffers (TLAS refit + camera upload + render + RGBA8 read-back per step)
-    props, descs, cam = up["props"], up["descs"], up["camera"]
+    _pins = []
+
+    def pinned_copy(a):                     # the step's inputs live in pinned host memory
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        _pins.append(t)
+        n = t.numpy()
+        n[:] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        return n.view(a.dtype).reshape(a.shape)
+    props, descs, cam = pinned_copy(up["props"]), pinned_copy(up["descs"]), pinned_copy(up["camera"])
     h2d = int(props.nbytes + descs.nbytes + cam.nbytes); d2h = W * H * 4
     ctx.reset_accum()
+
+    out_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()     # the frame's read-back target (pinned host memory)
 
     def step_e2e(k):
         ctx.set_instances(descs, props)
@@ -264,7 +274,7 @@ def main():
         if world > 1:
             total.copy_(accum)
             dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)
-        return ctx.read_output()
+        return ctx.read_output(out_pinned)
 
     for k in range(min(args.warmup, 2)):
         step_e2e(k)

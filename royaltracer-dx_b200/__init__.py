@@ -318,8 +318,11 @@ class Context:
         self._check(self.lib.rtx_read_accum(self.handle, _ptr(out)))
         return out
 
-    def read_output(self):
-        out = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+    def read_output(self, out=None):
+        """gOutput slice 0 as RGBA8; `out` may be a caller-owned (e.g. pinned) uint8 buffer of height*width*4 bytes."""
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.size == self.height * self.width * 4 and out.flags["C_CONTIGUOUS"]
         self._check(self.lib.rtx_read_output(self.handle, _ptr(out)))
         return out
 
