@@ -158,6 +158,7 @@ static rtx_status ensure_tables(rtx_ctx* c) {
         const ModelRec& m = c->models[i];
         br[i].nodes = m.bvh.nodes; br[i].tris = m.bvh.prims;
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = m.bvh.lo[k]; bb[i].hi[k] = m.bvh.hi[k]; }
+        bb[i].verts = m.d_verts; bb[i].n_verts = m.n_verts;
         mr[i].verts = m.d_verts; mr[i].idx = m.d_idx; mr[i].mat_offset = m.mat_offset; mr[i].n_tris = m.n_tris;
     }
     rtx_status st;

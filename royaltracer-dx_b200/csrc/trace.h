@@ -29,7 +29,7 @@ cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
 void free_bvh(Bvh8* b);
 
 // Fills instance records + world boxes from descs/props (device arrays) and per-model BLAS bounds.
-struct BlasBounds { float lo[3]; float hi[3]; };
+struct BlasBounds { float lo[3]; float hi[3]; const uint8_t* verts; uint32_t n_verts; };   // verts: the model's 28-B vertex buffer
 cudaError_t launch_instance_records(const rtx_instance_desc* d_descs, const rtx_instance_props* d_props, const BlasBounds* d_bounds,
                                     uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, cudaStream_t stream);
 
