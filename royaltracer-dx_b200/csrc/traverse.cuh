@@ -80,7 +80,10 @@ __device__ __forceinline__ void setup_box(RaySpace& r, float ox, float oy, float
     r.ix = rcp_approx(fabsf(dx) > tiny ? dx : copysignf(tiny, dx));
     r.iy = rcp_approx(fabsf(dy) > tiny ? dy : copysignf(tiny, dy));
     r.iz = rcp_approx(fabsf(dz) > tiny ? dz : copysignf(tiny, dz));
-    const uint32_t oct = (dx >= 0.0f ? 1u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 4u : 0u);
+    // octant from the SIGN BITS, consistent with copysignf above: a component that is exactly -0 gets a huge negative reciprocal and
+    // must pick the far/near planes of a negative direction (with `d >= 0` it was paired with the positive ones and the slab test
+    // culled every box — tests/test_gpu_parity.py::test_trace_edge_cases)
+    const uint32_t oct = ((__float_as_uint(dx) >> 31) ^ 1u) | (((__float_as_uint(dy) >> 31) ^ 1u) << 1) | (((__float_as_uint(dz) >> 31) ^ 1u) << 2);
     r.octinv4 = oct * 0x01010101u;
 }
 // triangle-test part (same rule as the oracle: first maximum in x,y,z order; swap kx,ky if d[kz] < 0;

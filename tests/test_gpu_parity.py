@@ -55,6 +55,15 @@ def test_trace_edge_cases(rtdx, orc):
     assert (ctx.trace(rays)["inst"] == rtdx.MISS).all()
     rays["tmax"] = 0.5                                                      # TMax cuts some of the hits
     _assert_hits_equal(ctx.trace(rays), osc.trace(rays, mode=0))
+    # negative zeros in the direction: the slab test must treat -0 like a (tiny) negative component, never cull a hit
+    rays["origin"] = (0.1, 1.0, 0.05)
+    rays["tmin"] = 1e-4
+    rays["tmax"] = 1e4
+    rays["direction"] = [(1, -0.0, -0.0), (-1, -0.0, 0.0), (-0.0, 1, -0.0), (-0.0, -1, -0.0), (-0.0, -0.0, 1), (0.0, -0.0, -1)]
+    ref = osc.trace(rays, mode=0)
+    assert (ref["inst"] != rtdx.MISS).sum() == 5                            # +z leaves through the open front of the box
+    _assert_hits_equal(ctx.trace(rays), ref)
+    assert np.array_equal(ctx.trace(rays, any_hit=True)["inst"] != rtdx.MISS, ref["inst"] != rtdx.MISS)
     # rays starting exactly on a surface with TMin = s_bias (the reference's bounce convention)
     rays["origin"] = (0.3, 0.0, 0.2)
     rays["tmin"] = 2e-5
