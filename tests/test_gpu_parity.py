@@ -72,6 +72,54 @@ def test_trace_edge_cases(rtdx, orc):
     ctx.close()
 
 
+def test_trace_fuzz_degenerate_geometry_and_rays(rtdx, orc):
+    """Hostile inputs against the brute-force definition (oracle mode 0): duplicated and zero-area triangles, coincident instances
+    (equal t: the tie goes to the lowest instance, then primitive id), mirrored / non-uniformly scaled / sheared instance
+    transforms, and rays with zero, denormal, huge, infinite and NaN components, TMin >= TMax, zero-length directions."""
+    rng = np.random.RandomState(5)
+    sc = rtdx.scenes.SceneDesc(); sc.name = "fuzz"
+    sc.materials = np.concatenate([rtdx.scenes.default_material(), rtdx.scenes.make_material((.5, .5, .5))])
+    nv = 60
+    pos = rng.uniform(-1, 1, size=(nv, 3)).astype(np.float32)
+    pos[:10] = np.round(pos[:10] * 4) / 4                                   # lattice points: exact edge / vertex hits happen
+    tri = rng.randint(0, nv, size=(80, 3))
+    tri[5] = tri[4]                                                         # duplicate triangle (tie on t)
+    tri[6] = (tri[6][0], tri[6][0], tri[6][1])                              # zero-area triangles
+    tri[7] = (3, 3, 3)
+    m0 = sc.add_model(pos, np.zeros_like(pos), tri, np.full(80, 1))
+    quad = np.array([[-2, -2, 0], [2, -2, 0], [2, 2, 0], [-2, 2, 0]], dtype=np.float32)
+    m1 = sc.add_model(quad, np.zeros_like(quad), np.array([[0, 1, 2], [0, 2, 3]]), np.full(2, 1))
+    eye = np.eye(4)
+    mirror = np.diag([-1.0, 1.0, 1.0, 1.0])
+    squash = np.diag([3.0, 0.25, 1.5, 1.0]); squash[:3, 3] = (0.5, -0.25, 0.125)
+    shear = np.eye(4); shear[0, 1] = 0.75; shear[2, 0] = -0.5; shear[:3, 3] = (-1, 0.5, 2)
+    for m in (eye, eye, mirror, squash, shear):                             # instances 0 and 1 coincide exactly
+        sc.add_instance(m0, m)
+    back = np.eye(4); back[2, 3] = -1.5
+    sc.add_instance(m1, back); sc.add_instance(m1, back)                    # two coincident quads
+    ctx, up = _upload(rtdx, sc, 16, 16)
+    osc = _oracle(orc, sc, up)
+    n = 20000
+    rays = random_rays(rtdx, rng, n, (-3, -3, -3), (3, 3, 3))
+    rays["origin"][:2000] = pos[rng.randint(0, nv, 2000)] + np.float32(2.0) * rays["direction"][:2000] * -1     # aimed at vertices
+    d = rays["direction"]
+    d[2000:2400, 0] = 0.0; d[2400:2800, 1] = -0.0; d[2800:3000, :2] = 0.0                                          # axis-parallel, +-0
+    d[3000:3100] *= np.float32(1e-30); d[3100:3200] *= np.float32(1e30); d[3200:3300] *= np.float32(1e-42)        # tiny / huge / denormal lengths
+    d[3300:3320] = 0.0                                                                                             # zero direction
+    d[3320:3340, 0] = np.nan; d[3340:3360, 1] = np.inf; rays["origin"][3360:3380, 2] = np.nan; rays["origin"][3380:3400, 0] = -np.inf
+    rays["tmin"][3400:3500] = 1.0; rays["tmax"][3400:3500] = 1.0                                                   # empty interval
+    rays["tmin"][3500:3600] = 2.0; rays["tmax"][3500:3600] = 1.0                                                   # inverted interval
+    rays["tmin"][3600:3700] = 0.0; rays["tmax"][3600:3700] = np.inf
+    rays["origin"][3700:3800] *= np.float32(1e6)                                                                   # far away
+    ref = osc.trace(rays, mode=0)
+    g = ctx.trace(rays)
+    _assert_hits_equal(g, ref)
+    assert (ref["inst"] != rtdx.MISS).sum() > 3000
+    ah = ctx.trace(rays, any_hit=True)
+    assert np.array_equal(ah["inst"] != rtdx.MISS, ref["inst"] != rtdx.MISS)
+    ctx.close()
+
+
 @pytest.mark.parametrize("n_side", [8, 40])
 def test_trace_mesh_room(rtdx, orc, n_side):
     sc = rtdx.scenes.mesh_room(n=n_side)
@@ -240,6 +288,42 @@ def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     r = ctx.selftest_dmath()
     assert r == {"rsqrt": 0, "div3": 0}, r
     ctx.close()
+
+
+def test_render_fuzz_hostile_materials_and_lights(rtdx, orc):
+    """Shading under hostile inputs, bit-exact against the oracle (E0 and 2 ReSTIR frames): mirror-smooth (Pr = 0, Pr < 0.04),
+    over-unity and zero Ks/Kd, the loader's default material (LUT = 0 => Ess = 0 => Inf => 0, ObjLoader.h:415), huge and tiny
+    emitters, a zero-area light triangle (normalize(0) = NaN in SampleLightNEE), missing and partly-zero vertex normals."""
+    rng = np.random.RandomState(11)
+    sc = rtdx.scenes.SceneDesc(); sc.name = "fuzz_mat"
+    mk = rtdx.scenes.make_material
+    mats = [rtdx.scenes.default_material(), mk((.7, .7, .7)), mk((.2, .4, .9), ks=(.9, .9, .9), roughness=0.0, metallic=1.0),
+            mk((.9, .1, .1), ks=(.04, .04, .04), roughness=0.03), mk((0, 0, 0), ks=(2.5, 1.5, 0.0), roughness=0.35, metallic=0.5),
+            mk((1, 1, 1), ks=(0, 0, 0), roughness=1.0), mk((0, 0, 0), ke=(1e4, 2e4, 5e3)), mk((0, 0, 0), ke=(3e-4, 0, 0)),
+            mk((.5, .5, .5), ke=(4, 4, 4), roughness=0.5)]
+    sc.materials = rtdx.scenes._fill_luts(np.concatenate(mats))
+    # a closed room of 6 quads (materials 1..5 and the default), two blobs, three emitters (one with a zero-area triangle)
+    pos, nrm, idx, tm = rtdx.scenes._quads_to_mesh(rtdx.scenes._box_quads((-2, 0, -2), (2, 3, 2)), [1, 2, 3, 4, 5, 0], flip=True)
+    room = sc.add_model(pos, nrm, idx, tm)
+    p, vn, i3 = rtdx.scenes._cube_sphere(4, 0.6, 9, 0.15)
+    vn[::3] = 0.0                                                           # every third vertex has no normal
+    vn[1::7, 1] = 0.0                                                       # and some have one zero component (Hit_v7.hlsl:36-44: treated as missing)
+    blob = sc.add_model(p, vn, i3, rng.randint(1, 6, size=i3.shape[0]))
+    lq = np.array([[-.5, 2.95, -.5], [.5, 2.95, -.5], [.5, 2.95, .5], [-.5, 2.95, .5], [0, 1.5, 0], [0, 1.5, 0]], dtype=np.float32)
+    light = sc.add_model(lq, np.zeros_like(lq), np.array([[0, 1, 2], [0, 2, 3], [4, 4, 5], [0, 3, 1]]), np.array([6, 8, 8, 7]))
+    sc.add_instance(room); sc.add_instance(light)
+    a = np.eye(4); a[:3, 3] = (-0.8, 0.8, 0.3)
+    b = np.diag([1.5, 0.6, 1.0, 1.0]); b[:3, 3] = (0.9, 1.2, -0.4)
+    sc.add_instance(blob, a); sc.add_instance(blob, b)
+    sc.eye, sc.center, sc.up = (0.0, 1.5, 1.9), (0.0, 1.3, 0.0), (0.0, 1.0, 0.0)
+    W, H = 72, 56
+    ctx, gpu, cnt, ref, octr = _render_both(rtdx, orc, sc, W, H, 3, 4, rtdx.FLAG_JITTER)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (cnt, octr)
+    mism = bits(gpu) != bits(ref)
+    assert mism.sum() == 0, "radiance mismatches: %d of %d floats" % (mism.sum(), mism.size)
+    assert (gpu[..., 3] < 3).any() or np.isfinite(gpu).all()               # non-finite samples are dropped by F20, never stored
+    ctx.close()
+    _restir_frames(rtdx, orc, sc, W, H, 3, 0, [(None, None)] * 2)
 
 
 def test_accumulation_reset_on_camera_change(rtdx):
