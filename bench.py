@@ -68,46 +68,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started before the
+    warm-up (nvidia-smi takes a while to come up, longer with 8 GPUs); mark_begin()/mark_end() bracket the timed region and only
+    the samples whose timestamps fall inside it are reported (all samples under load if none did)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             text, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             return out
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in text.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        used, scope = (inside, "timed region") if inside else (rows, "whole run (no sample fell inside the timed region)")
+        reasons = set()
+        for r in used:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if used:
+            out = {"sm_mhz": float(np.median([r[1] for r in used])), "sm_max_mhz": float(max(r[2] for r in used)), "reasons": sorted(reasons),
+                   "samples": len(used), "scope": scope}
         return out
 
 
@@ -182,6 +198,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    clocks = ClockSampler(local); clocks.start()          # long before the timed region: nvidia-smi needs time to come up
     rtdx, sc = build_scene(args)
     W, H = args.width, args.height
     stream = torch.cuda.Stream()            # a real (non-default) stream: the engine, the events and NCCL all use it
@@ -222,13 +239,14 @@ def main():
     for k in range(args.warmup):
         step_resident(k)
     barrier(); ctx.reset_counters()
-    clocks = ClockSampler(local); clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
     e0.record()
     for k in range(args.steps):
         step_resident(args.warmup + k)
     e1.record()
     barrier()
+    clocks.mark_end()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     cnt = ctx.counters()
