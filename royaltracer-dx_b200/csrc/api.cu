@@ -236,6 +236,7 @@ extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
 static SceneAS make_as(rtx_ctx* c) {
     SceneAS a;
     a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
+    a.one_bits = 0x3F800000u;
     return a;
 }
 

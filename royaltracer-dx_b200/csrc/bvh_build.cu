@@ -345,10 +345,10 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
     const uint32_t task_base = n_inner ? atomicAdd(&A.ctr->tasks_out, (unsigned)n_inner) : 0u;
     const int ex = exp_for_extent(phi.x - plo.x), ey = exp_for_extent(phi.y - plo.y), ez = exp_for_extent(phi.z - plo.z);
     const float sx = __uint_as_float((unsigned)ex << 23), sy = __uint_as_float((unsigned)ey << 23), sz = __uint_as_float((unsigned)ez << 23);
-    unsigned char meta[8], qlo[3][8], qhi[3][8];
+    unsigned char qlo[3][8], qhi[3][8];
+    unsigned W = 0;                          // unary primitive count of leaf child s at bits 3s..3s+2
     int inner_rank = 0, prim_off = 0;
     for (int s = 0; s < 8; s++) {
-        meta[s] = 0;
         for (int a = 0; a < 3; a++) { qlo[a][s] = 0; qhi[a][s] = 0; }
         int c = slot_child[s];
         if (c < 0) continue;
@@ -364,13 +364,12 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
             qlo[a][s] = (unsigned char)ql; qhi[a][s] = (unsigned char)qh;
         }
         if (imask & (1u << s)) {
-            meta[s] = (unsigned char)((1u << 5) | (24u + (unsigned)s));
             tasks_out[task_base + inner_rank] = make_uint2((unsigned)id, child_base + inner_rank);
             inner_rank++;
         } else {
             int pr[MAX_LEAF];
             const int pc = collect_prims(H, id, pr);
-            meta[s] = (unsigned char)((((1u << pc) - 1u) << 5) | (unsigned)prim_off);
+            W |= ((1u << pc) - 1u) << (3 * s);
             for (int k = 0; k < pc; k++)
                 src.write(A.out_prims + (size_t)(prim_base + prim_off + k) * PRIM_F4, A.vals[pr[k]]);
             prim_off += pc;
@@ -380,7 +379,7 @@ __device__ void emit_node(const CollapseArgs& A, const Source& src, const int* c
     uint4* o = A.out_nodes + (size_t)out_idx * 5;
     o[0] = make_uint4(__float_as_uint(plo.x), __float_as_uint(plo.y), __float_as_uint(plo.z),
                       (unsigned)ex | ((unsigned)ey << 8) | ((unsigned)ez << 16) | (imask << 24));
-    o[1] = make_uint4(child_base, prim_base, pack4(meta), pack4(meta + 4));
+    o[1] = make_uint4(child_base, prim_base, W | (imask << 24), 0u);
     o[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
     o[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     o[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
@@ -430,10 +429,10 @@ __global__ void k_single_node(Source src, const float4* __restrict__ plo, const 
         h.x = fmaxf(h.x, phi[i].x + pad); h.y = fmaxf(h.y, phi[i].y + pad); h.z = fmaxf(h.z, phi[i].z + pad);
     }
     const int ex = exp_for_extent(h.x - l.x), ey = exp_for_extent(h.y - l.y), ez = exp_for_extent(h.z - l.z);
-    unsigned meta0 = (((1u << n) - 1u) << 5) | 0u;
+    const unsigned W0 = (1u << n) - 1u;
     for (int i = 0; i < n; i++) src.write(out_prims + (size_t)i * PRIM_F4, (uint32_t)i);
     out_nodes[0] = make_uint4(__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), (unsigned)ex | ((unsigned)ey << 8) | ((unsigned)ez << 16));
-    out_nodes[1] = make_uint4(0u, 0u, meta0, 0u);
+    out_nodes[1] = make_uint4(0u, 0u, W0, 0u);
     out_nodes[2] = make_uint4(0u, 0u, 0u, 0u);               // qlo_x, qlo_y = 0
     out_nodes[3] = make_uint4(0u, 0u, 0xffu, 0u);            // qlo_z = 0, qhi_x[0] = 255
     out_nodes[4] = make_uint4(0xffu, 0u, 0xffu, 0u);         // qhi_y[0] = qhi_z[0] = 255

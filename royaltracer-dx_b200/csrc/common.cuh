@@ -31,12 +31,13 @@ void set_error(const std::string& s);
 // ---- acceleration structure (DESIGN.md §"Data layout in HBM") ------------------------------------
 // 80-B compressed 8-wide node, stored as 5 x uint4:
 //   n0 = (px, py, pz, ex | ey<<8 | ez<<16 | imask<<24)
-//   n1 = (child_base, prim_base, meta[0..3], meta[4..7])
+//   n1 = (child_base, prim_base, WI = imask << 24 | W, 0)
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
 //   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
 //   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
-// meta: 0 = empty; inner = 0b001_sssss with sssss = 24 + slot; leaf = unary(count 1..3) << 5 | offset in the
-// node's primitive range (< 24).
+// W: leaf child in slot s holds c (1..3) primitives <=> bits 3s .. 3s+c-1 set; the node's primitives are stored densely from prim_base in
+// bit order, so the primitive behind bit b is prim_base + popc(W & ((1 << b) - 1)).  imask bit s <=> slot s is an inner child; the inner
+// children are stored densely from child_base in slot order.  An empty slot has neither.
 // 48-B triangle = 3 x float4: (v0.xyz, bits(prim)), (v1.xyz, 0), (v2.xyz, 0).
 // 64-B instance record = 4 x float4: rows 0..2 of world->object (from objectToWorldInverse), (blas, instance, 0, 0).
 struct BlasRef {
@@ -49,6 +50,9 @@ struct SceneAS {
     const float4* inst_recs;
     const BlasRef* blas;
     uint32_t n_instances;
+    uint32_t one_bits;    // 0x3F800000, passed as a run-time value: keeps it in a register so that the byte->float PRMT of the node test takes its
+                          // selector as an immediate (with the constant folded in, ptxas re-materialised a selector register per PRMT: 43 extra
+                          // IMAD.U32 per node test)
 };
 
 // Ray queue entry layout (SoA): o_tmin[j] = (o.xyz, tmin), d_tmax[j] = (d.xyz, tmax).

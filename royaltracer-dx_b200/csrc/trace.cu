@@ -13,6 +13,9 @@
 namespace rtx {
 
 #define TRACE_BLOCK 128
+#ifndef RTX_COOP_TRI
+#define RTX_COOP_TRI 0         // warp-cooperative triangle testing (traverse.cuh); 0 = per-lane leaf loop
+#endif
 #ifndef RTX_TRACE_MINB
 #define RTX_TRACE_MINB 6       // resident CTAs per SM the register budget is set for
 #endif
@@ -30,6 +33,13 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint2 stack[RTX_STACK_SIZE];
+#if RTX_COOP_TRI
+    __shared__ CoopShared sh;
+    const unsigned wbase = threadIdx.x & ~31u;
+#endif
+    __shared__ uint8_t s_perm[2048];
+    fill_perm_table(s_perm, threadIdx.x, blockDim.x);
+    __syncthreads();
     Trav T;
     bool active = false;
     bool exhausted = (S.n_instances == 0u);
@@ -79,15 +89,34 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
         }
         // ---- traverse until too few lanes are left (or to the end once the queue is drained)
         const int threshold = exhausted ? 1 : fetch_th;
+#if RTX_COOP_TRI
         do {
+            uint32_t leaf_base = 0u, leaf_bits = 0u, leaf_W = 0u;
+            if (active) trav_node<ANY_HIT, STATS>(T, S, s_perm, stack, leaf_base, leaf_bits, leaf_W, &c_nodes);
+            const bool has = active && T.blas_sp >= 0 && leaf_bits != 0u;
+            const bool found = coop_triangles<ANY_HIT, STATS>(T, sh, has, leaf_base, leaf_bits, leaf_W, lane, lt_mask, wbase, &c_tris);
             if (active) {
-                if (trav_step<ANY_HIT, STATS>(T, S, stack, &c_nodes, &c_tris, &c_insts)) {
+                bool done;
+                if (ANY_HIT && found) { T.h.inst = T.cur_inst; done = true; }
+                else done = trav_finish<STATS>(T, S, sh, threadIdx.x, stack, leaf_base, T.blas_sp >= 0 ? 0u : leaf_bits, leaf_W, &c_insts);
+                if (done) {
                     active = false;
                     if (!ANY_HIT) hit_a[j] = make_float4(T.h.t, T.h.b1, T.h.b2, __uint_as_float(T.h.prim));
                     hit_inst[j] = T.h.inst;
                 }
             }
         } while (__popc(__ballot_sync(0xffffffffu, active)) >= threshold);
+#else
+        do {
+            if (active) {
+                if (trav_step<ANY_HIT, STATS>(T, S, s_perm, stack, &c_nodes, &c_tris, &c_insts)) {
+                    active = false;
+                    if (!ANY_HIT) hit_a[j] = make_float4(T.h.t, T.h.b1, T.h.b2, __uint_as_float(T.h.prim));
+                    hit_inst[j] = T.h.inst;
+                }
+            }
+        } while (__popc(__ballot_sync(0xffffffffu, active)) >= threshold);
+#endif
     }
     if (S.n_instances == 0u) {   // empty scene: everything misses
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

@@ -23,6 +23,9 @@
 namespace rtx {
 
 #define RTX_STACK_SIZE 40
+#ifndef RTX_COOP_THREADS
+#define RTX_COOP_THREADS 128     // = TRACE_BLOCK (trace.cu)
+#endif
 // A full stack drops the entry (wrong image, no memory fault) and raises g_stack_overflow, which every API call checks.
 __device__ unsigned int g_stack_overflow;
 #define RTX_PUSH(v)                                                   \
@@ -49,11 +52,13 @@ __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x 
 
 // byte i of x as a float that is affine in q (see RTX_CONV_MODE); the matching (scale, offset) are in plane_coeffs()
 template <int I>
-__device__ __forceinline__ float plane_byte(uint32_t x) {
+__device__ __forceinline__ float plane_byte(uint32_t x, uint32_t one) {
 #if RTX_CONV_MODE == 0
     return __uint_as_float(0x3F800000u | (((x >> (I * 8)) & 0xffu) << 15));     // 1 + q/256
 #else
-    return __uint_as_float(prmt(x, 0x3F800000u, 0x7604u | (I << 4)));            // 0x3F80qq00 = 1 + q*2^-15
+    uint32_t d;                                                                  // 0x3F80qq00 = 1 + q*2^-15
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "n"(0x7604 | (I << 4)));
+    return __uint_as_float(d);
 #endif
 }
 
@@ -170,10 +175,14 @@ __device__ __forceinline__ bool tri_test(const RaySpace& r, float4 a, float4 b, 
 }
 
 // Intersects the 8 quantised child boxes of one node; returns the hit mask in the traversal's group format:
-// inner children set bit 24 + (slot ^ octinv) (front-to-back priority), leaf children set their unary triangle
-// bits at their offset in the node's primitive range.
+// bits 24..31 = hit inner children at bit 24 + (slot ^ octinv) (front-to-back priority), bits 0..23 = the triangle bits of the hit leaf
+// children (child j owns bits 3j..3j+2, unary count).
+// The node carries WI = imask << 24 | W (common.cuh), so a hit child j contributes WI & C_j with a compile-time C_j: ONE predicated
+// LOP3 per child.  The octant permutation of the inner byte is one shared-memory table look-up per node (perm[o][h]: bit s of h -> bit
+// s ^ o).  (Before: per-child meta bytes that needed 2 extractions, a variable shift and an OR per child plus the meta decoding,
+// ~56 instructions per node against ~14.)
 __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4,
-                                                   float tmin, float tmax) {
+                                                   float tmin, float tmax, uint32_t one, const uint8_t* __restrict__ perm) {
     const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
     const uint32_t e = n0.w;
     const float ax = __uint_as_float((e & 0xffu) << 23) * r.ix;
@@ -197,36 +206,49 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, uint4 n0, 
     const float bzn = __fmaf_rn(fz, -w, bz), bzf = __fmaf_rn(fz, w, bz);
 #endif
     const bool nx = !(r.octinv4 & 1u), ny = !(r.octinv4 & 2u), nz = !(r.octinv4 & 4u);
-    uint32_t hitmask = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t meta4 = h ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
-        const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
-        const uint32_t xn = nx ? qhix : qlox, xf = nx ? qlox : qhix;
-        const uint32_t yn = ny ? qhiy : qloy, yf = ny ? qloy : qhiy;
-        const uint32_t zn = nz ? qhiz : qloz, zf = nz ? qloz : qhiz;
-#define RTX_CHILD(J)                                                                                         \
+    const uint32_t WI = n1.z;
+    uint32_t acc = 0;
+#define RTX_CHILD(H, J)                                                                                      \
         {                                                                                                    \
-            float t0x = __fmaf_rn(plane_byte<J>(xn), ax2, bxn);                                              \
-            float t0y = __fmaf_rn(plane_byte<J>(yn), ay2, byn);                                              \
-            float t0z = __fmaf_rn(plane_byte<J>(zn), az2, bzn);                                              \
-            float t1x = __fmaf_rn(plane_byte<J>(xf), ax2, bxf);                                              \
-            float t1y = __fmaf_rn(plane_byte<J>(yf), ay2, byf);                                              \
-            float t1z = __fmaf_rn(plane_byte<J>(zf), az2, bzf);                                              \
+            float t0x = __fmaf_rn(plane_byte<J>(xn, one), ax2, bxn);                                         \
+            float t0y = __fmaf_rn(plane_byte<J>(yn, one), ay2, byn);                                         \
+            float t0z = __fmaf_rn(plane_byte<J>(zn, one), az2, bzn);                                         \
+            float t1x = __fmaf_rn(plane_byte<J>(xf, one), ax2, bxf);                                         \
+            float t1y = __fmaf_rn(plane_byte<J>(yf, one), ay2, byf);                                         \
+            float t1z = __fmaf_rn(plane_byte<J>(zf, one), az2, bzf);                                         \
             float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                                             \
             float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                                             \
-            if (tn <= tf) hitmask |= extract_byte(child_bits4, J) << extract_byte(bit_index4, J);            \
+            asm("{ .reg .pred p; setp.le.f32 p, %1, %2; @p lop3.b32 %0, %3, %4, %0, 0xEA; }"                 \
+                : "+r"(acc) : "f"(tn), "f"(tf), "r"(WI), "n"((7u << (3 * (4 * H + J))) | (1u << (24 + 4 * H + J)))); \
         }
-        RTX_CHILD(0) RTX_CHILD(1) RTX_CHILD(2) RTX_CHILD(3)
-#undef RTX_CHILD
+#define RTX_HALF(H, QLOX, QLOY, QLOZ, QHIX, QHIY, QHIZ)                                                      \
+    {                                                                                                        \
+        const uint32_t xn = nx ? QHIX : QLOX, xf = nx ? QLOX : QHIX;                                         \
+        const uint32_t yn = ny ? QHIY : QLOY, yf = ny ? QLOY : QHIY;                                         \
+        const uint32_t zn = nz ? QHIZ : QLOZ, zf = nz ? QLOZ : QHIZ;                                         \
+        RTX_CHILD(H, 0) RTX_CHILD(H, 1) RTX_CHILD(H, 2) RTX_CHILD(H, 3)                                      \
     }
-    return hitmask;
+    RTX_HALF(0, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z)
+    RTX_HALF(1, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w)
+#undef RTX_HALF
+#undef RTX_CHILD
+    const uint32_t P = perm[((r.octinv4 & 7u) << 8) | (acc >> 24)];
+    return (acc & 0x00ffffffu) | (P << 24);
 }
+
+// bit s of h -> bit s ^ o, for all 8 octants o: the front-to-back order of the inner children (filled once per CTA)
+__device__ __forceinline__ void fill_perm_table(uint8_t* perm, unsigned tid, unsigned nthreads) {
+    for (unsigned i = tid; i < 2048u; i += nthreads) {
+        const unsigned o = i >> 8, h = i & 255u;
+        unsigned p = 0;
+        for (unsigned b = 0; b < 8u; b++)
+            if (h & (1u << b)) p |= 1u << (b ^ o);
+        perm[i] = (uint8_t)p;
+    }
+}
+
+// index of the primitive behind leaf bit `bit` of a node whose valid-primitive mask is W (primitives are stored densely in bit order)
+__device__ __forceinline__ uint32_t leaf_prim_index(uint32_t W, uint32_t bit) { return __popc(W & ~(0xffffffffu << bit)); }
 
 struct HitRec {
     float t, b1, b2;
@@ -269,10 +291,10 @@ __device__ __forceinline__ void trav_init(Trav& T, const SceneAS& S, float4 o_tm
 // closest-hit per pass against 3.98 ms; the same with pending leaf groups parked on the stack, 4.49 ms.)
 // Returns true when the ray is finished.
 template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stack, unsigned int* c_nodes, unsigned int* c_tris,
-                                          unsigned int* c_insts) {
+__device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, const uint8_t* perm, uint2* stack, unsigned int* c_nodes,
+                                          unsigned int* c_tris, unsigned int* c_insts) {
     uint2 G = T.G;
-    uint32_t leaf_base, leaf_bits;
+    uint32_t leaf_base, leaf_bits, leaf_W;
     int sp = T.sp;
     if (G.y & 0xff000000u) {
         const uint32_t bit = 31u - __clz(G.y);
@@ -284,13 +306,14 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
         const uint4* np = T.nodes + (size_t)(G.x + rel) * 5;
         const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
         if (STATS) (*c_nodes)++;
-        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t);
+        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t, S.one_bits, perm);
         G.x = n1.x;
         G.y = (hm & 0xff000000u) | (n0.w >> 24);
         leaf_base = n1.y;
         leaf_bits = hm & 0x00ffffffu;
-    } else {                                   // a leaf group that was parked on the stack
-        leaf_base = G.x; leaf_bits = G.y;
+        leaf_W = n1.z;
+    } else {                                   // a leaf group that was parked on the stack (dense bits)
+        leaf_base = G.x; leaf_bits = G.y; leaf_W = 0x00ffffffu;
         G = make_uint2(0u, 0u);
     }
 
@@ -298,7 +321,7 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
         while (leaf_bits != 0u) {
             const uint32_t bit = 31u - __clz(leaf_bits);
             leaf_bits &= ~(1u << bit);
-            const float4* tp = T.prims + (size_t)(leaf_base + bit) * 3;
+            const float4* tp = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 3;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (STATS) (*c_tris)++;
             float t, b1, b2;
@@ -318,10 +341,18 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
         // stack is back at this depth.
         const uint32_t bit = 31u - __clz(leaf_bits);
         leaf_bits &= ~(1u << bit);
-        const float4* ip = T.prims + (size_t)(leaf_base + bit) * 4;
+        const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
         const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
         if (STATS) (*c_insts)++;
-        if (leaf_bits) RTX_PUSH(make_uint2(leaf_base, leaf_bits));
+        if (leaf_bits) {                       // park the other instance leaves with their bits made dense
+            uint32_t dense = 0u;
+            do {
+                const uint32_t b = 31u - __clz(leaf_bits);
+                leaf_bits &= ~(1u << b);
+                dense |= 1u << leaf_prim_index(leaf_W, b);
+            } while (leaf_bits);
+            RTX_PUSH(make_uint2(leaf_base, dense));
+        }
         if (G.y & 0xff000000u) RTX_PUSH(G);
         T.blas_sp = sp;
         const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
@@ -340,6 +371,168 @@ __device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, uint2* stac
 
     if ((G.y & 0xff000000u) == 0u) {           // pop
         if (sp == T.blas_sp) {                 // the BLAS is exhausted: back to the TLAS / world space
+            setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
+            T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.blas_sp = -1;
+        }
+        if (sp == 0) { T.sp = 0; return true; }
+        G = stack[--sp];
+    }
+    T.G = G; T.sp = sp;
+    return false;
+}
+
+
+// ---- warp-cooperative triangle testing (RTX_COOP_TRI) -----------------------------------------------------------
+// ncu (profiles/r01_final_hotspots.txt) showed ~40 % of the closest-hit kernel's samples inside the per-lane leaf loop of
+// trav_step at 7 of 32 lanes active: a node visit yields 0 triangles for most lanes and 2-4 for a few, and every lane
+// waited for the longest list (and for one dependent LDG round trip per triangle).  Here the step is cut in three:
+//   A (per lane)   node test / parked group       -> (leaf_base, leaf_bits)
+//   B (whole warp) every pending (ray, triangle) pair of the warp is written to a shared-memory list and lane k tests
+//                  pair k with the owner's ray constants read from shared memory: one round of <= 32 tests, all
+//                  triangle loads in flight together; owners then fold the hits of their pairs into their record
+//   C (per lane)   instance entry, pop, completion.
+// The test itself (tri_test) and the closest-hit rule (lexicographic minimum of (t, instance, primitive), every pair
+// tested against the ray's original TMax) are order independent, so the result is bit-identical to the per-lane loop.
+struct CoopShared {
+    float4 ray_a[RTX_COOP_THREADS];   // object-space origin, tmin                (written by the owner when it enters a BLAS)
+    float4 ray_b[RTX_COOP_THREADS];   // Sx, Sy, Sz, tmax
+    uint4 ray_c[RTX_COOP_THREADS];    // ksel, triangle array pointer (lo, hi), -
+    uint2 item[RTX_COOP_THREADS];     // per warp, 32 pairs: (triangle index, owner lane)
+    float4 res[RTX_COOP_THREADS];     // per warp, 32 results: (t, b1, b2, bits(prim))
+};
+
+template <bool ANY_HIT, bool STATS>
+__device__ __forceinline__ void trav_node(Trav& T, const SceneAS& S, const uint8_t* perm, uint2* stack, uint32_t& leaf_base, uint32_t& leaf_bits,
+                                          uint32_t& leaf_W, unsigned int* c_nodes) {
+    uint2 G = T.G;
+    int sp = T.sp;
+    if (G.y & 0xff000000u) {
+        const uint32_t bit = 31u - __clz(G.y);
+        G.y &= ~(1u << bit);
+        const uint32_t imask = G.y & 0xffu;
+        if (G.y & 0xff000000u) RTX_PUSH(G);
+        const uint32_t slot = (bit - 24u) ^ (T.r.octinv4 & 0xffu);
+        const uint32_t rel = __popc(imask & ~(0xffffffffu << slot));
+        const uint4* np = T.nodes + (size_t)(G.x + rel) * 5;
+        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (STATS) (*c_nodes)++;
+        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t, S.one_bits, perm);
+        G.x = n1.x;
+        G.y = (hm & 0xff000000u) | (n0.w >> 24);
+        leaf_base = n1.y;
+        leaf_bits = hm & 0x00ffffffu;
+        leaf_W = n1.z;
+    } else {
+        leaf_base = G.x; leaf_bits = G.y; leaf_W = 0x00ffffffu;
+        G = make_uint2(0u, 0u);
+    }
+    T.G = G; T.sp = sp;
+}
+
+// Phase B.  Must be called by all 32 lanes in convergence.  `has` = this lane is inside a BLAS and has triangles pending.
+// Returns true (ANY_HIT only) when one of this lane's triangles was hit.
+template <bool ANY_HIT, bool STATS>
+__device__ __forceinline__ bool coop_triangles(Trav& T, CoopShared& sh, bool has, uint32_t leaf_base, uint32_t leaf_bits, uint32_t leaf_W,
+                                               unsigned lane, unsigned lt_mask, unsigned wbase, unsigned int* c_tris) {
+    bool found = false;
+    unsigned any = __ballot_sync(0xffffffffu, has);
+    while (any) {
+        const uint32_t c = has ? min((uint32_t)__popc(leaf_bits), 7u) : 0u;
+        const unsigned b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u), b2 = __ballot_sync(0xffffffffu, c & 4u);
+        const uint32_t prefix = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) + 4u * __popc(b2 & lt_mask);
+        const uint32_t total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+        const uint32_t mine_n = prefix < 32u ? min(c, 32u - prefix) : 0u;      // pairs of this lane that fit into this round
+        for (uint32_t r = 0; r < mine_n; r++) {
+            const uint32_t bit = 31u - __clz(leaf_bits);
+            leaf_bits &= ~(1u << bit);
+            sh.item[wbase + prefix + r] = make_uint2(leaf_base + leaf_prim_index(leaf_W, bit), lane);
+        }
+        __syncwarp();
+        bool hit = false;
+        if (lane < min(total, 32u)) {
+            const uint2 it = sh.item[wbase + lane];
+            const unsigned o = wbase + it.y;
+            const float4 ra = sh.ray_a[o], rb = sh.ray_b[o];
+            const uint4 rc = sh.ray_c[o];
+            const float4* tp = reinterpret_cast<const float4*>(((unsigned long long)rc.z << 32) | (unsigned long long)rc.y) + (size_t)it.x * 3;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), cc = __ldg(tp + 2);
+            if (STATS) (*c_tris)++;
+            RaySpace rs;
+            rs.ox = ra.x; rs.oy = ra.y; rs.oz = ra.z; rs.Sx = rb.x; rs.Sy = rb.y; rs.Sz = rb.z; rs.ksel = rc.x;
+            float t, u, v;
+            hit = tri_test(rs, a, b, cc, ra.w, rb.w, t, u, v);
+            if (!ANY_HIT && hit) sh.res[wbase + lane] = make_float4(t, u, v, a.w);
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {                                              // warp-uniform
+            __syncwarp();
+            if (mine_n) {
+                uint32_t mine = (hm >> prefix) & (0xffffffffu >> (32u - mine_n));
+                if (ANY_HIT) {
+                    if (mine) { found = true; leaf_bits = 0u; }
+                } else {
+                    while (mine) {
+                        const uint32_t k = __ffs(mine) - 1u;
+                        mine &= mine - 1u;
+                        const float4 r = sh.res[wbase + prefix + k];
+                        const uint32_t prim = __float_as_uint(r.w);
+                        if (T.h.inst == 0xFFFFFFFFu || hit_better(r.x, T.cur_inst, prim, T.h)) {
+                            T.h.t = r.x; T.h.b1 = r.y; T.h.b2 = r.z; T.h.prim = prim; T.h.inst = T.cur_inst;
+                        }
+                    }
+                }
+            }
+        }
+        has = has && leaf_bits != 0u;
+        any = __ballot_sync(0xffffffffu, has);
+        __syncwarp();                                          // the next round (or step) overwrites item/res
+    }
+    return found;
+}
+
+// Phase C: instance entry (TLAS lanes), pop, completion.  Returns true when the ray is finished.
+template <bool STATS>
+__device__ __forceinline__ bool trav_finish(Trav& T, const SceneAS& S, CoopShared& sh, unsigned tid, uint2* stack, uint32_t leaf_base,
+                                            uint32_t leaf_bits, uint32_t leaf_W, unsigned int* c_insts) {
+    uint2 G = T.G;
+    int sp = T.sp;
+    if (T.blas_sp < 0 && leaf_bits != 0u) {
+        const uint32_t bit = 31u - __clz(leaf_bits);
+        leaf_bits &= ~(1u << bit);
+        const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
+        const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+        if (STATS) (*c_insts)++;
+        if (leaf_bits) {                       // park the other instance leaves with their bits made dense
+            uint32_t dense = 0u;
+            do {
+                const uint32_t b = 31u - __clz(leaf_bits);
+                leaf_bits &= ~(1u << b);
+                dense |= 1u << leaf_prim_index(leaf_W, b);
+            } while (leaf_bits);
+            RTX_PUSH(make_uint2(leaf_base, dense));
+        }
+        if (G.y & 0xff000000u) RTX_PUSH(G);
+        T.blas_sp = sp;
+        const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
+        const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
+        const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
+        const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
+        const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
+        const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
+        setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
+        RaySpace ts;
+        setup_tri(ts, tdx, tdy, tdz);
+        const BlasRef br = S.blas[__float_as_uint(r3.x)];
+        T.nodes = br.nodes; T.prims = br.tris;
+        T.cur_inst = __float_as_uint(r3.y);
+        const unsigned long long pa = (unsigned long long)br.tris;
+        sh.ray_a[tid] = make_float4(tox, toy, toz, T.tmin);
+        sh.ray_b[tid] = make_float4(ts.Sx, ts.Sy, ts.Sz, T.tmax);
+        sh.ray_c[tid] = make_uint4(ts.ksel, (uint32_t)pa, (uint32_t)(pa >> 32), 0u);
+        G = make_uint2(0u, 0x80000000u);
+    }
+    if ((G.y & 0xff000000u) == 0u) {
+        if (sp == T.blas_sp) {
             setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
             T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.blas_sp = -1;
         }
