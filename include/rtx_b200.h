@@ -140,9 +140,12 @@ rtx_status rtx_last_pass_ms(rtx_ctx*, float* trace_ms, float* total_ms);
 rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stages, float* total_ms);
 /* runtime options.  RTX_OPT_TRACE_STATS: closest-hit traversals of rtx_render_pass also count nodes/triangles/instances
  * (instrumented kernel variant: for the roofline's B_ray, never for timed runs).  RTX_OPT_STAGE_TIMING: record CUDA events
- * around every traversal launch of a pass so that rtx_last_pass_ms can report the traversal share. */
+ * around every traversal launch of a pass so that rtx_last_pass_ms can report the traversal share.
+ * RTX_OPT_PASS_PARTS: 1..4 path ranges of a pass that run concurrently on separate CUDA streams (default 2; the image
+ * does not depend on it; passes with per-launch events, statistics or ReSTIR reuse always run as one part). */
 #define RTX_OPT_TRACE_STATS   1u
 #define RTX_OPT_STAGE_TIMING  2u
+#define RTX_OPT_PASS_PARTS    3u
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);

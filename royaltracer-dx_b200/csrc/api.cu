@@ -6,6 +6,8 @@
 #include <vector>
 
 #include "restir.h"
+#include <stdlib.h>
+
 #include "trace.h"
 #include "wavefront.h"
 
@@ -213,6 +215,10 @@ extern "C" rtx_status rtx_set_emissive_triangles(rtx_ctx* c, const rtx_light_tri
 static rtx_status ensure_wave(rtx_ctx* c) {
     if (c->wb_ready) return RTX_OK;
     RTX_CK(wave_alloc(&c->wb, c->cfg.width, c->cfg.height, c->cfg.samples_per_pass));
+    if (const char* e = getenv("RTX_PARTS")) {      // tuning override of RTX_OPT_PASS_PARTS
+        const int v = atoi(e);
+        if (v >= 1 && v <= WAVE_MAX_PARTS) c->wb.parts = v;
+    }
     c->wb_ready = true;
     return RTX_OK;
 }
@@ -417,16 +423,12 @@ static rtx_status trace_device_impl(rtx_ctx* c, const void* d_rays, uint32_t n, 
     RTX_CK(cudaSetDevice(c->cfg.device));
     rtx_status st;
     if ((st = ensure_trace_cap(c, n)) != RTX_OK) return st;
-    unsigned int* cursor = (unsigned int*)(c->d_stats) ;  // placeholder, replaced below
-    (void)cursor;
     static_assert(sizeof(rtx_ray) == 32, "rtx_ray must be 32 bytes");
     const unsigned grid = (n + 255) / 256;
     k_split_rays<<<grid, 256, 0, c->stream>>>((const float4*)d_rays, n, c->d_trace_o, c->d_trace_d);
-    // the cursor lives right after the stats block
-    unsigned int* d_cursor = nullptr;
+    // the cursor word of part 0 of the wavefront buffers
     if (!c->wb_ready) { if ((st = ensure_wave(c)) != RTX_OK) return st; }
-    d_cursor = c->wb.cursor;
-    RTX_CK(launch_trace(make_as(c), c->d_trace_o, c->d_trace_d, nullptr, n, d_cursor, c->d_trace_ha, c->d_trace_hi, any_hit != 0,
+    RTX_CK(launch_trace(make_as(c), c->d_trace_o, c->d_trace_d, nullptr, n, c->wb.cursor, c->d_trace_ha, c->d_trace_hi, any_hit != 0,
                         stats ? c->d_stats : nullptr, c->stream));
     k_pack_hits<<<grid, 256, 0, c->stream>>>(c->d_trace_ha, c->d_trace_hi, n, any_hit, c->d_trace_d, (rtx_hit*)d_hits);
     c->launches += 3;
@@ -526,6 +528,10 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     if (!c) return fail(RTX_ERR_ARG, "null context");
     if (option == RTX_OPT_TRACE_STATS) c->trace_stats = value != 0;
     else if (option == RTX_OPT_STAGE_TIMING) c->timing.stage_timing = value != 0;
+    else if (option == RTX_OPT_PASS_PARTS) {
+        if (value < 1u || value > (uint32_t)WAVE_MAX_PARTS) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PASS_PARTS must be 1..4");
+        c->wb.parts = (int)value;
+    }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;
 }

@@ -23,9 +23,6 @@
 namespace rtx {
 
 #define RTX_STACK_SIZE 40
-#ifndef RTX_COOP_THREADS
-#define RTX_COOP_THREADS 128     // = TRACE_BLOCK (trace.cu)
-#endif
 // A full stack drops the entry (wrong image, no memory fault) and raises g_stack_overflow, which every API call checks.
 __device__ unsigned int g_stack_overflow;
 #define RTX_PUSH(v)                                                   \
@@ -48,6 +45,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x >> (i * 8)) & 0xffu; }
 
 // byte i of x as a float that is affine in q (see RTX_CONV_MODE); the matching (scale, offset) are in plane_coeffs()
@@ -250,25 +248,16 @@ __device__ __forceinline__ void fill_perm_table(uint8_t* perm, unsigned tid, uns
 // index of the primitive behind leaf bit `bit` of a node whose valid-primitive mask is W (primitives are stored densely in bit order)
 __device__ __forceinline__ uint32_t leaf_prim_index(uint32_t W, uint32_t bit) { return __popc(W & ~(0xffffffffu << bit)); }
 
-struct HitRec {
-    float t, b1, b2;
-    uint32_t prim, inst;
-};
-
-__device__ __forceinline__ bool hit_better(float t, uint32_t inst, uint32_t prim, const HitRec& h) {
-    if (t < h.t) return true;
-    if (t > h.t) return false;
-    if (inst < h.inst) return true;
-    if (inst > h.inst) return false;
-    return prim < h.prim;
-}
-
-// Traversal state of one ray (registers) — lets a persistent warp retire and replace single lanes.
+// ---- per-ray traversal state ------------------------------------------------------------------------------------------------------
+// Hot state lives in registers (Trav); state that is touched a few times per ray lives in shared memory (TravCold), one float4 slot per
+// thread and array, so that the kernel fits 64 registers = 8 resident CTAs per SM.
 struct Trav {
-    RaySpace r;                 // current space
-    float wox, woy, woz, wdx, wdy, wdz;   // world-space ray
+    float ox, oy, oz;           // ray origin in the space currently traversed
+    float ix, iy, iz;           // approximate reciprocal direction (box tests only)
+    uint32_t octinv4;
     float tmin, tmax;
-    HitRec h;
+    float ht;                   // closest hit so far (t), tmax when there is none
+    uint32_t hinst;             // its instance, 0xFFFFFFFF = none
     const uint4* nodes; const float4* prims;
     uint2 G;
     uint32_t cur_inst;
@@ -276,131 +265,49 @@ struct Trav {
     int blas_sp;                // stack depth at which the current BLAS was entered; -1 while in the TLAS
 };
 
-__device__ __forceinline__ void trav_init(Trav& T, const SceneAS& S, float4 o_tmin, float4 d_tmax) {
-    T.wox = o_tmin.x; T.woy = o_tmin.y; T.woz = o_tmin.z; T.wdx = d_tmax.x; T.wdy = d_tmax.y; T.wdz = d_tmax.z;
+struct TravCold {               // this thread's slots
+    float4* wo;                 // world-space origin, bits(ray index)
+    float4* wd;                 // world-space direction, -
+    float4* hit;                // b1, b2, bits(prim), -
+    float4* tri;                // Sx, Sy, Sz, bits(ksel): the watertight shear constants of the BLAS being traversed
+};
+
+__device__ __forceinline__ void load_box(const Trav& T, RaySpace& r) {
+    r.ox = T.ox; r.oy = T.oy; r.oz = T.oz; r.ix = T.ix; r.iy = T.iy; r.iz = T.iz; r.octinv4 = T.octinv4;
+}
+__device__ __forceinline__ void store_box(Trav& T, const RaySpace& r) {
+    T.ox = r.ox; T.oy = r.oy; T.oz = r.oz; T.ix = r.ix; T.iy = r.iy; T.iz = r.iz; T.octinv4 = r.octinv4;
+}
+
+__device__ __forceinline__ void trav_init(Trav& T, const TravCold& C, const SceneAS& S, float4 o_tmin, float4 d_tmax, uint32_t j) {
+    *C.wo = make_float4(o_tmin.x, o_tmin.y, o_tmin.z, __uint_as_float(j));
+    *C.wd = d_tmax;
+    *C.hit = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
     T.tmin = o_tmin.w; T.tmax = d_tmax.w;
-    setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
-    T.h.t = d_tmax.w; T.h.b1 = 0.0f; T.h.b2 = 0.0f; T.h.prim = 0xFFFFFFFFu; T.h.inst = 0xFFFFFFFFu;
+    RaySpace r;
+    setup_box(r, o_tmin.x, o_tmin.y, o_tmin.z, d_tmax.x, d_tmax.y, d_tmax.z);
+    store_box(T, r);
+    T.ht = d_tmax.w; T.hinst = 0xFFFFFFFFu;
     T.nodes = S.tlas_nodes; T.prims = S.inst_recs;
     T.G = make_uint2(0u, 0x80000000u);
     T.cur_inst = 0; T.sp = 0; T.blas_sp = -1;
 }
 
-// One traversal step: at most one node intersection, then the node's leaf primitives, then a pop.
-// (Measured alternatives, both slower on C2: one triangle per step with the leaf group kept in registers, 4.38 ms
-// closest-hit per pass against 3.98 ms; the same with pending leaf groups parked on the stack, 4.49 ms.)
-// Returns true when the ray is finished.
-template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ bool trav_step(Trav& T, const SceneAS& S, const uint8_t* perm, uint2* stack, unsigned int* c_nodes,
-                                          unsigned int* c_tris, unsigned int* c_insts) {
-    uint2 G = T.G;
-    uint32_t leaf_base, leaf_bits, leaf_W;
-    int sp = T.sp;
-    if (G.y & 0xff000000u) {
-        const uint32_t bit = 31u - __clz(G.y);
-        G.y &= ~(1u << bit);
-        const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
-        if (G.y & 0xff000000u) RTX_PUSH(G);
-        const uint32_t slot = (bit - 24u) ^ (T.r.octinv4 & 0xffu);
-        const uint32_t rel = __popc(imask & ~(0xffffffffu << slot));
-        const uint4* np = T.nodes + (size_t)(G.x + rel) * 5;
-        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-        if (STATS) (*c_nodes)++;
-        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t, S.one_bits, perm);
-        G.x = n1.x;
-        G.y = (hm & 0xff000000u) | (n0.w >> 24);
-        leaf_base = n1.y;
-        leaf_bits = hm & 0x00ffffffu;
-        leaf_W = n1.z;
-    } else {                                   // a leaf group that was parked on the stack (dense bits)
-        leaf_base = G.x; leaf_bits = G.y; leaf_W = 0x00ffffffu;
-        G = make_uint2(0u, 0u);
-    }
+// ---- phase-scheduled traversal -------------------------------------------------------------------------------------
+// A step of one ray is: (N) intersect one node (or take a parked instance-leaf group from the stack), then (T) test the triangles of the
+// hit leaf children or (I) enter one instance, then (P) pop when the current group is used up.
+// ncu on C3 (profiles/r01_s4_*): with all of that in one per-lane step, the triangle loop ran at 2.3 of 32 lanes and the instance entry at
+// 4.5 — a lane meets a triangle leaf on one node visit in nine and an instance on one in six, yet with 23 active lanes nearly every
+// iteration of the warp paid for all three code paths.  Here a lane that finds triangles or an instance leaf PARKS (keeps
+// (leaf_base, leaf_bits, leaf_W) in registers) and the warp runs T / I only when enough lanes are parked, or when too few lanes are left
+// with node work (trace.cu).  A parked lane does nothing in between, so every ray still executes exactly the same sequence of steps and
+// the results are bit-identical.
+// (Measured alternatives, all slower: one triangle per step with the leaf group kept in registers; pending leaf groups parked on the
+// stack; warp-cooperative triangle tests through a shared-memory pair list, -5 % on C2 / +4 % on C3 against the per-lane step;
+// prefetch.global.L1 of a parked lane's first primitive, -2 %.)
+enum { PEND_NONE = 0, PEND_TRI = 1, PEND_INST = 2 };
 
-    if (T.blas_sp >= 0) {
-        while (leaf_bits != 0u) {
-            const uint32_t bit = 31u - __clz(leaf_bits);
-            leaf_bits &= ~(1u << bit);
-            const float4* tp = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 3;
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            if (STATS) (*c_tris)++;
-            float t, b1, b2;
-            if (tri_test(T.r, a, b, c, T.tmin, T.tmax, t, b1, b2)) {
-                const uint32_t prim = __float_as_uint(a.w);
-                if (ANY_HIT) {
-                    T.h.inst = T.cur_inst;
-                    return true;
-                }
-                if (T.h.inst == 0xFFFFFFFFu || hit_better(t, T.cur_inst, prim, T.h)) {
-                    T.h.t = t; T.h.b1 = b1; T.h.b2 = b2; T.h.prim = prim; T.h.inst = T.cur_inst;
-                }
-            }
-        }
-    } else if (leaf_bits != 0u) {
-        // instance leaf: enter the BLAS.  What is left of this level goes to the stack; the BLAS is left again when the
-        // stack is back at this depth.
-        const uint32_t bit = 31u - __clz(leaf_bits);
-        leaf_bits &= ~(1u << bit);
-        const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
-        const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-        if (STATS) (*c_insts)++;
-        if (leaf_bits) {                       // park the other instance leaves with their bits made dense
-            uint32_t dense = 0u;
-            do {
-                const uint32_t b = 31u - __clz(leaf_bits);
-                leaf_bits &= ~(1u << b);
-                dense |= 1u << leaf_prim_index(leaf_W, b);
-            } while (leaf_bits);
-            RTX_PUSH(make_uint2(leaf_base, dense));
-        }
-        if (G.y & 0xff000000u) RTX_PUSH(G);
-        T.blas_sp = sp;
-        const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
-        const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
-        const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
-        const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
-        const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
-        const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
-        setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
-        setup_tri(T.r, tdx, tdy, tdz);
-        const BlasRef br = S.blas[__float_as_uint(r3.x)];
-        T.nodes = br.nodes; T.prims = br.tris;
-        T.cur_inst = __float_as_uint(r3.y);
-        G = make_uint2(0u, 0x80000000u);
-    }
-
-    if ((G.y & 0xff000000u) == 0u) {           // pop
-        if (sp == T.blas_sp) {                 // the BLAS is exhausted: back to the TLAS / world space
-            setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
-            T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.blas_sp = -1;
-        }
-        if (sp == 0) { T.sp = 0; return true; }
-        G = stack[--sp];
-    }
-    T.G = G; T.sp = sp;
-    return false;
-}
-
-
-// ---- warp-cooperative triangle testing (RTX_COOP_TRI) -----------------------------------------------------------
-// ncu (profiles/r01_final_hotspots.txt) showed ~40 % of the closest-hit kernel's samples inside the per-lane leaf loop of
-// trav_step at 7 of 32 lanes active: a node visit yields 0 triangles for most lanes and 2-4 for a few, and every lane
-// waited for the longest list (and for one dependent LDG round trip per triangle).  Here the step is cut in three:
-//   A (per lane)   node test / parked group       -> (leaf_base, leaf_bits)
-//   B (whole warp) every pending (ray, triangle) pair of the warp is written to a shared-memory list and lane k tests
-//                  pair k with the owner's ray constants read from shared memory: one round of <= 32 tests, all
-//                  triangle loads in flight together; owners then fold the hits of their pairs into their record
-//   C (per lane)   instance entry, pop, completion.
-// The test itself (tri_test) and the closest-hit rule (lexicographic minimum of (t, instance, primitive), every pair
-// tested against the ray's original TMax) are order independent, so the result is bit-identical to the per-lane loop.
-struct CoopShared {
-    float4 ray_a[RTX_COOP_THREADS];   // object-space origin, tmin                (written by the owner when it enters a BLAS)
-    float4 ray_b[RTX_COOP_THREADS];   // Sx, Sy, Sz, tmax
-    uint4 ray_c[RTX_COOP_THREADS];    // ksel, triangle array pointer (lo, hi), -
-    uint2 item[RTX_COOP_THREADS];     // per warp, 32 pairs: (triangle index, owner lane)
-    float4 res[RTX_COOP_THREADS];     // per warp, 32 results: (t, b1, b2, bits(prim))
-};
-
+// (N).  Leaves (leaf_base, leaf_bits, leaf_W) != 0 when the lane has leaf work.
 template <bool ANY_HIT, bool STATS>
 __device__ __forceinline__ void trav_node(Trav& T, const SceneAS& S, const uint8_t* perm, uint2* stack, uint32_t& leaf_base, uint32_t& leaf_bits,
                                           uint32_t& leaf_W, unsigned int* c_nodes) {
@@ -409,137 +316,112 @@ __device__ __forceinline__ void trav_node(Trav& T, const SceneAS& S, const uint8
     if (G.y & 0xff000000u) {
         const uint32_t bit = 31u - __clz(G.y);
         G.y &= ~(1u << bit);
-        const uint32_t imask = G.y & 0xffu;
+        const uint32_t imask = G.y & 0xffu;   // low byte carries the node's imask for relative indexing
         if (G.y & 0xff000000u) RTX_PUSH(G);
-        const uint32_t slot = (bit - 24u) ^ (T.r.octinv4 & 0xffu);
+        const uint32_t slot = (bit - 24u) ^ (T.octinv4 & 0xffu);
         const uint32_t rel = __popc(imask & ~(0xffffffffu << slot));
         const uint4* np = T.nodes + (size_t)(G.x + rel) * 5;
         const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
         if (STATS) (*c_nodes)++;
-        const uint32_t hm = intersect_node(T.r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.h.t, S.one_bits, perm);
+        RaySpace r;
+        load_box(T, r);
+        const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, T.tmin, ANY_HIT ? T.tmax : T.ht, S.one_bits, perm);
         G.x = n1.x;
         G.y = (hm & 0xff000000u) | (n0.w >> 24);
         leaf_base = n1.y;
         leaf_bits = hm & 0x00ffffffu;
         leaf_W = n1.z;
-    } else {
+    } else {                                   // an instance-leaf group that was parked on the stack (dense bits)
         leaf_base = G.x; leaf_bits = G.y; leaf_W = 0x00ffffffu;
         G = make_uint2(0u, 0u);
     }
     T.G = G; T.sp = sp;
 }
 
-// Phase B.  Must be called by all 32 lanes in convergence.  `has` = this lane is inside a BLAS and has triangles pending.
-// Returns true (ANY_HIT only) when one of this lane's triangles was hit.
+// (T).  Returns true (ANY_HIT only) when a triangle was hit.
 template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ bool coop_triangles(Trav& T, CoopShared& sh, bool has, uint32_t leaf_base, uint32_t leaf_bits, uint32_t leaf_W,
-                                               unsigned lane, unsigned lt_mask, unsigned wbase, unsigned int* c_tris) {
-    bool found = false;
-    unsigned any = __ballot_sync(0xffffffffu, has);
-    while (any) {
-        const uint32_t c = has ? min((uint32_t)__popc(leaf_bits), 7u) : 0u;
-        const unsigned b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u), b2 = __ballot_sync(0xffffffffu, c & 4u);
-        const uint32_t prefix = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) + 4u * __popc(b2 & lt_mask);
-        const uint32_t total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
-        const uint32_t mine_n = prefix < 32u ? min(c, 32u - prefix) : 0u;      // pairs of this lane that fit into this round
-        for (uint32_t r = 0; r < mine_n; r++) {
-            const uint32_t bit = 31u - __clz(leaf_bits);
-            leaf_bits &= ~(1u << bit);
-            sh.item[wbase + prefix + r] = make_uint2(leaf_base + leaf_prim_index(leaf_W, bit), lane);
-        }
-        __syncwarp();
-        bool hit = false;
-        if (lane < min(total, 32u)) {
-            const uint2 it = sh.item[wbase + lane];
-            const unsigned o = wbase + it.y;
-            const float4 ra = sh.ray_a[o], rb = sh.ray_b[o];
-            const uint4 rc = sh.ray_c[o];
-            const float4* tp = reinterpret_cast<const float4*>(((unsigned long long)rc.z << 32) | (unsigned long long)rc.y) + (size_t)it.x * 3;
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), cc = __ldg(tp + 2);
-            if (STATS) (*c_tris)++;
-            RaySpace rs;
-            rs.ox = ra.x; rs.oy = ra.y; rs.oz = ra.z; rs.Sx = rb.x; rs.Sy = rb.y; rs.Sz = rb.z; rs.ksel = rc.x;
-            float t, u, v;
-            hit = tri_test(rs, a, b, cc, ra.w, rb.w, t, u, v);
-            if (!ANY_HIT && hit) sh.res[wbase + lane] = make_float4(t, u, v, a.w);
-        }
-        const unsigned hm = __ballot_sync(0xffffffffu, hit);
-        if (hm) {                                              // warp-uniform
-            __syncwarp();
-            if (mine_n) {
-                uint32_t mine = (hm >> prefix) & (0xffffffffu >> (32u - mine_n));
-                if (ANY_HIT) {
-                    if (mine) { found = true; leaf_bits = 0u; }
-                } else {
-                    while (mine) {
-                        const uint32_t k = __ffs(mine) - 1u;
-                        mine &= mine - 1u;
-                        const float4 r = sh.res[wbase + prefix + k];
-                        const uint32_t prim = __float_as_uint(r.w);
-                        if (T.h.inst == 0xFFFFFFFFu || hit_better(r.x, T.cur_inst, prim, T.h)) {
-                            T.h.t = r.x; T.h.b1 = r.y; T.h.b2 = r.z; T.h.prim = prim; T.h.inst = T.cur_inst;
-                        }
-                    }
-                }
-            }
-        }
-        has = has && leaf_bits != 0u;
-        any = __ballot_sync(0xffffffffu, has);
-        __syncwarp();                                          // the next round (or step) overwrites item/res
-    }
-    return found;
-}
-
-// Phase C: instance entry (TLAS lanes), pop, completion.  Returns true when the ray is finished.
-template <bool STATS>
-__device__ __forceinline__ bool trav_finish(Trav& T, const SceneAS& S, CoopShared& sh, unsigned tid, uint2* stack, uint32_t leaf_base,
-                                            uint32_t leaf_bits, uint32_t leaf_W, unsigned int* c_insts) {
-    uint2 G = T.G;
-    int sp = T.sp;
-    if (T.blas_sp < 0 && leaf_bits != 0u) {
+__device__ __forceinline__ bool trav_tris(Trav& T, const TravCold& C, uint32_t leaf_base, uint32_t leaf_bits, uint32_t leaf_W, unsigned int* c_tris) {
+    const float4 ts = *C.tri;
+    RaySpace r;
+    r.ox = T.ox; r.oy = T.oy; r.oz = T.oz; r.Sx = ts.x; r.Sy = ts.y; r.Sz = ts.z; r.ksel = __float_as_uint(ts.w);
+    while (leaf_bits != 0u) {
         const uint32_t bit = 31u - __clz(leaf_bits);
         leaf_bits &= ~(1u << bit);
-        const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
-        const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
-        if (STATS) (*c_insts)++;
-        if (leaf_bits) {                       // park the other instance leaves with their bits made dense
-            uint32_t dense = 0u;
-            do {
-                const uint32_t b = 31u - __clz(leaf_bits);
-                leaf_bits &= ~(1u << b);
-                dense |= 1u << leaf_prim_index(leaf_W, b);
-            } while (leaf_bits);
-            RTX_PUSH(make_uint2(leaf_base, dense));
+        const float4* tp = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 3;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (STATS) (*c_tris)++;
+        float t, b1, b2;
+        if (tri_test(r, a, b, c, T.tmin, T.tmax, t, b1, b2)) {
+            if (ANY_HIT) return true;
+            const uint32_t prim = __float_as_uint(a.w);
+            // closest hit = lexicographic minimum of (t, instance, primitive)
+            bool better = T.hinst == 0xFFFFFFFFu || t < T.ht;
+            if (!better && t == T.ht)
+                better = T.cur_inst < T.hinst || (T.cur_inst == T.hinst && prim < __float_as_uint(C.hit->z));
+            if (better) {
+                T.ht = t; T.hinst = T.cur_inst;
+                *C.hit = make_float4(b1, b2, a.w, 0.0f);
+            }
         }
-        if (G.y & 0xff000000u) RTX_PUSH(G);
-        T.blas_sp = sp;
-        const float tox = ((r0.x * T.wox + r0.y * T.woy) + r0.z * T.woz) + r0.w * 1.0f;
-        const float toy = ((r1.x * T.wox + r1.y * T.woy) + r1.z * T.woz) + r1.w * 1.0f;
-        const float toz = ((r2.x * T.wox + r2.y * T.woy) + r2.z * T.woz) + r2.w * 1.0f;
-        const float tdx = ((r0.x * T.wdx + r0.y * T.wdy) + r0.z * T.wdz) + r0.w * 0.0f;
-        const float tdy = ((r1.x * T.wdx + r1.y * T.wdy) + r1.z * T.wdz) + r1.w * 0.0f;
-        const float tdz = ((r2.x * T.wdx + r2.y * T.wdy) + r2.z * T.wdz) + r2.w * 0.0f;
-        setup_box(T.r, tox, toy, toz, tdx, tdy, tdz);
-        RaySpace ts;
-        setup_tri(ts, tdx, tdy, tdz);
-        const BlasRef br = S.blas[__float_as_uint(r3.x)];
-        T.nodes = br.nodes; T.prims = br.tris;
-        T.cur_inst = __float_as_uint(r3.y);
-        const unsigned long long pa = (unsigned long long)br.tris;
-        sh.ray_a[tid] = make_float4(tox, toy, toz, T.tmin);
-        sh.ray_b[tid] = make_float4(ts.Sx, ts.Sy, ts.Sz, T.tmax);
-        sh.ray_c[tid] = make_uint4(ts.ksel, (uint32_t)pa, (uint32_t)(pa >> 32), 0u);
-        G = make_uint2(0u, 0x80000000u);
     }
-    if ((G.y & 0xff000000u) == 0u) {
-        if (sp == T.blas_sp) {
-            setup_box(T.r, T.wox, T.woy, T.woz, T.wdx, T.wdy, T.wdz);
+    return false;
+}
+
+// (I)
+template <bool STATS>
+__device__ __forceinline__ void trav_enter_instance(Trav& T, const TravCold& C, const SceneAS& S, uint2* stack, uint32_t leaf_base,
+                                                    uint32_t leaf_bits, uint32_t leaf_W, unsigned int* c_insts) {
+    uint2 G = T.G;
+    int sp = T.sp;
+    const uint32_t bit = 31u - __clz(leaf_bits);
+    leaf_bits &= ~(1u << bit);
+    const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
+    const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+    if (STATS) (*c_insts)++;
+    if (leaf_bits) {                       // park the other instance leaves with their bits made dense
+        uint32_t dense = 0u;
+        do {
+            const uint32_t b = 31u - __clz(leaf_bits);
+            leaf_bits &= ~(1u << b);
+            dense |= 1u << leaf_prim_index(leaf_W, b);
+        } while (leaf_bits);
+        RTX_PUSH(make_uint2(leaf_base, dense));
+    }
+    if (G.y & 0xff000000u) RTX_PUSH(G);
+    T.blas_sp = sp;
+    const float4 wo = *C.wo, wd = *C.wd;
+    const float tox = ((r0.x * wo.x + r0.y * wo.y) + r0.z * wo.z) + r0.w * 1.0f;
+    const float toy = ((r1.x * wo.x + r1.y * wo.y) + r1.z * wo.z) + r1.w * 1.0f;
+    const float toz = ((r2.x * wo.x + r2.y * wo.y) + r2.z * wo.z) + r2.w * 1.0f;
+    const float tdx = ((r0.x * wd.x + r0.y * wd.y) + r0.z * wd.z) + r0.w * 0.0f;
+    const float tdy = ((r1.x * wd.x + r1.y * wd.y) + r1.z * wd.z) + r1.w * 0.0f;
+    const float tdz = ((r2.x * wd.x + r2.y * wd.y) + r2.z * wd.z) + r2.w * 0.0f;
+    RaySpace r;
+    setup_box(r, tox, toy, toz, tdx, tdy, tdz);
+    setup_tri(r, tdx, tdy, tdz);
+    store_box(T, r);
+    *C.tri = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float(r.ksel));
+    const BlasRef br = S.blas[__float_as_uint(r3.x)];
+    T.nodes = br.nodes; T.prims = br.tris;
+    T.cur_inst = __float_as_uint(r3.y);
+    T.G = make_uint2(0u, 0x80000000u); T.sp = sp;
+}
+
+// (P) pops the next group when the current one is used up; returns true when the ray is finished
+__device__ __forceinline__ bool trav_pop(Trav& T, const TravCold& C, const SceneAS& S, uint2* stack) {
+    if ((T.G.y & 0xff000000u) == 0u) {
+        int sp = T.sp;
+        if (sp == T.blas_sp) {                 // the BLAS is exhausted: back to the TLAS / world space
+            const float4 wo = *C.wo, wd = *C.wd;
+            RaySpace r;
+            setup_box(r, wo.x, wo.y, wo.z, wd.x, wd.y, wd.z);
+            store_box(T, r);
             T.nodes = S.tlas_nodes; T.prims = S.inst_recs; T.blas_sp = -1;
         }
-        if (sp == 0) { T.sp = 0; return true; }
-        G = stack[--sp];
+        if (sp == 0) return true;
+        T.G = stack[--sp];
+        T.sp = sp;
     }
-    T.G = G; T.sp = sp;
     return false;
 }
 

@@ -43,11 +43,13 @@ __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t
 }
 
 __global__ void __launch_bounds__(WF_BLOCK)
-k_generate(StateView st, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H, uint32_t first_sample,
-           uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi, unsigned long long* ray_counters) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) { *q0.count = st.n; atomicAdd(&ray_counters[2], (unsigned long long)st.n); }
-    if (p >= st.n) return;
+k_generate(StateView st, uint32_t p0, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
+           uint32_t first_sample, uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi, unsigned long long* ray_counters) {
+    // paths [p0, p0 + np) of the pass (one part of the frame, see wave_render_pass); queue slot = index within the part
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) { *q0.count = np; atomicAdd(&ray_counters[2], (unsigned long long)np); }
+    if (k >= np) return;
+    const uint32_t p = p0 + k;
     const uint32_t npx = W * H;
     const uint32_t pixel = p % npx, s = p / npx;
     const uint32_t x = pixel % W, y = pixel / W;
@@ -56,9 +58,9 @@ k_generate(StateView st, RayQueue q0, const rtx_camera_params* __restrict__ cam,
     if (flags & RTX_FLAG_JITTER) { jx = RandomFloat(seed); jy = RandomFloat(seed); }
     f3 o, dir;
     CameraRay(cam, W, H, x, y, jx, jy, o, dir);
-    q0.o_tmin[p] = f4(o, 0.0001f);
-    q0.d_tmax[p] = f4(dir, 10000.0f);
-    q0.pid[p] = p;
+    q0.o_tmin[k] = f4(o, 0.0001f);
+    q0.d_tmax[k] = f4(dir, 10000.0f);
+    q0.pid[k] = p;
     st.at(SP_N1, p) = make_float4(0, 0, 0, __uint_as_float(seed.x));
     st.at(SP_O, p) = f4u(-dir, seed.y);
     st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
@@ -417,11 +419,12 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
 
 // ---- stage: estimator E0 (Pass_init_di_v7.hlsl:166-181 + Pass_spat_di_v7.hlsl:334-372 with no accepted neighbours)
 __global__ void __launch_bounds__(WF_BLOCK)
-k_finalize(StateView st, SceneData S, const float* __restrict__ vis_di, const float* __restrict__ vis_gi,
+k_finalize(StateView st, uint32_t p0, uint32_t np, SceneData S, const float* __restrict__ vis_di, const float* __restrict__ vis_gi,
            const uint32_t* __restrict__ shadow_counts, unsigned long long* ray_counters) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
-    if (p >= st.n) return;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
+    if (k >= np) return;
+    const uint32_t p = p0 + k;
     const float4 res = st.at(SP_RESULT, p);
     if (res.w != 1.0f) return;
     const float4 a0 = st.at(SP_X1, p);
@@ -566,8 +569,8 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMalloc((void**)&B->hit_inst, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->vis_di, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->vis_gi, (size_t)n * 4));
-    CKE(cudaMalloc((void**)&B->counts, 128 * 4));
-    CKE(cudaMalloc((void**)&B->cursor, 16));
+    CKE(cudaMalloc((void**)&B->counts, WAVE_MAX_PARTS * 128 * 4));
+    CKE(cudaMalloc((void**)&B->cursor, WAVE_MAX_PARTS * 16));
     CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
     CKE(cudaMemset(B->ray_counters, 0, 64));
     CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
@@ -582,6 +585,11 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
 }
 
 void wave_free(WaveBuffers* B) {
+    for (int i = 0; i < WAVE_MAX_PARTS - 1; i++) {
+        if (B->aux[i]) cudaStreamDestroy(B->aux[i]);
+        if (B->ev_join[i]) cudaEventDestroy(B->ev_join[i]);
+    }
+    if (B->ev_fork) cudaEventDestroy(B->ev_fork);
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
     void* ptrs[] = {B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
@@ -597,16 +605,49 @@ k_scatter_vis(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ p
     if (hit_inst[j] != 0xFFFFFFFFu) vis[pid[j]] = 0.0f;
 }
 
+// One DispatchRays-equivalent.  The frame's paths are cut into `parts` contiguous ranges that run the whole stage sequence independently,
+// part 0 on the caller's stream and the others on auxiliary streams (forked from and joined back into the caller's stream with events):
+// every persistent traversal launch ends in a tail in which a few warps finish the longest rays on an otherwise empty GPU (0.14 ms of a
+// 0.43 ms launch at 1080p, profiles/r01_s4_*), and the other parts' kernels fill it.  Paths never interact before the accumulation, so the
+// result does not depend on `parts`.
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
                              uint64_t* launches, PassTiming* T, bool accumulate) {
     const uint32_t npx = S.width * S.height;
     const uint32_t n = npx * spp;
     if (n > B.n_paths) return cudaErrorInvalidValue;
     StateView st{B.state, n};
-    const unsigned grid = (n + WF_BLOCK - 1) / WF_BLOCK;
     uint64_t L = 0;
     T->n_marks = 0;
-    auto mark = [&](StageKind k) -> cudaError_t {       // per-launch CUDA events (RTX_OPT_STAGE_TIMING only)
+    int parts = B.parts < 1 ? 1 : (B.parts > WAVE_MAX_PARTS ? WAVE_MAX_PARTS : B.parts);
+    // per-launch events, the counting traversal variant, the material-binned queues and the ReSTIR frame (which reads the hit records
+    // of the whole frame afterwards) run as one part
+    if (T->stage_timing || T->stats || !accumulate || (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) || n < 65536u) parts = 1;
+    for (int h = 1; h < parts; h++) {
+        if (!B.aux[h - 1]) CKE(cudaStreamCreateWithFlags(&B.aux[h - 1], cudaStreamNonBlocking));
+        if (!B.ev_join[h - 1]) CKE(cudaEventCreateWithFlags(&B.ev_join[h - 1], cudaEventDisableTiming));
+    }
+    if (parts > 1 && !B.ev_fork) CKE(cudaEventCreateWithFlags(&B.ev_fork, cudaEventDisableTiming));
+
+    struct Part {
+        cudaStream_t stream; uint32_t p0, np; unsigned grid, ggrid;
+        uint32_t* counts; unsigned int* cursor; float4* hit_a; uint32_t* hit_inst;
+        RayQueue q[2], sdi, sgi, qin, qout;
+        int cur;
+    } P[WAVE_MAX_PARTS];
+    auto view = [](const RayQueue& q, uint32_t off) { RayQueue v = q; v.o_tmin += off; v.d_tmax += off; v.pid += off; return v; };
+    for (int h = 0; h < parts; h++) {
+        Part& p = P[h];
+        p.stream = h == 0 ? stream : B.aux[h - 1];
+        p.p0 = (uint32_t)((uint64_t)n * h / parts); p.np = (uint32_t)((uint64_t)n * (h + 1) / parts) - p.p0;
+        p.grid = (p.np + WF_BLOCK - 1) / WF_BLOCK; p.ggrid = (p.np + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
+        p.counts = B.counts + 128 * h; p.cursor = B.cursor + 4 * h;
+        p.hit_a = B.hit_a + p.p0; p.hit_inst = B.hit_inst + p.p0;
+        // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
+        p.q[0] = view(B.q[0], p.p0); p.q[1] = view(B.q[1], p.p0); p.sdi = view(B.sq[0], p.p0); p.sgi = view(B.sq[1], p.p0);
+        p.sdi.count = p.counts + 2; p.sgi.count = p.counts + 3;
+        p.cur = 0;
+    }
+    auto mark = [&](StageKind k) -> cudaError_t {       // per-launch CUDA events (RTX_OPT_STAGE_TIMING only: one part)
         if (T->stage_timing && T->n_marks + 2 < WAVE_MAX_EVENTS) {
             T->kind[T->n_marks] = (unsigned char)k;
             CKE(cudaEventRecord(T->ev[2 + T->n_marks], stream));
@@ -615,59 +656,83 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         L++;
         return cudaSuccess;
     };
-    auto closest = [&](const RayQueue& q) -> cudaError_t {
+    auto closest = [&](Part& p, const RayQueue& q) -> cudaError_t {
         CKE(mark(SK_CLOSEST));
-        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, false, T->stats, stream);
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, parts);
     };
-    auto shadow = [&](const RayQueue& q, float* vis) -> cudaError_t {
+    auto shadow = [&](Part& p, const RayQueue& q, float* vis) -> cudaError_t {
         CKE(mark(SK_ANY));
-        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream));
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts));
         CKE(mark(SK_SCATTER));
-        k_scatter_vis<<<grid, WF_BLOCK, 0, stream>>>(q.count, q.pid, B.hit_inst, vis);
+        k_scatter_vis<<<p.grid, WF_BLOCK, 0, p.stream>>>(q.count, q.pid, p.hit_inst, vis);
         return cudaSuccess;
     };
-    CKE(cudaMemsetAsync(B.counts, 0, 128 * 4, stream));
-    // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
-    RayQueue q0 = B.q[0], q1 = B.q[1], sdi = B.sq[0], sgi = B.sq[1];
-    q0.count = B.counts + 0; q1.count = B.counts + 1; sdi.count = B.counts + 2; sgi.count = B.counts + 3;
+    // stage s of one part; the parts are issued round-robin stage by stage so that every stream always has work queued
+    const int n_stages = 7 + 2 * ((int)S.bounces + 1) + 2;
+    auto stage = [&](Part& p, int s) -> cudaError_t {
+        RayQueue q0 = p.q[0], q1 = p.q[1], qa = p.q[0];
+        q0.count = p.counts + 0; q1.count = p.counts + 1; qa.count = p.counts + 4;
+        const int last = 7 + 2 * ((int)S.bounces + 1);
+        if (s == 0) {
+            CKE(cudaMemsetAsync(p.counts, 0, 128 * 4, p.stream));
+            CKE(mark(SK_GENERATE));
+            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.p0, p.np, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
+                                                          B.ray_counters);
+        } else if (s == 1) {
+            CKE(closest(p, q0));
+        } else if (s == 2) {
+            CKE(mark(SK_SHADE_PRIMARY));
+            k_shade_primary<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, q0, p.hit_a, p.hit_inst, q1, B.ray_counters);
+        } else if (s == 3) {
+            CKE(closest(p, q1));
+        } else if (s == 4) {
+            CKE(mark(SK_DI_FINISH));
+            k_di_finish<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, q1, p.hit_a, p.hit_inst, p.sdi, qa, B.ray_counters);
+        } else if (s == 5) {
+            CKE(shadow(p, p.sdi, B.vis_di));        // DI visibility (connect); hit_inst is reused by the next closest trace
+        } else if (s == 6) {
+            CKE(closest(p, qa));
+            p.qin = qa; p.cur = 0;
+        } else if (s < last) {
+            const uint32_t iter = (uint32_t)(s - 7) / 2u;
+            if (((s - 7) & 1) == 0) {               // k_gi_step(iter)
+                p.qout = p.q[p.cur ^ 1]; p.qout.count = p.counts + 5 + iter;
+                const uint32_t* perm = nullptr;
+                if (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) {
+                    CKE(mark(SK_SORT));
+                    CKE(cudaMemsetAsync(B.bins, 0, 2 * WF_NBIN * 4, p.stream));
+                    k_bin_count<<<p.grid, WF_BLOCK, 0, p.stream>>>(S, p.qin.count, p.hit_a, p.hit_inst, B.bin_keys, B.bins);
+                    k_bin_scan<<<1, 32, 0, p.stream>>>(B.bins);
+                    k_bin_scatter<<<p.grid, WF_BLOCK, 0, p.stream>>>(p.qin.count, B.bin_keys, B.bins, B.perm);
+                    L += 2;
+                    perm = B.perm;
+                }
+                CKE(mark(SK_GI_STEP));
+                if (iter == 0u) k_gi_step<true><<<p.ggrid, RTX_GI_BLOCK, 0, p.stream>>>(st, S, p.qin, p.hit_a, p.hit_inst, p.sgi, p.qout, iter, B.ray_counters, perm);
+                else k_gi_step<false><<<p.ggrid, RTX_GI_BLOCK, 0, p.stream>>>(st, S, p.qin, p.hit_a, p.hit_inst, p.sgi, p.qout, iter, B.ray_counters, perm);
+            } else if (iter < S.bounces) {
+                CKE(closest(p, p.qout));
+                p.qin = p.qout; p.cur ^= 1;
+            }
+        } else if (s == last) {
+            CKE(shadow(p, p.sgi, B.vis_gi));
+        } else {
+            CKE(mark(SK_FINALIZE));
+            k_finalize<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.p0, p.np, S, B.vis_di, B.vis_gi, p.counts + 2, B.ray_counters);
+        }
+        return cudaSuccess;
+    };
     CKE(cudaEventRecord(T->ev[0], stream));
-    CKE(mark(SK_GENERATE));
-    k_generate<<<grid, WF_BLOCK, 0, stream>>>(st, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi, B.ray_counters);
-    CKE(closest(q0));
-    CKE(mark(SK_SHADE_PRIMARY));
-    k_shade_primary<<<grid, WF_BLOCK, 0, stream>>>(st, S, q0, B.hit_a, B.hit_inst, q1, B.ray_counters);
-    CKE(closest(q1));
-    RayQueue qa = B.q[0]; qa.count = B.counts + 4;
-    CKE(mark(SK_DI_FINISH));
-    k_di_finish<<<grid, WF_BLOCK, 0, stream>>>(st, S, q1, B.hit_a, B.hit_inst, sdi, qa, B.ray_counters);
-    CKE(shadow(sdi, B.vis_di));                 // DI visibility (connect); hit_inst is reused by the next closest trace
-    CKE(closest(qa));
-    int cur = 0;
-    RayQueue qin = qa;
-    for (uint32_t iter = 0; iter <= S.bounces; iter++) {
-        RayQueue qout = B.q[cur ^ 1]; qout.count = B.counts + 5 + iter;
-        const unsigned ggrid = (n + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
-        const uint32_t* perm = nullptr;
-        if (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) {
-            CKE(mark(SK_SORT));
-            CKE(cudaMemsetAsync(B.bins, 0, 2 * WF_NBIN * 4, stream));
-            k_bin_count<<<grid, WF_BLOCK, 0, stream>>>(S, qin.count, B.hit_a, B.hit_inst, B.bin_keys, B.bins);
-            k_bin_scan<<<1, 32, 0, stream>>>(B.bins);
-            k_bin_scatter<<<grid, WF_BLOCK, 0, stream>>>(qin.count, B.bin_keys, B.bins, B.perm);
-            L += 2;
-            perm = B.perm;
-        }
-        CKE(mark(SK_GI_STEP));
-        if (iter == 0u) k_gi_step<true><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters, perm);
-        else k_gi_step<false><<<ggrid, RTX_GI_BLOCK, 0, stream>>>(st, S, qin, B.hit_a, B.hit_inst, sgi, qout, iter, B.ray_counters, perm);
-        if (iter < S.bounces) {
-            CKE(closest(qout));
-            qin = qout; cur ^= 1;
-        }
+    if (parts > 1) {
+        CKE(cudaEventRecord(B.ev_fork, stream));
+        for (int h = 1; h < parts; h++) CKE(cudaStreamWaitEvent(P[h].stream, B.ev_fork, 0));
     }
-    CKE(shadow(sgi, B.vis_gi));
-    CKE(mark(SK_FINALIZE));
-    k_finalize<<<grid, WF_BLOCK, 0, stream>>>(st, S, B.vis_di, B.vis_gi, B.counts + 2, B.ray_counters);
+    for (int s = 0; s < n_stages; s++)
+        for (int h = 0; h < parts; h++) CKE(stage(P[h], s));
+    for (int h = 1; h < parts; h++) {
+        CKE(cudaEventRecord(B.ev_join[h - 1], P[h].stream));
+        CKE(cudaStreamWaitEvent(stream, B.ev_join[h - 1], 0));
+    }
     if (accumulate) {       // E0: the pass's samples go straight to gPermanentData; the ReSTIR frame accumulates after RayGen3
         CKE(mark(SK_ACCUMULATE));
         k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "shade.cuh"
+#include "trace.h"
 
 namespace rtx {
 
@@ -32,15 +33,18 @@ struct RayQueue {
     float4* o_tmin; float4* d_tmax; uint32_t* pid; uint32_t* count;   // count lives on the device
 };
 
+#define WAVE_MAX_PARTS 4
 struct WaveBuffers {
     uint32_t n_paths = 0;
+    int parts = 2;                     // path ranges of a pass that run concurrently on separate streams (wave_render_pass)
+    cudaStream_t aux[WAVE_MAX_PARTS - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[WAVE_MAX_PARTS - 1] = {};
     float4* state = nullptr;           // NSTATE * n_paths
     RayQueue q[2];                     // closest-hit ray queues (ping-pong)
     RayQueue sq[2];                    // shadow queues: [0] DI visibility, [1] GI reservoir winner
     float4* hit_a = nullptr; uint32_t* hit_inst = nullptr;    // hit records of the queue just traced
     float* vis_di = nullptr; float* vis_gi = nullptr;         // per path, 1 = visible
     uint32_t* counts = nullptr;        // 4 queue counters + scratch
-    unsigned int* cursor = nullptr;
+    unsigned int* cursor = nullptr;    // 4 words per part (launch_trace)
     unsigned long long* ray_counters = nullptr;   // [0] closest, [1] shadow, [2] paths
     float4* accum = nullptr;           // gPermanentData
     uint8_t* output = nullptr;         // gOutput slice 0

@@ -281,6 +281,24 @@ def test_material_sorted_queues_do_not_change_the_image(rtdx, orc):
     ctx.close()
 
 
+def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
+    """RTX_OPT_PASS_PARTS: a pass of >= 65536 paths is cut into path ranges that run on separate CUDA streams; ray counts and the
+    accumulated radiance stay bit-identical to the oracle for 1..4 parts (paths never interact before the accumulation)."""
+    sc = rtdx.scenes.mesh_room(n=16)
+    W, H, bounces = 384, 192, 3                                                            # 73 728 paths
+    ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
+    osc = orc.OracleScene(sc, up["props"], up["lights"])
+    ref, octr = osc.render(up["camera"], W, H, 0, 1, bounces=bounces, flags=0)
+    for parts in (1, 2, 3, 4):
+        ctx.set_option(rtdx.OPT_PASS_PARTS, parts)
+        ctx.reset_accum(); ctx.reset_counters()
+        ctx.render_pass(0, 1); ctx.synchronize()
+        cnt = ctx.counters()
+        assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (parts, cnt, octr)
+        assert (bits(ctx.read_accum()) != bits(ref)).sum() == 0, parts
+    ctx.close()
+
+
 def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
     (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""
@@ -434,6 +452,13 @@ def test_full_size_properties_c2(rtdx):
     ctx.reset_accum(); ctx.render_pass(1, 1); ctx.synchronize()
     a1 = ctx.read_accum()
     assert np.array_equal((a0 + a1).view(np.uint32), a01.view(np.uint32))                  # accumulation is a plain running sum
+    for parts in (1, 3, 4):                                                                 # concurrent path ranges (default 2)
+        ctx.set_option(rtdx.OPT_PASS_PARTS, parts)
+        ctx.reset_accum(); ctx.reset_counters(); ctx.render_pass(0, 1); ctx.synchronize()
+        assert np.array_equal(ctx.read_accum().view(np.uint32), a0.view(np.uint32)), parts
+        c = ctx.counters()
+        assert all(c[k] == c0[k] for k in ("paths", "closest_rays", "shadow_rays")), (parts, c, c0)
+    ctx.set_option(rtdx.OPT_PASS_PARTS, 2)
     rays = rtdx.scenes.camera_rays(up["camera"], W, H, step=4)
     ch, ah = ctx.trace(rays), ctx.trace(rays, any_hit=True)
     assert np.array_equal(ch["inst"] != rtdx.MISS, ah["inst"] != rtdx.MISS)
