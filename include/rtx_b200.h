@@ -50,6 +50,9 @@ typedef struct { float t, u, v; uint32_t prim; uint32_t inst; } rtx_hit;      /*
 #define RTX_FLAG_JITTER          1u  /* 2 RandomFloat draws before anything else (legacy include/RayGen.hlsl:84-85) */
 #define RTX_FLAG_LAMBERT_ONLY    2u  /* strategy probabilities forced to (1,0) (BASELINE config C1) */
 #define RTX_FLAG_SORT_MATERIAL   4u  /* bin shading queues by material id */
+#define RTX_FLAG_LEGACY_RR       16u /* rtx_render_pass runs the reference's legacy estimator (include/RayGen.hlsl:60-137 + include/Hit.hlsl:
+                                       * RIS-10 NEE with one shadow ray per bounce, MIS on emitter hits, Russian roulette after depth 3);
+                                       * cfg.bounces (<= 60) caps the number of closest-hit rays per path */
 #define RTX_FLAG_RESTIR          8u  /* allocate the reservoir / sample buffers u2..u7 (rdn/Renderer.cpp:1331-1577) for rtx_render_frame */
 
 /* Compile-time #defines of shaders/Common_v7.hlsl:1-28 that BASELINE configs vary, as runtime fields. */

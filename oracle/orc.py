@@ -9,7 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liborc.so")
 
-FLAG_JITTER, FLAG_LAMBERT_ONLY = 1, 2
+FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_LEGACY_RR = 1, 2, 16
 
 
 class OrcConfig(C.Structure):

@@ -956,6 +956,277 @@ inline f3 RenderSample(const Ctx& c, const orc_camera& cam, uint32_t x, uint32_t
     return Cc;
 }
 
+// ============================================================================================ legacy estimator
+// The reference's older single-pass path tracer: include/RayGen.hlsl:60-137 (path loop with Russian roulette after depth 3),
+// include/Hit.hlsl:58-357 (everything in ClosestHit: MIS-weighted emitter hits, RIS over RIS_M = 10 light candidates with ONE
+// shadow ray per bounce, BSDF sample), include/Miss.hlsl, include/BRDF.hlsl, include/GGX.hlsl, include/Lambertian.hlsl,
+// include/Common.hlsl (PI 3.1415, s_bias 1e-5, EPSILON 1e-4).  Full fp32 materials (no MaterialOptimized), face-forwarded normals,
+// primary direction NOT normalised (RayGen.hlsl:89).  It runs on the v7 buffers (S4 materials with LUT[16], S7 lights, S6 instance
+// properties hold the same quantities as the legacy structs).  Deviations, applied to oracle and GPU alike: D2 (seed from the sample
+// index), D13: the path loop is capped at cfg.bounces closest-hit rays instead of 10 000 000.
+namespace legacy {
+const float L_EPS = 0.0001f, L_BIAS = 0.00001f;
+
+struct Payload {
+    f3 color; f3 emission; f3 direction; f3 origin; float util_x, util_y; uint32_t seed[2]; float pdf; f3 hitNormal;
+};
+inline f3 Kd3(const orc_material& m) { return mk3(m.Kd[0], m.Kd[1], m.Kd[2]); }
+inline f3 Ks3(const orc_material& m) { return mk3(m.Ks[0], m.Ks[1], m.Ks[2]); }
+inline f3 Ke3(const orc_material& m) { return mk3(m.Ke[0], m.Ke[1], m.Ke[2]); }
+inline f3 abs3(f3 v) { return mk3(fabsf(v.x), fabsf(v.y), fabsf(v.z)); }
+
+// include/GGX.hlsl:4-27
+inline float ESS_LUT(const orc_material& mat, float NdotV) {
+    NdotV = saturate1(NdotV);
+    float thetaIdxF = NdotV * 15.0f;
+    int i0 = (int)floorf(thetaIdxF);
+    int i1 = std::min(i0 + 1, 15);
+    float w = thetaIdxF - (float)i0;
+    return lerp1(mat.LUT[i0], mat.LUT[i1], w);
+}
+// :37-46 (denominator clamped, unlike v7)
+inline float D_GGX(float NdotH, float roughness) {
+    float alpha = roughness * roughness;
+    float alpha2 = alpha * alpha;
+    float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (alpha2 - 1.0f) + 1.0f);
+    denom = fmaxf(denom, 1e-7f);
+    return alpha2 / ((PI_REF * denom) * denom);
+}
+// :87-142: Heitz VNDF, invalid samples (below the surface) become the zero vector
+inline f3 SampleBRDF_GGX(const orc_material& mat, f3 outgoing, f3 normal, uint32_t seed[2]) {
+    float alpha = mat.Pr_Pm_Ps_Pc[0] * mat.Pr_Pm_Ps_Pc[0];
+    f3 N = normalize3(normal), V = normalize3(outgoing);
+    float e0 = RandomFloat(seed), e1 = RandomFloat(seed);
+    f3 T1, T2;
+    CoordinateSystem(N, T1, T2);
+    f3 Vh = normalize3(mk3(dot3(T1, V), dot3(T2, V), dot3(N, V)));
+    if (Vh.z < 0.0f) Vh = -Vh;
+    f3 Vs = normalize3(mk3(alpha * Vh.x, alpha * Vh.y, Vh.z));
+    float lensq = Vs.x * Vs.x + Vs.y * Vs.y;
+    f3 T1h, T2h;
+    if (lensq > 0.0f) { T1h = mk3(-Vs.y, Vs.x, 0.0f) / sqrtf(lensq); T2h = cross3(Vs, T1h); }
+    else { T1h = mk3(1, 0, 0); T2h = mk3(0, 1, 0); }
+    float r = sqrtf(e0);
+    float phi = (2.0f * PI_REF) * e1;
+    float sn, cs; d_sincos(phi, &sn, &cs);
+    float x = r * cs, y = r * sn;
+    f3 Nhs = (x * T1h + y * T2h) + sqrtf(fmaxf(0.0f, (1.0f - x * x) - y * y)) * Vs;
+    f3 Nh = normalize3(mk3(alpha * Nhs.x, alpha * Nhs.y, Nhs.z));
+    f3 H = (Nh.x * T1 + Nh.y * T2) + Nh.z * N;
+    f3 sample = reflect3(-V, H);
+    if (dot3(sample, N) <= 0.0f) sample = mk3(0, 0, 0);
+    return sample;
+}
+// :145-176
+inline f3 EvaluateBRDF_GGX(const orc_material& mat, f3 normal, f3 incoming, f3 outgoing) {
+    f3 N = normalize3(normal), V = normalize3(outgoing), L = normalize3(-incoming);
+    f3 H = normalize3(V + L);
+    float NdotV = saturate1(dot3(N, V)), NdotL = saturate1(dot3(N, L)), NdotH = saturate1(dot3(N, H)), VdotH = saturate1(dot3(V, H));
+    f3 F = SchlickFresnel(Ks3(mat), VdotH);
+    float D = D_GGX(NdotH, mat.Pr_Pm_Ps_Pc[0]);
+    float G = G2_SmithGGX(NdotV, NdotL, mat.Pr_Pm_Ps_Pc[0] * mat.Pr_Pm_Ps_Pc[0]);
+    float denominator = (4.0f * NdotV) * NdotL;
+    denominator = fmaxf(denominator, 1e-7f);
+    f3 specular = ((F * D) * G) / denominator;
+    float Ess = ESS_LUT(mat, NdotV);
+    float kms = (1.0f - Ess) / Ess;
+    f3 ks = Ks3(mat);
+    return specular * mk3(1.0f + ks.x * kms, 1.0f + ks.y * kms, 1.0f + ks.z * kms);
+}
+// :179-197
+inline float BRDF_PDF_GGX(const orc_material& mat, f3 normal, f3 incoming, f3 outgoing) {
+    f3 N = normalize3(normal), V = normalize3(outgoing), L = normalize3(-incoming);
+    f3 H = normalize3(V + L);
+    float NdotH = saturate1(dot3(N, H)), NdotV = saturate1(dot3(N, V));
+    float alpha = mat.Pr_Pm_Ps_Pc[0] * mat.Pr_Pm_Ps_Pc[0];
+    float G1 = G1_SmithGGX(NdotV, alpha);
+    float D = D_GGX(NdotH, mat.Pr_Pm_Ps_Pc[0]);
+    return (G1 * D) / (NdotV * 4.0f);
+}
+// include/BRDF.hlsl:10-53: strategy 1 (GGX) iff r <= p_s; clearcoat and dissolve enter the probabilities
+inline uint32_t SelectSamplingStrategy(const Ctx& c, const orc_material& mat, f3 outgoing, f3 normal, uint32_t seed[2]) {
+    float r = RandomFloat(seed);
+    float metallic = mat.Pr_Pm_Ps_Pc[1], clearcoat = mat.Pr_Pm_Ps_Pc[3];
+    float cosTheta = dot3(normal, outgoing);
+    f3 fresnel = SchlickFresnel(Ks3(mat), cosTheta);
+    float p_s = fminf(1.0f, (((fresnel.x + fresnel.y) + fresnel.z) / 3.0f + clearcoat) + metallic);
+    if (c.cfg.flags & ORC_FLAG_LAMBERT_ONLY) return 0u;
+    return r <= p_s ? 1u : 0u;
+}
+// BRDF.hlsl:72-106; include/Lambertian.hlsl:54-66 (pdf floor 1e-4)
+inline f3 EvaluateBRDF(uint32_t strategy, const orc_material& mat, f3 normal, f3 incidence, f3 outgoing) {
+    return strategy == 0u ? Kd3(mat) / PI_REF : EvaluateBRDF_GGX(mat, normal, incidence, outgoing);
+}
+inline float BRDF_PDF(uint32_t strategy, const orc_material& mat, f3 normal, f3 incidence, f3 outgoing) {
+    return strategy == 0u ? fmaxf(dot3(normal, -incidence), 0.0001f) / PI_REF : BRDF_PDF_GGX(mat, normal, incidence, outgoing);
+}
+
+// include/Hit.hlsl:58-357
+inline void ClosestHit(const Ctx& c, Payload& payload, f3 ro, f3 rd, const Hit& h) {
+    const orc_scene& S = *c.S;
+    const Instance& inst = S.instances[h.inst];
+    const Model& M = S.models[inst.model];
+    uint32_t vertId = 3 * h.prim;
+    uint32_t mslot = vertId + M.mat_offset;
+    uint32_t materialID = mslot < S.material_ids.size() ? S.material_ids[mslot] : 0u;
+    const orc_material mat = fetch_material(S, materialID);
+    float bary[3] = {(1.0f - h.b1) - h.b2, h.b1, h.b2};
+    uint32_t i0 = M.idx[vertId], i1 = M.idx[vertId + 1], i2 = M.idx[vertId + 2];
+    f3 e1 = M.pos[i1] - M.pos[i0], e2 = M.pos[i2] - M.pos[i0];
+    f3 flatNormal = normalize3(cross3(e1, e2));
+    f3 smooth = mk3(0, 0, 0);
+    const uint32_t vi[3] = {i0, i1, i2};
+    for (int i = 0; i < 3; i++) {
+        f3 n = M.nrm[vi[i]];
+        if (n.x != 0.0f && n.y != 0.0f && n.z != 0.0f) smooth = smooth + n * bary[i];
+        else smooth = smooth + flatNormal * bary[i];
+    }
+    f3 normal;
+    if (length3(smooth) > 0.0001f) normal = normalize3(smooth); else normal = flatNormal;
+    f4 wn = mul44(inst.p.objectToWorldNormal, normal.x, normal.y, normal.z, 0.0f);
+    normal = normalize3(mk3(wn.x, wn.y, wn.z));
+    f4 wf = mul44(inst.p.objectToWorldNormal, flatNormal.x, flatNormal.y, flatNormal.z, 0.0f);
+    flatNormal = normalize3(mk3(wf.x, wf.y, wf.z));
+    if (dot3(normal, -payload.direction) < 0.0f) normal = -normal;                 // :108-111 face-forwarding
+    if (dot3(flatNormal, -payload.direction) < 0.0f) flatNormal = -flatNormal;
+    f3 worldOrigin = ro + h.t * rd;
+    f3 direct = mk3(0, 0, 0), emissive = mk3(0, 0, 0);
+    float pdf_sample = 1.0f;
+    f3 brdf_sample = mk3(0, 0, 0);
+    f3 origin = payload.origin;
+    f3 incoming = -payload.direction;
+    const f3 Ke = Ke3(mat);
+    if (length3(Ke) > 0.0f) {                                                       // :127-171 emitter hit
+        if (payload.util_y == 0.0f) { emissive = Ke; payload.util_x = 1.0f; }
+        else {
+            f3 L = worldOrigin - origin;
+            float dist2 = fmaxf(dot3(L, L), L_EPS);
+            float dist = fmaxf(sqrtf(dist2), L_EPS);
+            f3 Ln = L / dist;
+            float cos_e = fmaxf(L_EPS, dot3(normal, -Ln));
+            const float* MM = inst.p.objectToWorld;
+            f4 a = mul44(MM, M.pos[i0].x, M.pos[i0].y, M.pos[i0].z, 1.0f);
+            f4 b = mul44(MM, M.pos[i1].x, M.pos[i1].y, M.pos[i1].z, 1.0f);
+            f4 cc = mul44(MM, M.pos[i2].x, M.pos[i2].y, M.pos[i2].z, 1.0f);
+            f3 x_v = mk3(a.x, a.y, a.z), y_v = mk3(b.x, b.y, b.z), z_v = mk3(cc.x, cc.y, cc.z);
+            f3 cross_l = cross3(y_v - x_v, z_v - x_v);
+            float area_l = fabsf(length3(cross_l) * 0.5f);
+            float s_weight = area_l * (((Ke.x + Ke.y) + Ke.z) / 3.0f);
+            float t_weight = S.lights.empty() ? 0.0f : S.lights[0].total_weight;
+            float weight = s_weight / t_weight;
+            float pdf_l = fmaxf(L_EPS, (weight * dist2) / cos_e);
+            float weight_emissive = payload.pdf / (payload.pdf + pdf_l);
+            emissive = (Ke * payload.color) * weight_emissive;
+            payload.util_x = 1.0f;
+        }
+    } else {                                                                        // :173-331 RIS-10 NEE + BSDF sample
+        f3 outgoing = -payload.direction;
+        uint32_t strategy = SelectSamplingStrategy(c, mat, outgoing, normal, payload.seed);
+        const int RIS_M = 10;
+        float ris_weights[RIS_M], ris_luminance[RIS_M], ris_dist[RIS_M], ris_cos_theta[RIS_M], ris_pdf_brdf_light[RIS_M], ris_cdf[RIS_M], ris_pdf_l[RIS_M];
+        f3 ris_f[RIS_M], ris_LDir[RIS_M];
+        for (int i = 0; i < RIS_M; i++) {
+            float randomValue = RandomFloat(payload.seed);
+            orc_light_tri zl; memset(&zl, 0, sizeof zl);
+            const orc_light_tri& lt = S.lights.empty() ? zl : S.lights[SelectLight(S, randomValue)];
+            const float* MM = S.instances[lt.instanceID].p.objectToWorld;
+            f4 a = mul44(MM, lt.x[0], lt.x[1], lt.x[2], 1.0f);
+            f4 b = mul44(MM, lt.y[0], lt.y[1], lt.y[2], 1.0f);
+            f4 cc = mul44(MM, lt.z[0], lt.z[1], lt.z[2], 1.0f);
+            f3 x_v = mk3(a.x, a.y, a.z), y_v = mk3(b.x, b.y, b.z), z_v = mk3(cc.x, cc.y, cc.z);
+            float xi1 = RandomFloat(payload.seed), xi2 = RandomFloat(payload.seed);
+            if (xi1 + xi2 > 1.0f) { xi1 = 1.0f - xi1; xi2 = 1.0f - xi2; }
+            float u = (1.0f - xi1) - xi2, v = xi1, w = xi2;
+            f3 samplePoint = (u * x_v + v * y_v) + w * z_v;
+            f3 L = samplePoint - (worldOrigin + L_BIAS * flatNormal);
+            float dist2 = fmaxf(dot3(L, L), L_EPS);
+            float dist = fmaxf(sqrtf(dist2), L_EPS);
+            f3 L_norm = L / dist;
+            f3 cross_l = cross3(y_v - x_v, z_v - x_v);
+            f3 normal_l = normalize3(cross_l);
+            float area_l = fabsf(length3(cross_l) * 0.5f);
+            float cos_theta_x = fmaxf(L_EPS, dot3(normal, L_norm));
+            float cos_theta_y = fmaxf(L_EPS, dot3(normal_l, -L_norm));
+            float G = fmaxf((cos_theta_x * cos_theta_y) / dist2, L_EPS);
+            float pdf_l = lt.weight / fmaxf(area_l, L_EPS);
+            f3 emission_l = mk3(lt.emission[0], lt.emission[1], lt.emission[2]);
+            f3 brdf_light = EvaluateBRDF(strategy, mat, normal, -L_norm, -payload.direction);
+            float pdf_brdf_light = fmaxf(BRDF_PDF(strategy, mat, normal, -L_norm, -payload.direction), L_EPS);
+            ris_f[i] = (emission_l * brdf_light) * G;
+            float lum = ((emission_l.x + emission_l.y) + emission_l.z) / 3.0f;
+            ris_luminance[i] = (lum * brdf_light.x) * G;                            // float3 -> float keeps .x (:268)
+            ris_weights[i] = (1.0f / 10.0f) * (((lum * brdf_light.x) * G) / pdf_l);
+            ris_LDir[i] = L_norm; ris_dist[i] = dist; ris_cos_theta[i] = cos_theta_y;
+            ris_pdf_brdf_light[i] = pdf_brdf_light; ris_pdf_l[i] = pdf_l;
+        }
+        ris_cdf[0] = ris_weights[0];
+        for (int i = 1; i < RIS_M; i++) ris_cdf[i] = ris_cdf[i - 1] + ris_weights[i];
+        float ris_total_weight = ris_cdf[RIS_M - 1];
+        float threshold = RandomFloat(payload.seed) * ris_total_weight;
+        int sel = 0;
+        for (int i = 0; i < RIS_M; i++) if (threshold < ris_cdf[i]) { sel = i; break; }
+        float WX = fmaxf(L_EPS, (1.0f / fmaxf(L_EPS, ris_luminance[sel])) * ris_total_weight);
+        bool hit = TraceShadow(c, worldOrigin + L_BIAS * flatNormal, ris_LDir[sel], L_BIAS, fabsf(ris_dist[sel]) - L_BIAS);
+        float visible = hit ? 0.0f : 1.0f;
+        direct = (ris_f[sel] * visible) * WX;
+        float pdf_l_sa = fmaxf(L_EPS, ((ris_pdf_l[sel] * ris_dist[sel]) * ris_dist[sel]) / ris_cos_theta[sel]);
+        float weight_light = pdf_l_sa / (pdf_l_sa + ris_pdf_brdf_light[sel]);
+        direct = direct * (payload.color * weight_light);
+        f3 sample = strategy == 0u ? RandomUnitVectorInHemisphere(normal, payload.seed) : SampleBRDF_GGX(mat, outgoing, normal, payload.seed);
+        payload.direction = sample;
+        payload.origin = worldOrigin + L_BIAS * flatNormal;
+        incoming = -payload.direction;
+        if (length3(payload.direction) < 0.01f) payload.util_x = 1.1f;              // :320-323 invalid sample ends the path
+        else {
+            pdf_sample = fmaxf(BRDF_PDF(strategy, mat, normal, incoming, outgoing), 0.0001f);
+            brdf_sample = EvaluateBRDF(strategy, mat, normal, incoming, outgoing);
+        }
+    }
+    payload.emission = payload.emission + (abs3(direct) + abs3(emissive));          // :337
+    payload.color = ((payload.color * brdf_sample) * dot3(normal, -incoming)) / pdf_sample;   // :342
+    payload.pdf = pdf_sample;
+    payload.hitNormal = normal;
+}
+
+// include/RayGen.hlsl:60-137 for one sample
+inline f3 RenderSample(const Ctx& c, const orc_camera& cam, uint32_t x, uint32_t y, uint32_t sample) {
+    Payload p;
+    init_seed(x, y, 2u, sample, p.seed);                                            // uint(samples + 1) = 2; D2
+    float jx = RandomFloat(p.seed), jy = RandomFloat(p.seed);
+    float dimx = (float)c.cfg.width, dimy = (float)c.cfg.height;
+    f4 o4 = mul44(cam.viewI, 0.0f, 0.0f, 0.0f, 1.0f);
+    float dx = (((float)x + jx) / dimx) * 2.0f - 1.0f;
+    float dy = (((float)y + jy) / dimy) * 2.0f - 1.0f;
+    f4 target = mul44(cam.projectionI, dx, -dy, 1.0f, 1.0f);
+    f4 d4 = mul44(cam.viewI, target.x, target.y, target.z, 0.0f);
+    p.color = mk3(1, 1, 1); p.emission = mk3(0, 0, 0);
+    p.origin = mk3(o4.x, o4.y, o4.z); p.direction = mk3(d4.x, d4.y, d4.z);          // not normalised (:89)
+    p.pdf = 1.0f; p.hitNormal = mk3(0, 0, 0);
+    c.C->paths++;
+    for (uint32_t yb = 0; yb < c.cfg.bounces; yb++) {                               // D13
+        p.util_x = 0.0f; p.util_y = (float)yb;
+        c.C->closest_rays++;
+        Hit h;
+        const f3 ro = p.origin, rd = p.direction;
+        if (trace(*c.S, ro, rd, 0.0001f, 10000.0f, false, c.mode, h, *c.C)) ClosestHit(c, p, ro, rd, h);
+        else {                                                                       // include/Miss.hlsl:9-11
+            p.emission = p.emission + mk3(0.0f, 0.0f, 0.0f) * p.color;
+            p.util_x = 1.0f;
+        }
+        if (p.util_x >= 1.0f) break;
+        if (yb > 3u) {                                                              // :118-130 Russian roulette
+            float max_throughput = fmaxf(p.color.x, fmaxf(p.color.y, p.color.z));
+            float q = fminf(fmaxf(max_throughput, 0.05f), 1.0f);
+            float random = RandomFloat(p.seed);
+            if (random > q) break;
+            p.color = p.color * (1.0f / q);
+        }
+    }
+    return p.emission;
+}
+}  // namespace legacy
+
 // ============================================================================================ ReSTIR reuse
 // Passes 2 and 3 of the reference's frame: shaders/Pass_temp_di_v7.hlsl:46-204 (RayGen2), shaders/Pass_spat_di_v7.hlsl:46-464
 // (RayGen3), shaders/MIS_v7.hlsl, include/MIS_GI_v6.hlsl, shaders/Common_v7.hlsl:203-350, shaders/Sampler_v7.hlsl:738-785.
@@ -1288,7 +1559,8 @@ void orc_render_rows(orc_scene* s, const orc_config* cfg, const orc_camera* cam,
         for (uint32_t x = 0; x < cfg->width; x += step) {
             float* px = accum + 4 * ((size_t)y * cfg->width + x);
             for (uint32_t k = 0; k < n_samples; k++) {
-                f3 C = RenderSample(c, *cam, x, y, first_sample + k, nullptr);
+                f3 C = (cfg->flags & ORC_FLAG_LEGACY_RR) ? legacy::RenderSample(c, *cam, x, y, first_sample + k)
+                                                         : RenderSample(c, *cam, x, y, first_sample + k, nullptr);
                 // Pass_spat_di_v7.hlsl:388-404: drop non-finite samples, sum += C, n += 1
                 if (!any_nan_inf(C)) { px[0] += C.x; px[1] += C.y; px[2] += C.z; px[3] += 1.0f; }
             }

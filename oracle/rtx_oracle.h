@@ -31,6 +31,8 @@ typedef struct { float t, u, v; uint32_t prim; uint32_t inst; } orc_hit;        
 
 #define ORC_FLAG_JITTER        1u   /* 2 RandomFloat draws before anything else (legacy include/RayGen.hlsl:84-85) */
 #define ORC_FLAG_LAMBERT_ONLY  2u   /* strategy probabilities forced to (1,0) */
+#define ORC_FLAG_LEGACY_RR     16u  /* orc_render runs the legacy estimator (include/RayGen.hlsl + include/Hit.hlsl: RIS-10 NEE with one shadow
+                                       ray per bounce, MIS on emitter hits, Russian roulette after depth 3); cfg.bounces caps the path length */
 
 typedef struct {
     uint32_t width, height;

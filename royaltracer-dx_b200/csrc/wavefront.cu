@@ -743,6 +743,12 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     return cudaSuccess;
 }
 
+cudaError_t wave_accumulate(WaveBuffers& B, uint32_t npx, uint32_t spp, cudaStream_t stream) {
+    StateView st{B.state, npx * spp};
+    k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
+    return cudaGetLastError();
+}
+
 cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream, uint64_t* launches) {
     k_resolve<<<(n_pixels + 255) / 256, 256, 0, stream>>>(B.accum, n_pixels, (uchar4*)B.output);
     if (launches) *launches += 1;

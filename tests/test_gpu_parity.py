@@ -281,6 +281,30 @@ def test_material_sorted_queues_do_not_change_the_image(rtdx, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("scene_name", ["cornell", "mesh", "inst"])
+def test_legacy_rr_estimator_bit_exact(rtdx, orc, scene_name):
+    """RTX_FLAG_LEGACY_RR: the reference's older estimator (include/RayGen.hlsl + include/Hit.hlsl: RIS-10 NEE with one
+    shadow ray per bounce, MIS on emitter hits, Russian roulette after depth 3, fp32 materials, face-forwarded normals) as a wavefront;
+    ray counts and accumulated radiance bit-identical to the oracle's restatement, 2 passes of 2 samples."""
+    sc = {"cornell": lambda: rtdx.scenes.cornell(), "mesh": lambda: rtdx.scenes.mesh_room(n=20),
+          "inst": lambda: rtdx.scenes.instanced_blobs(n_models=3, n_side=6, lattice=3, emissive_fraction=0.2)}[scene_name]()
+    W, H, bounces = 96, 64, 12
+    flags = rtdx.FLAG_LEGACY_RR
+    ctx = rtdx.Context(W, H, bounces=bounces, flags=flags, samples_per_pass=2)
+    up = ctx.upload_scene(sc)
+    osc = orc.OracleScene(sc, up["props"], up["lights"])
+    ctx.render_pass(0, 2); ctx.render_pass(2, 2); ctx.synchronize()
+    cnt = ctx.counters()
+    ref, octr = osc.render(up["camera"], W, H, 0, 4, bounces=bounces, flags=flags)
+    assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"] and cnt["paths"] == octr["paths"], (cnt, octr)
+    gpu = ctx.read_accum()
+    assert (bits(gpu) != bits(ref)).sum() == 0
+    assert gpu[..., 3].mean() > 0.9 * 4 and np.isfinite(gpu).all() and gpu[..., :3].sum() > 0       # the estimator produces light
+    if scene_name == "mesh":                                                                        # closed room: paths end by RR / emitter hits,
+        assert 4.5 * W * H * 4 < octr["closest_rays"] < 0.9 * bounces * W * H * 4                   # not by the cap
+    ctx.close()
+
+
 def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
     """RTX_OPT_PASS_PARTS: a pass of >= 65536 paths is cut into path ranges that run on separate CUDA streams; ray counts and the
     accumulated radiance stay bit-identical to the oracle for 1..4 parts (paths never interact before the accumulation)."""

@@ -17,11 +17,12 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--bounces", type=int, default=6)
 ap.add_argument("--passes", type=int, default=8)
+ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sc = rtdx.scenes.mesh_room(n=a.side) if a.scene == "mesh" else rtdx.scenes.instanced_blobs()
-ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, stream=stream.cuda_stream)
+ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags, stream=stream.cuda_stream)
 ctx.upload_scene(sc)
 for p in range(3):
     ctx.render_pass(p, 1)
