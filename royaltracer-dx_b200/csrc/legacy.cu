@@ -6,8 +6,8 @@
 // EPSILON 1e-4).  Full fp32 materials, face-forwarded normals, primary direction not normalised (RayGen.hlsl:89).
 // The megakernel loop is cut at its two TraceRay calls: per bounce  closest trace -> k_legacy_hit -> any-hit trace -> k_legacy_shadow.
 // Every path carries its TEA state and draws in the reference's order; additions to payload.emission happen in bounce order
-// (the NEE term of bounce y is added by k_legacy_shadow before bounce y+1 is shaded), so the result is bit-identical to the CPU oracle
-// (oracle/rtx_oracle.cpp, namespace legacy).  Deviations: D2 (seed from the sample index), D13 (path length capped at cfg.bounces).
+// (the NEE term of bounce y is added by k_legacy_shadow before bounce y+1 is shaded), so the result is bit-identical to a
+// sequential CPU evaluation in the same fp32 operation order (tests/test_gpu_parity.py).  Deviations: D2 (seed from the sample index), D13 (path length capped at cfg.bounces).
 #include "trace.h"
 #include "wave_dev.cuh"
 

@@ -45,6 +45,10 @@ g["restir"] = {"width": W2, "height": H2, "frames": 3, "bounces": 2, "closest_ra
                "accum_bits": [int(v) for v in acc2.view(np.uint32).reshape(-1)],
                "reservoir_crc32": int(zlib.crc32(np.ascontiguousarray(dump).view(np.uint8).tobytes())),
                "M_di_sum": int(dump[..., 11].sum()), "M_gi_sum": int(dump[..., 23].sum())}
+# legacy estimator: Cornell, 24x24, 4 samples, path cap 12, GGX allowed
+acc3, ctr3 = osc.render(cam, W, H, 0, 4, bounces=12, flags=orc.FLAG_LEGACY_RR)
+g["legacy"] = {"size": W, "spp": 4, "bounces": 12, "closest_rays": ctr3["closest_rays"], "shadow_rays": ctr3["shadow_rays"],
+               "accum_bits": [int(v) for v in acc3.view(np.uint32).reshape(-1)]}
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_kat.json"), "w") as f:
     json.dump(g, f)
 print("wrote golden_kat.json", len(json.dumps(g)), "bytes")

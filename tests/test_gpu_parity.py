@@ -406,6 +406,22 @@ def test_cuda_path_matches_committed_golden_fixtures(rtdx):
     ctx.close()
 
 
+def test_legacy_cuda_path_matches_committed_golden(rtdx):
+    """RTX_FLAG_LEGACY_RR against tests/golden/golden_kat.json["legacy"] — no oracle call at run time."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kat.json")) as f:
+        g = json.load(f)["legacy"]
+    W = H = g["size"]
+    ctx, up = _upload(rtdx, rtdx.scenes.cornell(), W, H, bounces=g["bounces"], flags=rtdx.FLAG_LEGACY_RR, samples_per_pass=4)
+    ctx.reset_counters()
+    ctx.render_pass(0, g["spp"]); ctx.synchronize()
+    cnt = ctx.counters()
+    assert cnt["closest_rays"] == g["closest_rays"] and cnt["shadow_rays"] == g["shadow_rays"]
+    assert [int(v) for v in ctx.read_accum().view(np.uint32).reshape(-1)] == g["accum_bits"]
+    ctx.close()
+
+
 def test_restir_cuda_path_matches_committed_golden(rtdx):
     """3 ReSTIR frames on the engine against tests/golden/golden_kat.json["restir"] — no oracle call at run time."""
     import json
