@@ -283,7 +283,10 @@ def main():
     h2d = int(props.nbytes + descs.nbytes + cam.nbytes); d2h = W * H * 4
     ctx.reset_accum()
 
-    out_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()     # the frame's read-back target (pinned host memory)
+    # the frame's read-back targets (pinned host memory): one frame is kept in flight, so the RGBA8 copy of frame k overlaps the
+    # rendering of frame k+1 (rtx_read_output_async / rtx_wait_output); every frame's image is complete on the host before the timed
+    # region ends, and frame k's image is waited for before frame k+1's read-back is queued
+    out_pinned = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
 
     def step_e2e(k):
         ctx.set_instances(descs, props)
@@ -292,15 +295,18 @@ def main():
         if world > 1:
             total.copy_(accum)
             dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)
-        return ctx.read_output(out_pinned)
+        ctx.wait_output()                       # frame k-1's image is on the host (the consumer may use it now)
+        ctx.read_output_async(out_pinned[k & 1])
 
     for k in range(min(args.warmup, 2)):
         step_e2e(k)
+    ctx.wait_output()
     barrier(); ctx.reset_counters()
     e0.record()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(args.warmup + k)
+    ctx.wait_output()
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)

@@ -117,6 +117,12 @@ rtx_status rtx_synchronize(rtx_ctx*);
 /* gPermanentData (u1): float4 per pixel, row-major; gOutput slice 0 (u0): RGBA8 */
 rtx_status rtx_read_accum(rtx_ctx*, float* host_out);
 rtx_status rtx_read_output(rtx_ctx*, uint8_t* rgba8_out);
+/* the same without stalling the caller (the reference blocks on its fence every frame, rdn/Renderer.cpp:717-735; a host that keeps
+ * one frame in flight overlaps the read-back of frame k with the rendering of frame k+1): resolve + D2H copy are enqueued and the
+ * call returns; rtx_wait_output blocks until the image of the last rtx_read_output_async is complete in rgba8_out (pinned memory
+ * for a truly asynchronous copy).  rgba8_out must stay valid until then. */
+rtx_status rtx_read_output_async(rtx_ctx*, uint8_t* rgba8_out);
+rtx_status rtx_wait_output(rtx_ctx*);
 /* device pointer of gPermanentData, for the per-pass NCCL reduce over NVLink */
 rtx_status rtx_accum_device_ptr(rtx_ctx*, void** out);
 /* raw TraceRay (T3 closest / T4 any-hit): host buffers, or device buffers with _device */

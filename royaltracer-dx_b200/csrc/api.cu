@@ -33,6 +33,15 @@ struct rtx_ctx {
     rtx_instance_desc* d_descs = nullptr; rtx_instance_props* d_props = nullptr; uint32_t n_instances = 0;
     uint32_t* d_inst_model = nullptr;
     float4* d_inst_recs = nullptr;
+    // per-frame instance update (rdn/Renderer.cpp:594: the TLAS is refitted every frame): buffers are kept between calls and the host
+    // arrays go through a ring of two pinned staging blocks, so that rtx_set_instances neither allocates nor synchronises
+    size_t cap_descs = 0, cap_props = 0, cap_inst_model = 0, cap_recs = 0, cap_lo = 0, cap_hi = 0, cap_box6 = 0, cap_tlas_prims = 0;
+    unsigned int* d_box6 = nullptr;
+    float4 *d_box_lo = nullptr, *d_box_hi = nullptr;
+    void* d_tlas_ctr = nullptr;
+    struct Stage { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool pending = false; } stage[2];
+    int stage_i = 0;
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr; bool copy_pending = false;
     Bvh8 tlas;
     BlasRef* d_blas = nullptr; BlasBounds* d_bounds = nullptr; ModelRef* d_model_refs = nullptr; uint32_t n_tables = 0;
     rtx_light_triangle* d_lights = nullptr; uint32_t n_lights = 0;
@@ -93,6 +102,11 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     for (void* p : ptrs) if (p) cudaFree(p);
     free_bvh(&c->tlas);
     free_tables(c);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_resolved) cudaEventDestroy(c->ev_resolved);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    for (auto& sg : c->stage) { if (sg.p) cudaFreeHost(sg.p); if (sg.ev) cudaEventDestroy(sg.ev); }
+    { void* q[] = {c->d_box_lo, c->d_box_hi, c->d_tlas_ctr, c->d_box6}; for (void* p : q) if (p) cudaFree(p); }
     if (c->wb_ready) wave_free(&c->wb);
     if (c->rs_ready) restir_free(&c->rs);
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
@@ -171,31 +185,67 @@ static rtx_status ensure_tables(rtx_ctx* c) {
     return RTX_OK;
 }
 
+// device buffer of at least n elements; reallocated (cudaFree synchronises) only when it has to grow
+template <typename T>
+static rtx_status reserve(T** dptr, size_t* cap, size_t n) {
+    if (*dptr && *cap >= n) return RTX_OK;
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    RTX_CK(cudaMalloc((void**)dptr, (n ? n : 1) * sizeof(T)));
+    *cap = n ? n : 1;
+    return RTX_OK;
+}
+
 extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* descs, const rtx_instance_props* props, uint32_t n) {
     if (!c || ((!descs || !props) && n)) return fail(RTX_ERR_ARG, "rtx_set_instances: null argument");
     RTX_CK(cudaSetDevice(c->cfg.device));
-    std::vector<uint32_t> inst_model(n);
     for (uint32_t i = 0; i < n; i++) {
         if (descs[i].blas >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_set_instances: instance references an unknown model");
         if (c->models[descs[i].blas].n_tris == 0) return fail(RTX_ERR_ARG, "rtx_set_instances: instance of an empty model");
-        inst_model[i] = (uint32_t)descs[i].blas;
     }
     rtx_status st;
     if ((st = ensure_tables(c)) != RTX_OK) return st;
-    if ((st = upload(&c->d_descs, descs, n, c->stream)) != RTX_OK) return st;
-    if ((st = upload(&c->d_props, props, n, c->stream)) != RTX_OK) return st;
-    if ((st = upload(&c->d_inst_model, inst_model.data(), n, c->stream)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_descs, &c->cap_descs, n)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_props, &c->cap_props, n)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_inst_model, &c->cap_inst_model, n)) != RTX_OK) return st;
+    // the caller's arrays are copied into a pinned staging block (the library copies on upload, S-rows ownership); the block is reused
+    // two calls later, after the event recorded behind its H2D copies
+    rtx_ctx::Stage& sg = c->stage[c->stage_i]; c->stage_i ^= 1;
+    if (!sg.ev) RTX_CK(cudaEventCreateWithFlags(&sg.ev, cudaEventDisableTiming));
+    if (sg.pending) { RTX_CK(cudaEventSynchronize(sg.ev)); sg.pending = false; }
+    const size_t b_descs = (size_t)n * sizeof(rtx_instance_desc), b_props = (size_t)n * sizeof(rtx_instance_props), b_im = (size_t)n * 4;
+    if (sg.cap < b_descs + b_props + b_im) {
+        if (sg.p) cudaFreeHost(sg.p);
+        sg.cap = b_descs + b_props + b_im + 4096;
+        RTX_CK(cudaMallocHost(&sg.p, sg.cap));
+    }
+    if (n) {
+        uint8_t* h = (uint8_t*)sg.p;
+        memcpy(h, descs, b_descs); memcpy(h + b_descs, props, b_props);
+        uint32_t* im = (uint32_t*)(h + b_descs + b_props);
+        for (uint32_t i = 0; i < n; i++) im[i] = (uint32_t)descs[i].blas;
+        RTX_CK(cudaMemcpyAsync(c->d_descs, h, b_descs, cudaMemcpyHostToDevice, c->stream));
+        RTX_CK(cudaMemcpyAsync(c->d_props, h + b_descs, b_props, cudaMemcpyHostToDevice, c->stream));
+        RTX_CK(cudaMemcpyAsync(c->d_inst_model, im, b_im, cudaMemcpyHostToDevice, c->stream));
+        RTX_CK(cudaEventRecord(sg.ev, c->stream)); sg.pending = true;
+    }
     c->n_instances = n;
-    if (c->d_inst_recs) { cudaFree(c->d_inst_recs); c->d_inst_recs = nullptr; }
-    free_bvh(&c->tlas);
-    float4 *d_lo = nullptr, *d_hi = nullptr;
-    RTX_CK(cudaMalloc((void**)&c->d_inst_recs, (size_t)(n ? n : 1) * 64));
-    RTX_CK(cudaMalloc((void**)&d_lo, (size_t)(n ? n : 1) * 16));
-    RTX_CK(cudaMalloc((void**)&d_hi, (size_t)(n ? n : 1) * 16));
-    cudaError_t e = launch_instance_records(c->d_descs, c->d_props, c->d_bounds, n, c->d_inst_recs, d_lo, d_hi, c->stream);
-    if (e == cudaSuccess && n) e = build_tlas(c->d_inst_recs, d_lo, d_hi, n, &c->tlas, c->stream);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_lo); cudaFree(d_hi);
+    if ((st = reserve(&c->d_inst_recs, &c->cap_recs, (size_t)n * 4)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_box_lo, &c->cap_lo, n)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_box_hi, &c->cap_hi, n)) != RTX_OK) return st;
+    if ((st = reserve(&c->d_box6, &c->cap_box6, (size_t)n * 6)) != RTX_OK) return st;
+    cudaError_t e = launch_instance_records(c->d_descs, c->d_props, c->d_bounds, n, c->d_inst_recs, c->d_box_lo, c->d_box_hi, c->d_box6, c->stream);
+    if (e == cudaSuccess && n) {
+        if (!c->d_tlas_ctr) RTX_CK(cudaMalloc(&c->d_tlas_ctr, 256));
+        if (tlas_fits_one_node(n) && c->tlas.nodes && c->cap_tlas_prims >= n) {
+            // a TLAS of one node is rewritten in place: no allocation, no host synchronisation (the per-frame path of BASELINE config C2)
+            e = update_tlas_one_node(c->d_inst_recs, c->d_box_lo, c->d_box_hi, n, &c->tlas, c->d_tlas_ctr, c->stream);
+        } else {
+            RTX_CK(cudaStreamSynchronize(c->stream));
+            free_bvh(&c->tlas);
+            e = build_tlas(c->d_inst_recs, c->d_box_lo, c->d_box_hi, n, &c->tlas, c->stream);
+            c->cap_tlas_prims = e == cudaSuccess ? c->tlas.n_prims : 0;
+        }
+    }
     c->launches += 6;
     RTX_CK(e);
     return RTX_OK;
@@ -235,8 +285,7 @@ extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
     c->cam = *cam; c->have_cam = true;
     RTX_CK(cudaMemcpyAsync(c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, c->stream));
     if (different) RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
-    RTX_CK(cudaStreamSynchronize(c->stream));
-    return RTX_OK;
+    return RTX_OK;      // the 512-B copy from pageable memory is staged by the driver before the call returns
 }
 
 static SceneAS make_as(rtx_ctx* c) {
@@ -368,9 +417,40 @@ extern "C" rtx_status rtx_read_output(rtx_ctx* c, uint8_t* rgba8_out) {
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     const uint32_t npx = c->cfg.width * c->cfg.height;
+    if (c->copy_pending) { RTX_CK(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
     RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
     RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->stream));
     RTX_CK(cudaStreamSynchronize(c->stream));
+    return RTX_OK;
+}
+
+// Resolve + read-back without stalling the caller: the D2H copy runs on a copy stream behind the resolve kernel, the next frame's
+// kernels overlap it.  rtx_wait_output blocks until the image of the LAST rtx_read_output_async call is in rgba8_out.
+extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
+    if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output_async: null argument");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    if (!c->copy_stream) {
+        RTX_CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        RTX_CK(cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming));
+        RTX_CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+    }
+    const uint32_t npx = c->cfg.width * c->cfg.height;
+    if (c->copy_pending) RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));      // gOutput is rewritten by the resolve below
+    RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
+    RTX_CK(cudaEventRecord(c->ev_resolved, c->stream));
+    RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+    RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    RTX_CK(cudaEventRecord(c->ev_copied, c->copy_stream));
+    c->copy_pending = true;
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_wait_output(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    if (c->copy_pending) RTX_CK(cudaEventSynchronize(c->ev_copied));
     return RTX_OK;
 }
 

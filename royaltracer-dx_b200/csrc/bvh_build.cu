@@ -571,6 +571,21 @@ cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
     return build_generic<4, RecSource>(d_box_lo, d_box_hi, n_instances, src, (BuildCounters*)ctr.p, out, stream);
 }
 
+bool tlas_fits_one_node(uint32_t n_instances) { return n_instances >= 1u && n_instances <= (uint32_t)MAX_LEAF; }
+
+cudaError_t update_tlas_one_node(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* out,
+                                 void* d_ctr, cudaStream_t stream) {
+    if (!tlas_fits_one_node(n_instances) || !out->nodes || !out->prims) return cudaErrorInvalidValue;
+    static_assert(sizeof(BuildCounters) <= 256, "update_tlas_one_node: scratch too small");
+    BuildCounters* ctr = (BuildCounters*)d_ctr;
+    k_init_counters<<<1, 1, 0, stream>>>(ctr);
+    k_box_bounds<<<(n_instances + 255) / 256, 256, 0, stream>>>(d_box_lo, d_box_hi, n_instances, ctr);
+    RecSource src{d_inst_recs};
+    k_single_node<4, RecSource><<<1, 32, 0, stream>>>(src, d_box_lo, d_box_hi, (int)n_instances, out->nodes, out->prims, ctr);
+    out->n_nodes = 1; out->n_prims = n_instances;
+    return cudaGetLastError();
+}
+
 void free_bvh(Bvh8* b) {
     if (b->nodes) cudaFree(b->nodes);
     if (b->prims) cudaFree(b->prims);
@@ -609,18 +624,25 @@ __global__ void k_instance_records(const rtx_instance_desc* __restrict__ descs, 
 
 // Tight world boxes: the extent of the instance's TRANSFORMED VERTICES instead of the 8 corners of its object-space box.
 // For a rotated instance the corner box is up to sqrt(3) larger per axis than the geometry; C3 (1000 rotated instances)
-// entered 4.4 instances per ray with corner boxes.  One CTA per instance; every vertex of the model's buffer is taken
-// (a superset of the referenced ones, so the box stays conservative); same 2^-15 padding as before.
+// entered 4.4 instances per ray with corner boxes.  TIGHT_CHUNKS CTAs per instance share its vertices (the per-frame TLAS update of
+// the 0.5 M-vertex C2 mesh took 1.1 ms with one CTA per instance) and fold their partial extents with order-preserving atomics;
+// every vertex of the model's buffer is taken (a superset of the referenced ones, so the box stays conservative); same 2^-15 padding.
+#define TIGHT_CHUNKS 64
+__global__ void k_tight_init(uint32_t n, unsigned int* __restrict__ acc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6u * n) acc[i] = (i % 6u) < 3u ? 0xffffffffu : 0u;
+}
 __global__ void __launch_bounds__(256)
 k_instance_tight_boxes(const rtx_instance_desc* __restrict__ descs, const BlasBounds* __restrict__ bounds, uint32_t n,
-                       float4* __restrict__ lo, float4* __restrict__ hi) {
-    const uint32_t i = blockIdx.x;
+                       unsigned int* __restrict__ acc) {
+    const uint32_t i = blockIdx.y;
     if (i >= n) return;
     const BlasBounds b = bounds[(uint32_t)descs[i].blas];
+    if (blockIdx.x * 256u >= b.n_verts) return;
     float t[3][4];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) t[r][c] = descs[i].transform[r][c];
     float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t v = threadIdx.x; v < b.n_verts; v += blockDim.x) {
+    for (uint32_t v = blockIdx.x * 256u + threadIdx.x; v < b.n_verts; v += gridDim.x * 256u) {
         const float* p = reinterpret_cast<const float*>(b.verts + (size_t)v * 28);
         const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
         for (int r = 0; r < 3; r++) {
@@ -635,24 +657,38 @@ k_instance_tight_boxes(const rtx_instance_desc* __restrict__ descs, const BlasBo
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int r = 0; r < 3; r++) for (int w = 0; w < 8; w++) { l[r] = fminf(l[r], sl[r][w]); h[r] = fmaxf(h[r], sh[r][w]); }
-        float s = 0.0f;
-        for (int r = 0; r < 3; r++) s = fmaxf(s, fmaxf(fabsf(l[r]), fabsf(h[r])));
-        const float pad = s * 3.0517578125e-5f + 1e-30f;
-        // never larger than the corner box already written by k_instance_records
-        const float4 cl = lo[i], ch = hi[i];
-        lo[i] = make_float4(fmaxf(l[0] - pad, cl.x), fmaxf(l[1] - pad, cl.y), fmaxf(l[2] - pad, cl.z), 0.0f);
-        hi[i] = make_float4(fminf(h[0] + pad, ch.x), fminf(h[1] + pad, ch.y), fminf(h[2] + pad, ch.z), 0.0f);
+        for (int r = 0; r < 3; r++) {
+            for (int w = 0; w < 8; w++) { l[r] = fminf(l[r], sl[r][w]); h[r] = fmaxf(h[r], sh[r][w]); }
+            atomicMin(&acc[6 * i + r], enc_f(l[r]));
+            atomicMax(&acc[6 * i + 3 + r], enc_f(h[r]));
+        }
     }
+}
+__global__ void k_tight_finish(uint32_t n, const unsigned int* __restrict__ acc, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float l[3], h[3];
+    for (int r = 0; r < 3; r++) { l[r] = dec_f(acc[6 * i + r]); h[r] = dec_f(acc[6 * i + 3 + r]); }
+    float s = 0.0f;
+    for (int r = 0; r < 3; r++) s = fmaxf(s, fmaxf(fabsf(l[r]), fabsf(h[r])));
+    const float pad = s * 3.0517578125e-5f + 1e-30f;
+    // never larger than the corner box already written by k_instance_records
+    const float4 cl = lo[i], ch = hi[i];
+    lo[i] = make_float4(fmaxf(l[0] - pad, cl.x), fmaxf(l[1] - pad, cl.y), fmaxf(l[2] - pad, cl.z), 0.0f);
+    hi[i] = make_float4(fminf(h[0] + pad, ch.x), fminf(h[1] + pad, ch.y), fminf(h[2] + pad, ch.z), 0.0f);
 }
 
 cudaError_t launch_instance_records(const rtx_instance_desc* d_descs, const rtx_instance_props* d_props, const BlasBounds* d_bounds,
-                                    uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, cudaStream_t stream) {
+                                    uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, unsigned int* d_scratch6, cudaStream_t stream) {
     if (n) {
         k_instance_records<<<(n + 127) / 128, 128, 0, stream>>>(d_descs, d_props, d_bounds, n, d_recs, d_lo, d_hi);
         static int tight = -1;
         if (tight < 0) { const char* e = getenv("RTX_TIGHT_INSTANCE_BOXES"); tight = e ? atoi(e) : 1; }
-        if (tight) k_instance_tight_boxes<<<n, 256, 0, stream>>>(d_descs, d_bounds, n, d_lo, d_hi);
+        if (tight && d_scratch6) {
+            k_tight_init<<<(6 * n + 255) / 256, 256, 0, stream>>>(n, d_scratch6);
+            k_instance_tight_boxes<<<dim3(TIGHT_CHUNKS, n), 256, 0, stream>>>(d_descs, d_bounds, n, d_scratch6);
+            k_tight_finish<<<(n + 255) / 256, 256, 0, stream>>>(n, d_scratch6, d_lo, d_hi);
+        }
     }
     return cudaGetLastError();
 }

@@ -28,10 +28,16 @@ cudaError_t build_blas(const uint8_t* d_vertices, uint32_t n_vertices, const uin
 cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances,
                        Bvh8* out, cudaStream_t stream);
 void free_bvh(Bvh8* b);
+// Per-frame TLAS update when the whole TLAS is one node (n_instances <= the leaf size): rewrites out->nodes / out->prims in place,
+// stream-ordered, no allocation, no host synchronisation.  d_ctr = 256 B of device scratch.
+bool tlas_fits_one_node(uint32_t n_instances);
+cudaError_t update_tlas_one_node(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* out,
+                                 void* d_ctr, cudaStream_t stream);
 
 // Fills instance records + world boxes from descs/props (device arrays) and per-model BLAS bounds.
 struct BlasBounds { float lo[3]; float hi[3]; const uint8_t* verts; uint32_t n_verts; };   // verts: the model's 28-B vertex buffer
 cudaError_t launch_instance_records(const rtx_instance_desc* d_descs, const rtx_instance_props* d_props, const BlasBounds* d_bounds,
-                                    uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, cudaStream_t stream);
+                                    uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, unsigned int* d_scratch6 /* 6 words per instance */,
+                                    cudaStream_t stream);
 
 }  // namespace rtx
