@@ -25,6 +25,9 @@ namespace rtx {
 #ifndef RTX_FETCH_CHUNK
 #define RTX_FETCH_CHUNK 32     // rays a warp claims from the global cursor with one atomic
 #endif
+#ifndef RTX_FETCH_MIN
+#define RTX_FETCH_MIN 32u      // guided self-scheduling (claims shrinking to this many rays as the queue runs out) measured slower than
+#endif                         // constant claims: 8.94 against 8.82 ms per C2 pass with a minimum of 4; kept as a build knob
 #ifndef RTX_SCHED_DEFAULT
 #define RTX_SCHED_DEFAULT 0x060808   // th_tri | th_inst << 8 | th_node << 16: run the triangle (instance) phase when >= th lanes are parked,
 #endif                               // or whenever fewer than th_node lanes have node work left (sweep: profiles/r01_s4_sched_sweep.txt)
@@ -50,10 +53,15 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     bool exhausted = (S.n_instances == 0u);
     // the warp's private pool of claimed rays [pool_next, pool_end) and one chunk claimed ahead of need (its atomic
     // is in flight while the warp traverses): all warp-uniform
-    uint32_t pool_next = 0, pool_end = 0, ahead = 0;
+    uint32_t pool_next = 0, pool_end = 0, ahead = 0, ahead_sz = 0, claim_sz = RTX_FETCH_CHUNK;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     bool have_ahead = false;
     unsigned int c_nodes = 0, c_tris = 0, c_insts = 0;
 
+#ifdef RTX_TRACE_TIMELINE
+    unsigned long long tl_t0, tl_tex = 0, tl_rays = 0; unsigned tl_steps = 0, tl_drain_steps = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_t0));
+#endif
     for (;;) {
         // ---- refill idle lanes from the pool
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
@@ -64,12 +72,20 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
             uint32_t mine = pool_next + rank;
             pool_next += take;
             if (take < need) {                                   // pool empty: switch to the chunk claimed ahead (or claim one now)
-                if (!have_ahead) { if (lane == 0) ahead = atomicAdd(cursor, (unsigned)RTX_FETCH_CHUNK); }
+                const uint32_t sz = have_ahead ? ahead_sz : claim_sz;
+                if (!have_ahead) { if (lane == 0) ahead = atomicAdd(cursor, (unsigned)sz); }
                 const uint32_t base = __shfl_sync(0xffffffffu, ahead, 0);
                 have_ahead = false;
-                if (base >= n) { exhausted = true; pool_next = pool_end = 0; need = take; }
+                if (base >= n) {
+                    exhausted = true; pool_next = pool_end = 0; need = take;
+#ifdef RTX_TRACE_TIMELINE
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_tex));
+#endif
+                }
                 else {
-                    pool_end = min(base + (uint32_t)RTX_FETCH_CHUNK, n);
+                    pool_end = min(base + sz, n);
+                    // optional guided self-scheduling (RTX_FETCH_MIN < RTX_FETCH_CHUNK): the claims shrink as the queue runs out
+                    claim_sz = min((uint32_t)RTX_FETCH_CHUNK, max(RTX_FETCH_MIN, (n - pool_end) / (2u * n_warps)));
                     const uint32_t take2 = min(need - take, pool_end - base);
                     if (rank >= take) mine = base + (rank - take);
                     pool_next = base + take2;
@@ -81,7 +97,8 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
                 active = true;
             }
             if (!exhausted && !have_ahead && pool_end - pool_next < 32u) {   // claim the next chunk now, use it later
-                if (lane == 0) ahead = atomicAdd(cursor, (unsigned)RTX_FETCH_CHUNK);
+                if (lane == 0) ahead = atomicAdd(cursor, (unsigned)claim_sz);
+                ahead_sz = claim_sz;
                 have_ahead = true;
             }
         }
@@ -131,8 +148,21 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
                 RTX_FINISH(false)
             }
 #undef RTX_FINISH
+#ifdef RTX_TRACE_TIMELINE
+            tl_steps++; if (exhausted) tl_drain_steps++;
+#endif
         } while (__popc(__ballot_sync(0xffffffffu, active)) >= threshold);
     }
+#ifdef RTX_TRACE_TIMELINE
+    {
+        unsigned long long tl_t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_t1));
+        const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (lane == 0 && (wid % 37u) == 0u && n > 100000u)
+            printf("TL %u n %u start %llu exhausted_at %llu end %llu steps %u drain_steps %u\n", wid, n, tl_t0 % 100000000ull,
+                   tl_tex ? tl_tex - tl_t0 : 0ull, tl_t1 - tl_t0, tl_steps, tl_drain_steps);
+    }
+#endif
     if (S.n_instances == 0u) {   // empty scene: everything misses
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             if (!ANY_HIT) hit_a[i] = make_float4(__ldg(d_tmax + i).w, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
