@@ -155,6 +155,8 @@ rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stage
 #define RTX_OPT_TRACE_STATS   1u
 #define RTX_OPT_STAGE_TIMING  2u
 #define RTX_OPT_PASS_PARTS    3u
+#define RTX_OPT_TLAS_REBUILD  4u   /* 1: rtx_set_instances always rebuilds the TLAS; 0 (default): it refits the last build when the instance
+                                    * list still names the same models (rdn/Renderer.cpp:594 refits every frame) */
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);

@@ -34,7 +34,7 @@ assert vertex_dt.itemsize == 28 and material_dt.itemsize == 128 and props_dt.ite
 assert camera_dt.itemsize == 512 and desc_dt.itemsize == 64 and ray_dt.itemsize == 32 and hit_dt.itemsize == 20
 
 FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL, FLAG_RESTIR, FLAG_LEGACY_RR = 1, 2, 4, 8, 16
-OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS = 1, 2, 3
+OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS, OPT_TLAS_REBUILD = 1, 2, 3, 4
 MISS = 0xFFFFFFFF
 STAGE_NAMES = ["generate", "closest", "any", "shade_primary", "di_finish", "gi_step", "scatter", "finalize", "accumulate", "sort"]
 

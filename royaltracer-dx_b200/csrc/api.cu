@@ -37,6 +37,8 @@ struct rtx_ctx {
     // arrays go through a ring of two pinned staging blocks, so that rtx_set_instances neither allocates nor synchronises
     size_t cap_descs = 0, cap_props = 0, cap_inst_model = 0, cap_recs = 0, cap_lo = 0, cap_hi = 0, cap_box6 = 0, cap_tlas_prims = 0;
     unsigned int* d_box6 = nullptr;
+    std::vector<uint32_t> tlas_models;      // instance -> model of the TLAS currently built (a refit needs the same)
+    bool force_tlas_rebuild = false;        // RTX_OPT_TLAS_REBUILD: rebuild instead of refitting
     float4 *d_box_lo = nullptr, *d_box_hi = nullptr;
     void* d_tlas_ctr = nullptr;
     struct Stage { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool pending = false; } stage[2];
@@ -236,15 +238,22 @@ extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* des
     cudaError_t e = launch_instance_records(c->d_descs, c->d_props, c->d_bounds, n, c->d_inst_recs, c->d_box_lo, c->d_box_hi, c->d_box6, c->stream);
     if (e == cudaSuccess && n) {
         if (!c->d_tlas_ctr) RTX_CK(cudaMalloc(&c->d_tlas_ctr, 256));
+        bool same_models = c->tlas_models.size() == n;
+        for (uint32_t i = 0; same_models && i < n; i++) same_models = c->tlas_models[i] == (uint32_t)descs[i].blas;
         if (tlas_fits_one_node(n) && c->tlas.nodes && c->cap_tlas_prims >= n) {
             // a TLAS of one node is rewritten in place: no allocation, no host synchronisation (the per-frame path of BASELINE config C2)
             e = update_tlas_one_node(c->d_inst_recs, c->d_box_lo, c->d_box_hi, n, &c->tlas, c->d_tlas_ctr, c->stream);
+        } else if (c->tlas.nodes && c->tlas.n_prims == n && same_models && !c->force_tlas_rebuild) {
+            // same instances of the same models as the last build: REFIT (what the reference does every frame, rdn/Renderer.cpp:594)
+            e = refit_tlas(c->d_inst_recs, c->d_box_lo, c->d_box_hi, n, &c->tlas, c->stream);
         } else {
             RTX_CK(cudaStreamSynchronize(c->stream));
             free_bvh(&c->tlas);
             e = build_tlas(c->d_inst_recs, c->d_box_lo, c->d_box_hi, n, &c->tlas, c->stream);
             c->cap_tlas_prims = e == cudaSuccess ? c->tlas.n_prims : 0;
         }
+        c->tlas_models.resize(n);
+        for (uint32_t i = 0; i < n; i++) c->tlas_models[i] = (uint32_t)descs[i].blas;
     }
     c->launches += 6;
     RTX_CK(e);
@@ -609,6 +618,7 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     if (!c) return fail(RTX_ERR_ARG, "null context");
     if (option == RTX_OPT_TRACE_STATS) c->trace_stats = value != 0;
     else if (option == RTX_OPT_STAGE_TIMING) c->timing.stage_timing = value != 0;
+    else if (option == RTX_OPT_TLAS_REBUILD) c->force_tlas_rebuild = value != 0;
     else if (option == RTX_OPT_PASS_PARTS) {
         if (value < 1u || value > (uint32_t)WAVE_MAX_PARTS) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PASS_PARTS must be 1..4");
         c->wb.parts = (int)value;

@@ -460,6 +460,7 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
     out->sah_cost = 0.0f;
 
     if (n <= MAX_LEAF) {
+        out->n_levels = 1; out->level_start[0] = 0; out->level_start[1] = 1;
         k_single_node<PRIM_F4, Source><<<1, 32, 0, stream>>>(src, d_plo, d_phi, (int)n, d_nodes, d_prims, d_ctr);
     } else {
         Scratch keys_a, keys_b, vals_a, vals_b, child_s, cnt_s, cost_s, dec_s, nlo_s, nhi_s, cl_a, cl_b, nn_s, val_s, valid_s, pos_s,
@@ -515,10 +516,12 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
         CKE(cudaMemcpyAsync(tasks_a.p, &root_task, sizeof root_task, cudaMemcpyHostToDevice, stream));
         unsigned n_in = 1;
         uint2* tin = (uint2*)tasks_a.p; uint2* tout = (uint2*)tasks_b.p;
+        out->n_levels = 1; out->level_start[0] = 0; out->level_start[1] = 1;
         while (n_in > 0) {
             k_collapse<PRIM_F4, Source><<<grid(n_in), TB, 0, stream>>>(A, src, tin, n_in, tout);
             CKE(cudaMemcpyAsync(&h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, stream));
             CKE(cudaStreamSynchronize(stream));
+            if (h_ctr.tasks_out > 0 && out->n_levels < 47u) { out->n_levels++; out->level_start[out->n_levels] = h_ctr.nodes; }
             n_in = h_ctr.tasks_out;
             CKE(cudaMemsetAsync(&d_ctr->tasks_out, 0, sizeof(unsigned), stream));
             uint2* t = tin; tin = tout; tout = t;
@@ -569,6 +572,99 @@ cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
     if (n_instances) k_box_bounds<<<(n_instances + 255) / 256, 256, 0, stream>>>(d_box_lo, d_box_hi, n_instances, (BuildCounters*)ctr.p);
     RecSource src{d_inst_recs};
     return build_generic<4, RecSource>(d_box_lo, d_box_hi, n_instances, src, (BuildCounters*)ctr.p, out, stream);
+}
+
+// ---- TLAS refit ------------------------------------------------------------------------------------------------------
+// leaf order of the instance records: prims[k] (4 x float4) carries its instance id in .w.y
+__global__ void k_refit_prims(const float4* __restrict__ recs, uint32_t n_prims, float4* __restrict__ prims) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_prims) return;
+    const uint32_t inst = __float_as_uint(prims[4 * k + 3].y);
+    for (int r = 0; r < 4; r++) prims[4 * k + r] = recs[4 * (size_t)inst + r];
+}
+
+// the box a node's quantised planes describe (a conservative superset of everything below it)
+__device__ __forceinline__ void node_box(const uint4* np, float lo[3], float hi[3]) {
+    const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+    const float p[3] = {__uint_as_float(n0.x), __uint_as_float(n0.y), __uint_as_float(n0.z)};
+    const float sc[3] = {__uint_as_float((n0.w & 0xffu) << 23), __uint_as_float(((n0.w >> 8) & 0xffu) << 23), __uint_as_float(((n0.w >> 16) & 0xffu) << 23)};
+    const uint32_t qlo[3][2] = {{n2.x, n2.y}, {n2.z, n2.w}, {n3.x, n3.y}}, qhi[3][2] = {{n3.z, n3.w}, {n4.x, n4.y}, {n4.z, n4.w}};
+    const uint32_t WI = n1.z;
+    for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+    for (int s = 0; s < 8; s++) {
+        if (!((WI >> (24 + s)) & 1u) && !((WI >> (3 * s)) & 7u)) continue;     // empty slot
+        for (int a = 0; a < 3; a++) {
+            const float ql = (float)((qlo[a][s >> 2] >> (8 * (s & 3))) & 0xffu), qh = (float)((qhi[a][s >> 2] >> (8 * (s & 3))) & 0xffu);
+            lo[a] = fminf(lo[a], p[a] + ql * sc[a]); hi[a] = fmaxf(hi[a], p[a] + qh * sc[a]);
+        }
+    }
+}
+
+// one thread per node of one level: child boxes from the refitted children (inner) or the instances' world boxes (leaves), then the same
+// origin / exponent / outward quantisation as emit_node
+__global__ void k_refit_level(uint4* __restrict__ nodes, uint32_t first, uint32_t count, const float4* __restrict__ prims,
+                              const float4* __restrict__ box_lo, const float4* __restrict__ box_hi) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint4* np = nodes + (size_t)(first + t) * 5;
+    const uint4 n0 = np[0], n1 = np[1];
+    const uint32_t WI = n1.z, imask = WI >> 24, W = WI & 0x00ffffffu;
+    float clo[8][3], chi[8][3];
+    bool used[8];
+    float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int s = 0; s < 8; s++) {
+        used[s] = false;
+        if ((imask >> s) & 1u) {
+            const uint32_t child = n1.x + __popc(imask & ((1u << s) - 1u));
+            node_box(nodes + (size_t)child * 5, clo[s], chi[s]);
+            used[s] = true;
+        } else if ((W >> (3 * s)) & 7u) {
+            for (int a = 0; a < 3; a++) { clo[s][a] = INFINITY; chi[s][a] = -INFINITY; }
+            for (int k = 0; k < 3; k++) {
+                if (!((W >> (3 * s + k)) & 1u)) continue;
+                const uint32_t slot = n1.y + __popc(W & ((1u << (3 * s + k)) - 1u));
+                const uint32_t inst = __float_as_uint(prims[4 * (size_t)slot + 3].y);
+                const float4 l = box_lo[inst], h = box_hi[inst];
+                clo[s][0] = fminf(clo[s][0], l.x); clo[s][1] = fminf(clo[s][1], l.y); clo[s][2] = fminf(clo[s][2], l.z);
+                chi[s][0] = fmaxf(chi[s][0], h.x); chi[s][1] = fmaxf(chi[s][1], h.y); chi[s][2] = fmaxf(chi[s][2], h.z);
+            }
+            used[s] = true;
+        }
+        if (used[s]) for (int a = 0; a < 3; a++) { plo[a] = fminf(plo[a], clo[s][a]); phi[a] = fmaxf(phi[a], chi[s][a]); }
+    }
+    int e[3]; float sv[3];
+    for (int a = 0; a < 3; a++) { e[a] = exp_for_extent(phi[a] - plo[a]); sv[a] = __uint_as_float((unsigned)e[a] << 23); }
+    unsigned char qlo[3][8], qhi[3][8];
+    for (int s = 0; s < 8; s++) {
+        for (int a = 0; a < 3; a++) { qlo[a][s] = 0; qhi[a][s] = 0; }
+        if (!used[s]) continue;
+        for (int a = 0; a < 3; a++) {
+            int ql = (int)floorf((clo[s][a] - plo[a]) / sv[a]);
+            int qh = (int)ceilf((chi[s][a] - plo[a]) / sv[a]);
+            ql = max(0, min(255, ql)); qh = max(0, min(255, qh));
+            while (ql > 0 && plo[a] + (float)ql * sv[a] > clo[s][a]) ql--;
+            while (qh < 255 && plo[a] + (float)qh * sv[a] < chi[s][a]) qh++;
+            qlo[a][s] = (unsigned char)ql; qhi[a][s] = (unsigned char)qh;
+        }
+    }
+    auto pack4 = [](const unsigned char* b) { return (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24); };
+    np[0] = make_uint4(__float_as_uint(plo[0]), __float_as_uint(plo[1]), __float_as_uint(plo[2]),
+                       (unsigned)e[0] | ((unsigned)e[1] << 8) | ((unsigned)e[2] << 16) | (n0.w & 0xff000000u));
+    np[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    np[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    np[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+}
+
+cudaError_t refit_tlas(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* b,
+                       cudaStream_t stream) {
+    if (!b->nodes || !b->prims || b->n_prims != n_instances || b->n_levels == 0u || b->level_start[b->n_levels] != b->n_nodes)
+        return cudaErrorInvalidValue;
+    k_refit_prims<<<(n_instances + 255) / 256, 256, 0, stream>>>(d_inst_recs, n_instances, b->prims);
+    for (int lv = (int)b->n_levels - 1; lv >= 0; lv--) {
+        const uint32_t first = b->level_start[lv], count = b->level_start[lv + 1] - first;
+        if (count) k_refit_level<<<(count + 127) / 128, 128, 0, stream>>>(b->nodes, first, count, b->prims, d_box_lo, d_box_hi);
+    }
+    return cudaGetLastError();
 }
 
 bool tlas_fits_one_node(uint32_t n_instances) { return n_instances >= 1u && n_instances <= (uint32_t)MAX_LEAF; }

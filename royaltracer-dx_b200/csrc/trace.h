@@ -19,6 +19,8 @@ struct Bvh8 {
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // padded bounds of everything inside
     float build_ms = 0.0f;
     float sah_cost = 0.0f;      // SAH cost of the wide tree relative to the root area (c_node = 1, c_prim = 0.3)
+    // nodes are emitted level by level (children always behind their parent): level k = [level_start[k], level_start[k + 1])
+    uint32_t level_start[48] = {0}; uint32_t n_levels = 0;
 };
 
 // BLAS over an indexed triangle list (vertex stride 28 B, position first).  Returns device allocations owned by the caller.
@@ -30,6 +32,11 @@ cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
 void free_bvh(Bvh8* b);
 // Per-frame TLAS update when the whole TLAS is one node (n_instances <= the leaf size): rewrites out->nodes / out->prims in place,
 // stream-ordered, no allocation, no host synchronisation.  d_ctr = 256 B of device scratch.
+// Per-frame TLAS REFIT (rdn/Renderer.cpp:594, TopLevelASGenerator update path): keeps the topology of the last build, copies the new instance
+// records into leaf order and recomputes every node's origin, exponents and quantised child boxes bottom-up, one launch per level.
+// Stream-ordered, no allocation, no host synchronisation.  Valid while the instance count is the one the TLAS was built for.
+cudaError_t refit_tlas(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* inout,
+                       cudaStream_t stream);
 bool tlas_fits_one_node(uint32_t n_instances);
 cudaError_t update_tlas_one_node(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* out,
                                  void* d_ctr, cudaStream_t stream);

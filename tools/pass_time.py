@@ -18,12 +18,15 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--bounces", type=int, default=6)
 ap.add_argument("--passes", type=int, default=8)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--refit", type=int, default=0, help="call rtx_set_instances this many times after the upload (TLAS refit)")
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sc = rtdx.scenes.mesh_room(n=a.side) if a.scene == "mesh" else rtdx.scenes.instanced_blobs()
 ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags, stream=stream.cuda_stream)
-ctx.upload_scene(sc)
+up = ctx.upload_scene(sc)
+for _ in range(a.refit):
+    ctx.set_instances(up["descs"], up["props"])
 for p in range(3):
     ctx.render_pass(p, 1)
 ctx.synchronize(); ctx.reset_counters()
