@@ -14,7 +14,9 @@ def main(path, which=-1):
         u = row[ui]
         v = v / 1e6 if u in ("ns", "nsecond") else (v / 1e3 if u in ("us", "usecond") else v)
         seq.append((row[ki].split("(")[0], v))
-    idx = [i for i, (n, _) in enumerate(seq) if "k_generate" in n]
+    # a pass starts at its first k_generate; with concurrent path ranges (RTX_OPT_PASS_PARTS) the parts' launches alternate, so the
+    # k_generate launches of one pass follow each other
+    idx = [i for i, (n, _) in enumerate(seq) if "k_generate" in n and (i == 0 or "k_generate" not in seq[i - 1][0])]
     s = idx[which]
     e = idx[which + 1] if which + 1 < 0 and which + 1 < len(idx) and which != -1 else len(seq)
     tot = 0.0
