@@ -305,6 +305,36 @@ def test_legacy_rr_estimator_bit_exact(rtdx, orc, scene_name):
     ctx.close()
 
 
+def test_async_readback_and_frame_in_flight_match_blocking_calls(rtdx):
+    """rtx_read_output_async / rtx_wait_output with one frame in flight (bench.py's e2e loop) give the images of the blocking per-frame
+    loop: same RGBA8 bytes after every frame, with rtx_set_instances / rtx_set_camera called every frame in both loops."""
+    sc = rtdx.scenes.mesh_room(n=12)
+    W, H = 128, 96
+    imgs = []
+    for mode in ("blocking", "in_flight"):
+        ctx, up = _upload(rtdx, sc, W, H, bounces=2)
+        outs = [np.zeros((H, W, 4), dtype=np.uint8) for _ in range(2)]
+        got = []
+        for k in range(4):
+            ctx.set_instances(up["descs"], up["props"])
+            ctx.set_camera(up["camera"])
+            ctx.render_pass(k, 1)
+            if mode == "blocking":
+                got.append(ctx.read_output().copy())
+            else:
+                ctx.wait_output()
+                if k > 0:
+                    got.append(outs[(k - 1) & 1].copy())
+                ctx.read_output_async(outs[k & 1])
+        if mode == "in_flight":
+            ctx.wait_output(); got.append(outs[3 & 1].copy())
+        imgs.append(got)
+        ctx.close()
+    for a, b in zip(*imgs):
+        assert np.array_equal(a, b)
+    assert imgs[0][3].any() and not np.array_equal(imgs[0][0], imgs[0][3])
+
+
 def test_tlas_refit_matches_rebuild_and_oracle(rtdx, orc):
     """Per-frame TLAS refit (rdn/Renderer.cpp:594): rtx_set_instances keeps the topology of the last build and refits the node boxes on
     the stream; hits after large seeded instance motion equal those of a forced rebuild (RTX_OPT_TLAS_REBUILD) and of the oracle."""
