@@ -330,7 +330,7 @@ def main():
                     "algorithmic_bytes_per_launch": cnt_t["closest_rays"] * b_ray / n_launch, "peak_source": peak_src,
                     "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri, "instances_per_ray": n_inst,
                     "launches": n_launch, "avg_launch_ms": trace_ms / n_launch, "rays_per_launch": cnt_t["closest_rays"] / n_launch, "trace_share_of_step": trace_ms / pass_ms if pass_ms else None,
-                    "note": "BVH (%.1f MB) is L2-resident at this scene size; HBM peak is the conservative denominator (SURVEY.md §8d)" % (sum(b["bytes"] for b in blas) / 1e6)}
+                    "note": "BVH (%.1f MB) is L2-resident at this scene size; HBM peak is the conservative denominator (SURVEY.md §8d); per-launch durations are from the same K steps re-run with CUDA events around every traversal launch (RTX_OPT_STAGE_TIMING: one path range per pass, full-size launches), the timed steps of `value` run as 2 concurrent path ranges" % (sum(b["bytes"] for b in blas) / 1e6)}
         cpu = None
         if not args.no_cpu_baseline:
             v, r, dt, _ = cpu_oracle_sample(rtdx, sc, args, 1, cam, props, up["lights"])
