@@ -18,22 +18,23 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--bounces", type=int, default=6)
 ap.add_argument("--passes", type=int, default=8)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--spp", type=int, default=1, help="samples per pass (paths in flight = W*H*spp)")
 ap.add_argument("--refit", type=int, default=0, help="call rtx_set_instances this many times after the upload (TLAS refit)")
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sc = rtdx.scenes.mesh_room(n=a.side) if a.scene == "mesh" else rtdx.scenes.instanced_blobs()
-ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags, stream=stream.cuda_stream)
+ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags, samples_per_pass=a.spp, stream=stream.cuda_stream)
 up = ctx.upload_scene(sc)
 for _ in range(a.refit):
     ctx.set_instances(up["descs"], up["props"])
 for p in range(3):
-    ctx.render_pass(p, 1)
+    ctx.render_pass(p * a.spp, a.spp)
 ctx.synchronize(); ctx.reset_counters()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for p in range(a.passes):
-    ctx.render_pass(3 + p, 1)
+    ctx.render_pass((3 + p) * a.spp, a.spp)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.passes
 c = ctx.counters()
