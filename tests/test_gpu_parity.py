@@ -570,3 +570,30 @@ def test_full_size_properties_c2(rtdx):
     img = ctx.read_output()
     assert img.shape == (H, W, 4) and (img[..., 3] == 255).all()
     ctx.close()
+
+
+def test_full_size_properties_c3(rtdx):
+    """BASELINE config C3 at full size (10 M instanced triangles, 1000 instances, 3840x2160, bounces 3, ~0.5 M light triangles):
+    size-independent properties — determinism, sample counting, the ray bound 5 + bounces per path, any-hit == closest-exists, and
+    invariance of the image under a per-frame TLAS refit with unchanged transforms and under the number of concurrent path ranges."""
+    sc = rtdx.scenes.instanced_blobs()
+    W, H, bounces = 3840, 2160, 3
+    ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
+    assert len(sc.instances) == 1000 and sc.n_triangles() > 10_000_000
+    ctx.reset_counters()
+    ctx.render_pass(0, 1); ctx.synchronize()
+    a0 = ctx.read_accum(); c0 = ctx.counters()
+    assert c0["paths"] == W * H and c0["closest_rays"] + c0["shadow_rays"] <= c0["paths"] * (5 + bounces)
+    assert (a0[..., 3] <= 1).all() and a0[..., 3].mean() > 0.99 and a0[..., :3].sum() > 0
+    ctx.set_instances(up["descs"], up["props"])                       # refit (same transforms): hits must not change
+    ctx.set_option(rtdx.OPT_PASS_PARTS, 3)
+    ctx.reset_accum(); ctx.reset_counters(); ctx.render_pass(0, 1); ctx.synchronize()
+    c1 = ctx.counters()
+    assert np.array_equal(ctx.read_accum().view(np.uint32), a0.view(np.uint32))
+    assert all(c1[k] == c0[k] for k in ("paths", "closest_rays", "shadow_rays")), (c0, c1)
+    rays = rtdx.scenes.camera_rays(up["camera"], W, H, step=8)
+    ch, ah = ctx.trace(rays), ctx.trace(rays, any_hit=True)
+    assert np.array_equal(ch["inst"] != rtdx.MISS, ah["inst"] != rtdx.MISS)
+    hit = ch["inst"] != rtdx.MISS
+    assert 0.2 < hit.mean() and (ch["inst"][hit] < 1000).all()
+    ctx.close()
