@@ -23,6 +23,10 @@ namespace rtx {
     } while (0)
 
 #define WF_BLOCK 128
+#ifndef RTX_SP_MINB
+#define RTX_SP_MINB 8     // resident CTAs per SM the register budget of k_shade_primary / k_di_finish is set for: 64 registers with ~150 B
+                          // of spills measured best (di_finish 0.344 -> 0.305 ms per C2 pass against the unconstrained 108 registers)
+#endif
 #ifndef RTX_GI_BLOCK
 #define RTX_GI_BLOCK 384    // CTA size of k_gi_step: 2 x 384 threads per SM at 85 registers measured best (profiles/)
 #endif
@@ -94,7 +98,7 @@ __device__ __forceinline__ void SampleLightNEE(const SceneData& S, float& pdf_li
 }
 
 // ---- stage: primary hit -> RIS over NEE candidates -> BSDF candidate ray (Pass_init_di_v7.hlsl:99-159, Sampler_v7.hlsl:653-700)
-__global__ void __launch_bounds__(WF_BLOCK)
+__global__ void __launch_bounds__(WF_BLOCK, RTX_SP_MINB)
 k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
                 RayQueue qout, unsigned long long* ray_counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,7 +153,7 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
 
 // ---- stage: BSDF candidate of the DI reservoir, DI visibility ray, first indirect ray
 // (Sampler_v7.hlsl:231-270,729-735; Pass_init_di_v7.hlsl:161-167; Path_Sampler_v7.hlsl:13-52)
-__global__ void __launch_bounds__(WF_BLOCK)
+__global__ void __launch_bounds__(WF_BLOCK, RTX_SP_MINB)
 k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hit_a, const uint32_t* __restrict__ hit_inst,
             RayQueue q_shadow, RayQueue qout, unsigned long long* ray_counters) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
