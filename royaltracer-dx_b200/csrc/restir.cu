@@ -23,6 +23,10 @@ namespace rtx {
     } while (0)
 
 #define RS_BLOCK 128
+#ifndef RTX_RS_MINB
+#define RTX_RS_MINB 8      // resident CTAs per SM the register budget of the reuse kernels (k_temporal_a/b, k_spatial_a/b) is set for:
+                           // 64 registers instead of 72-122 measured best (ReSTIR frame on C2 13.2 -> 12.96 ms)
+#endif
 #define RS_TEMPORAL_M_CAP 16u        // Common_v7.hlsl:19-20
 #define RS_SPATIAL_M_CAP 128u        // :17-18
 #define RS_CANDIDATES 3u             // :13
@@ -173,7 +177,7 @@ __device__ __forceinline__ TemporalSetup temporal_setup(const SceneData& S, cons
     return t;
 }
 
-__global__ void __launch_bounds__(RS_BLOCK)
+__global__ void __launch_bounds__(RS_BLOCK, RTX_RS_MINB)
 k_temporal_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, uint32_t n_inst, RayQueue q) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     bool e0 = false, e1 = false; VisRay r0, r1;
@@ -198,7 +202,7 @@ k_temporal_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, u
     push_ray(q, e1, r1.o, 0.0f, r1.d, r1.tmax, pix * 16u + 1u);
 }
 
-__global__ void __launch_bounds__(RS_BLOCK)
+__global__ void __launch_bounds__(RS_BLOCK, RTX_RS_MINB)
 k_temporal_b(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, uint32_t n_inst, uint32_t frame) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= R.n) return;
@@ -250,7 +254,7 @@ k_temporal_b(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, u
 
 // ------------------------------------------------------------------------------------------------ spatial reuse (RayGen3)
 // neighbour search, Pass_spat_di_v7.hlsl:84-196.  Writes the candidate lists and the RNG state that follows them.
-__global__ void __launch_bounds__(RS_BLOCK)
+__global__ void __launch_bounds__(RS_BLOCK, RTX_RS_MINB)
 k_spatial_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, uint32_t frame, RayQueue q) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = pix < R.n;
@@ -317,7 +321,7 @@ k_spatial_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, ui
 }
 
 // pairwise MIS + reservoir merges (Pass_spat_di_v7.hlsl:198-341), GI final shade (:367-381), emits the DI winner's ray (:343-352)
-__global__ void __launch_bounds__(RS_BLOCK)
+__global__ void __launch_bounds__(RS_BLOCK, RTX_RS_MINB)
 k_spatial_b(RsView R, SceneData S, RayQueue q) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     bool e = false; VisRay vr; vr.o = vr.d = mk3(0, 0, 0); vr.tmax = 0.0f;
