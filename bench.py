@@ -282,6 +282,8 @@ def main():
     props, descs, cam = pinned_copy(up["props"]), pinned_copy(up["descs"]), pinned_copy(up["camera"])
     h2d = int(props.nbytes + descs.nbytes + cam.nbytes); d2h = W * H * 4
     ctx.reset_accum()
+    if world > 1 and rank == 0:
+        ctx.set_resolve_source(total.data_ptr())     # rank 0 displays the reduced image, not its private partial sum
 
     # the frame's read-back targets (pinned host memory): one frame is kept in flight, so the RGBA8 copy of frame k overlaps the
     # rendering of frame k+1 (rtx_read_output_async / rtx_wait_output); every frame's image is complete on the host before the timed

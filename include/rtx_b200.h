@@ -123,6 +123,9 @@ rtx_status rtx_read_output(rtx_ctx*, uint8_t* rgba8_out);
  * for a truly asynchronous copy).  rgba8_out must stay valid until then. */
 rtx_status rtx_read_output_async(rtx_ctx*, uint8_t* rgba8_out);
 rtx_status rtx_wait_output(rtx_ctx*);
+/* multi-GPU: the accumulation buffer rtx_read_output* resolves — a device buffer of W*H float4 owned by the caller, typically the
+ * destination of the per-pass reduce on rank 0 ("rank 0 then runs F20's divide + sRGB"); NULL = the context's own buffer */
+rtx_status rtx_set_resolve_source(rtx_ctx*, const void* d_accum_float4);
 /* device pointer of gPermanentData, for the per-pass NCCL reduce over NVLink */
 rtx_status rtx_accum_device_ptr(rtx_ctx*, void** out);
 /* raw TraceRay (T3 closest / T4 any-hit): host buffers, or device buffers with _device */

@@ -57,7 +57,7 @@ class RtxBlasInfo(C.Structure):
 # every symbol include/rtx_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model", "rtx_blas_info_get", "rtx_set_material_ids",
                "rtx_set_materials", "rtx_set_instances", "rtx_set_emissive_triangles", "rtx_set_camera", "rtx_render_pass",
-               "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_read_output_async", "rtx_wait_output",
+               "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_read_output_async", "rtx_wait_output", "rtx_set_resolve_source",
                "rtx_accum_device_ptr", "rtx_trace",
                "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel",
                "rtx_selftest_dmath", "rtx_render_frame", "rtx_reset_restir", "rtx_read_restir"]
@@ -99,6 +99,7 @@ def load_library():
     lib.rtx_read_output.argtypes = [vp, vp]
     lib.rtx_read_output_async.argtypes = [vp, vp]
     lib.rtx_wait_output.argtypes = [vp]
+    lib.rtx_set_resolve_source.argtypes = [vp, vp]
     lib.rtx_accum_device_ptr.argtypes = [vp, C.POINTER(vp)]
     lib.rtx_trace.argtypes = [vp, vp, u32, vp, C.c_int]
     lib.rtx_trace_device.argtypes = [vp, vp, u32, vp, C.c_int]
@@ -333,6 +334,10 @@ class Context:
         """Enqueue resolve + read-back into the caller-owned (pinned) uint8 buffer `out`; wait_output() completes it."""
         assert out.dtype == np.uint8 and out.size == self.height * self.width * 4 and out.flags["C_CONTIGUOUS"]
         self._check(self.lib.rtx_read_output_async(self.handle, _ptr(out)))
+
+    def set_resolve_source(self, device_ptr):
+        """Resolve (read_output*) from an external device accumulation buffer, e.g. the reduced multi-GPU sum; None = the context's own."""
+        self._check(self.lib.rtx_set_resolve_source(self.handle, C.c_void_p(int(device_ptr) if device_ptr else None)))
 
     def wait_output(self):
         self._check(self.lib.rtx_wait_output(self.handle))

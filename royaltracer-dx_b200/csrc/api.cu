@@ -456,6 +456,16 @@ extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
     return RTX_OK;
 }
 
+// Multi-GPU hosts: rank 0 resolves the REDUCED accumulation buffer (a device float4-per-pixel buffer it owns, e.g. the destination of the
+// per-pass ncclReduce) instead of this context's private partial sum.  nullptr restores the context's own buffer.
+extern "C" rtx_status rtx_set_resolve_source(rtx_ctx* c, const void* d_accum_float4) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    c->wb.resolve_source = (const float4*)d_accum_float4;
+    return RTX_OK;
+}
+
 extern "C" rtx_status rtx_wait_output(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
     RTX_CK(cudaSetDevice(c->cfg.device));

@@ -751,7 +751,7 @@ cudaError_t wave_accumulate(WaveBuffers& B, uint32_t npx, uint32_t spp, cudaStre
 }
 
 cudaError_t wave_resolve(WaveBuffers& B, uint32_t n_pixels, cudaStream_t stream, uint64_t* launches) {
-    k_resolve<<<(n_pixels + 255) / 256, 256, 0, stream>>>(B.accum, n_pixels, (uchar4*)B.output);
+    k_resolve<<<(n_pixels + 255) / 256, 256, 0, stream>>>(B.resolve_source ? B.resolve_source : B.accum, n_pixels, (uchar4*)B.output);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -46,6 +46,7 @@ struct WaveBuffers {
     uint32_t* counts = nullptr;        // 4 queue counters + scratch
     unsigned int* cursor = nullptr;    // 4 words per part (launch_trace)
     unsigned long long* ray_counters = nullptr;   // [0] closest, [1] shadow, [2] paths
+    const float4* resolve_source = nullptr;   // rtx_set_resolve_source: an external accumulation buffer (the multi-GPU sum) to resolve instead
     float4* accum = nullptr;           // gPermanentData
     uint8_t* output = nullptr;         // gOutput slice 0
     rtx_camera_params* cam = nullptr;  // b0 (device copy)

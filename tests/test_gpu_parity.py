@@ -335,6 +335,26 @@ def test_async_readback_and_frame_in_flight_match_blocking_calls(rtdx):
     assert imgs[0][3].any() and not np.array_equal(imgs[0][0], imgs[0][3])
 
 
+def test_resolve_source_external_accumulation_buffer(rtdx):
+    """rtx_set_resolve_source: rank 0 of a multi-GPU job resolves the reduced accumulation buffer instead of its private partial sum."""
+    import importlib
+    import torch
+    wrap = importlib.import_module("royaltracer-dx_b200.dist").wrap_device_buffer
+    sc = rtdx.scenes.cornell()
+    W, H = 96, 64
+    ctx, up = _upload(rtdx, sc, W, H, bounces=2)
+    ctx.render_pass(0, 1); img0 = ctx.read_output().copy()
+    saved = wrap(ctx.accum_device_ptr(), (H, W, 4)).clone()
+    ctx.render_pass(1, 1); img1 = ctx.read_output().copy()
+    assert not np.array_equal(img0, img1)
+    ctx.set_resolve_source(saved.data_ptr())
+    assert np.array_equal(ctx.read_output(), img0)
+    ctx.set_resolve_source(None)
+    assert np.array_equal(ctx.read_output(), img1)
+    torch.cuda.synchronize()
+    ctx.close()
+
+
 def test_tlas_refit_matches_rebuild_and_oracle(rtdx, orc):
     """Per-frame TLAS refit (rdn/Renderer.cpp:594): rtx_set_instances keeps the topology of the last build and refits the node boxes on
     the stream; hits after large seeded instance motion equal those of a forced rebuild (RTX_OPT_TLAS_REBUILD) and of the oracle."""
