@@ -335,6 +335,30 @@ def test_async_readback_and_frame_in_flight_match_blocking_calls(rtdx):
     assert imgs[0][3].any() and not np.array_equal(imgs[0][0], imgs[0][3])
 
 
+def test_instance_list_changes_between_frames(rtdx, orc):
+    """rtx_set_instances through its three paths — rebuild (count or models changed), refit (same models), one-node rewrite (<= 3
+    instances) — in one context: the instance list shrinks, is permuted to other models, and grows back; hits equal the oracle each time."""
+    sc = rtdx.scenes.instanced_blobs(n_models=3, n_side=5, lattice=3, emissive_fraction=0.1)      # 27 instances
+    W, H = 48, 32
+    ctx, up = _upload(rtdx, sc, W, H)
+    osc = _oracle(orc, sc, up)
+    rng = np.random.RandomState(9)
+    rays = np.concatenate([rtdx.scenes.camera_rays(up["camera"], W, H), random_rays(rtdx, rng, 8000, -5.0, 5.0)])
+    all_models = [i[0] for i in sc.instances]
+    all_xf = [np.asarray(i[1], dtype=np.float32) for i in sc.instances]
+    n_models = max(all_models) + 1
+    for pick, shift in ((range(27), 0), (range(0, 27, 4), 0), (range(0, 27, 4), 1), (range(2), 0), (range(3), 1), (range(27), 1), (range(27), 1)):
+        idx = list(pick)
+        models = [(all_models[i] + shift) % n_models for i in idx]
+        props, descs = rtdx.instance_properties([all_xf[i] for i in idx], [up["model_ids"][m] for m in models])
+        ctx.set_instances(descs, props)
+        got = ctx.trace(rays)
+        osc._model_ids = models
+        osc.set_props(props)
+        _assert_hits_equal(got, osc.trace(rays, mode=1))
+    ctx.close()
+
+
 def test_resolve_source_external_accumulation_buffer(rtdx):
     """rtx_set_resolve_source: rank 0 of a multi-GPU job resolves the reduced accumulation buffer instead of its private partial sum."""
     import importlib
