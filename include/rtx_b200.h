@@ -128,6 +128,17 @@ rtx_status rtx_wait_output(rtx_ctx*);
 rtx_status rtx_set_resolve_source(rtx_ctx*, const void* d_accum_float4);
 /* device pointer of gPermanentData, for the per-pass NCCL reduce over NVLink */
 rtx_status rtx_accum_device_ptr(rtx_ctx*, void** out);
+/* Multi-GPU (the reference is single-GPU): the scene is replicated, every rank renders its own samples of the full frame
+ * and the accumulation buffers are combined by ONE ncclReduce(sum, fp32, W*H*4, root 0) per progressive pass over NVLink.
+ * rtx_comm_unique_id: 128 bytes from ncclGetUniqueId on one rank, handed to the others by the host.  rtx_comm_init: collective;
+ * afterwards rank 0's rtx_read_output* resolve the reduced sum.  rtx_reduce_accum: queues the reduce behind everything rendered so far
+ * on a side stream; the render stream does not wait (the next pass overlaps it, only its final accumulation waits for the reduce to
+ * have read gPermanentData).  NCCL is bound at run time (dlopen of libnccl.so.2). */
+rtx_status rtx_comm_unique_id(void* out128);
+rtx_status rtx_comm_init(rtx_ctx*, const void* unique_id128, int rank, int world);
+rtx_status rtx_reduce_accum(rtx_ctx*);
+rtx_status rtx_read_reduced_accum(rtx_ctx*, float* host_out);   /* rank 0: the sum over ranks, float4 per pixel */
+rtx_status rtx_comm_destroy(rtx_ctx*);
 /* raw TraceRay (T3 closest / T4 any-hit): host buffers, or device buffers with _device */
 rtx_status rtx_trace(rtx_ctx*, const rtx_ray* rays, uint32_t n, rtx_hit* out, int any_hit);
 rtx_status rtx_trace_device(rtx_ctx*, const void* d_rays, uint32_t n, void* d_hits, int any_hit);
@@ -160,6 +171,10 @@ rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stage
 #define RTX_OPT_PASS_PARTS    3u
 #define RTX_OPT_TLAS_REBUILD  4u   /* 1: rtx_set_instances always rebuilds the TLAS; 0 (default): it refits the last build when the instance
                                     * list still names the same models (rdn/Renderer.cpp:594 refits every frame) */
+/* launch tuning of the traversal kernels (0 = built-in default, the measured optimum; csrc/trace.cu): */
+#define RTX_OPT_TRACE_FETCH_TH 5u  /* a warp refills its idle lanes when fewer than this many lanes are still traversing (default 24) */
+#define RTX_OPT_TRACE_SCHED    6u  /* phase scheduling thresholds th_tri | th_inst << 8 | th_node << 16 (default 0x060808) */
+#define RTX_OPT_TRACE_WAVES    7u  /* persistent grid = SMs x resident CTAs x waves (default 1) */
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);

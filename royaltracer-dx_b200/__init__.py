@@ -15,7 +15,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(HERE, "librtx_b200.so")   # the override is for A/B builds of the kernels
-HOST_LIB_PATH = os.path.join(HERE, "librtx_host.so")
+HOST_LIB_PATH = os.path.join(HERE, "librdx_prep.so")       # host-side data preparation (no engine inside; the C++ Renderer class lives in
+HOST_FULL_LIB_PATH = os.path.join(HERE, "librtx_host.so")  # librtx_host.so, which links the engine)
 
 # ---------------------------------------------------------------------------------------------- POD layouts
 vertex_dt = np.dtype([("position", "<f4", 3), ("normal_material", "<f4", 4)])
@@ -34,7 +35,7 @@ assert vertex_dt.itemsize == 28 and material_dt.itemsize == 128 and props_dt.ite
 assert camera_dt.itemsize == 512 and desc_dt.itemsize == 64 and ray_dt.itemsize == 32 and hit_dt.itemsize == 20
 
 FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL, FLAG_RESTIR, FLAG_LEGACY_RR = 1, 2, 4, 8, 16
-OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS, OPT_TLAS_REBUILD = 1, 2, 3, 4
+OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS, OPT_TLAS_REBUILD, OPT_TRACE_FETCH_TH, OPT_TRACE_SCHED, OPT_TRACE_WAVES = 1, 2, 3, 4, 5, 6, 7
 MISS = 0xFFFFFFFF
 STAGE_NAMES = ["generate", "closest", "any", "shade_primary", "di_finish", "gi_step", "scatter", "finalize", "accumulate", "sort"]
 
@@ -60,7 +61,8 @@ ABI_SYMBOLS = ["rtx_last_error", "rtx_create", "rtx_destroy", "rtx_upload_model"
                "rtx_reset_accum", "rtx_synchronize", "rtx_read_accum", "rtx_read_output", "rtx_read_output_async", "rtx_wait_output", "rtx_set_resolve_source",
                "rtx_accum_device_ptr", "rtx_trace",
                "rtx_trace_device", "rtx_trace_stats", "rtx_get_counters", "rtx_reset_counters", "rtx_last_pass_ms", "rtx_last_pass_stage_ms", "rtx_set_option", "rtx_debug_pixel",
-               "rtx_selftest_dmath", "rtx_render_frame", "rtx_reset_restir", "rtx_read_restir"]
+               "rtx_selftest_dmath", "rtx_render_frame", "rtx_reset_restir", "rtx_read_restir",
+               "rtx_comm_unique_id", "rtx_comm_init", "rtx_reduce_accum", "rtx_read_reduced_accum", "rtx_comm_destroy"]
 HOST_SYMBOLS = ["rdx_instance_properties", "rdx_collect_emissive_triangles", "rdx_camera_params", "rdx_generate_ess_lut",
                 "rdx_obj_load", "rdx_obj_free", "rdx_obj_error", "rdx_obj_counts", "rdx_obj_copy"]
 
@@ -114,6 +116,11 @@ def load_library():
     lib.rtx_render_frame.argtypes = [vp, u32]
     lib.rtx_reset_restir.argtypes = [vp]
     lib.rtx_read_restir.argtypes = [vp, vp]
+    lib.rtx_comm_unique_id.argtypes = [vp]
+    lib.rtx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.rtx_reduce_accum.argtypes = [vp]
+    lib.rtx_read_reduced_accum.argtypes = [vp, vp]
+    lib.rtx_comm_destroy.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -124,7 +131,6 @@ def load_host_library():
         return _host
     if not os.path.exists(HOST_LIB_PATH):
         raise RtxError("host library missing: %s (run `python royaltracer-dx_b200/build.py`)" % HOST_LIB_PATH)
-    load_library()   # librtx_host.so links against librtx_b200.so
     h = C.CDLL(HOST_LIB_PATH)
     vp, u32 = C.c_void_p, C.c_uint32
     h.rdx_instance_properties.argtypes = [vp, vp, u32, vp, vp]
@@ -346,6 +352,26 @@ class Context:
         p = C.c_void_p()
         self._check(self.lib.rtx_accum_device_ptr(self.handle, C.byref(p)))
         return p.value
+
+    # multi-GPU: the per-pass NCCL reduce of gPermanentData lives behind the C ABI (rtx_comm_init / rtx_reduce_accum)
+    def comm_unique_id(self):
+        """128 bytes of ncclGetUniqueId (call on one rank, hand to the others)."""
+        buf = (C.c_ubyte * 128)()
+        self._check(self.lib.rtx_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        assert len(unique_id) == 128
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.rtx_comm_init(self.handle, C.cast(buf, C.c_void_p), rank, world))
+
+    def reduce_accum(self):
+        self._check(self.lib.rtx_reduce_accum(self.handle))
+
+    def read_reduced_accum(self):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._check(self.lib.rtx_read_reduced_accum(self.handle, _ptr(out)))
+        return out
 
     def trace(self, rays, any_hit=False):
         r = np.ascontiguousarray(rays, dtype=ray_dt)

@@ -9,12 +9,14 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "librtx_b200.so")
 HOSTLIB = os.path.join(HERE, "librtx_host.so")
+PREPLIB = os.path.join(HERE, "librdx_prep.so")    # host-side data preparation only: no engine, no CUDA dependency
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # reproducible fp32: no implicit FMA contraction (see csrc/dmath.cuh)
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+OBJ = os.path.join(HERE, "..", "build", "obj")
 
 
 def _newer(target, sources):
@@ -32,7 +34,25 @@ def build(force=False, verbose=False):
     cu = _sources(CSRC, (".cu",))
     deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(HERE, "..", "include", "rtx_b200.h")]
     if force or _newer(LIB, deps):
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cu
+        # one object per translation unit, compiled concurrently (no relocatable device code: every kernel lives in one file), then linked
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(OBJ, exist_ok=True)
+        hdrs = [d for d in deps if not d.endswith(".cu")]
+
+        def compile_one(src):
+            obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+            if force or _newer(obj, [src] + hdrs):
+                cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+                print(" ".join(cmd), flush=True)
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                if verbose or r.returncode:
+                    print(r.stdout, flush=True)
+                if r.returncode:
+                    raise subprocess.CalledProcessError(r.returncode, cmd)
+            return obj
+        with ThreadPoolExecutor(max_workers=min(len(cu), os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, cu))
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     hs = _sources(HOST, (".cpp",))
@@ -40,6 +60,10 @@ def build(force=False, verbose=False):
     if hs and (force or _newer(HOSTLIB, hdeps)):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOSTLIB] + hs + [
             "-L" + HERE, "-lrtx_b200", "-Wl,-rpath,$ORIGIN"]
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    if hs and (force or _newer(PREPLIB, hdeps)):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-DRDX_PREP_ONLY", "-o", PREPLIB] + hs
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     return LIB, HOSTLIB

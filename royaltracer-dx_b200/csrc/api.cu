@@ -1,5 +1,6 @@
 // api.cu — the C ABI (include/rtx_b200.h): context, scene upload, acceleration-structure builds, render passes.
 // Plays the role of the DXR runtime + pipeline state behind rdn/Renderer.cpp's calls.
+#include <dlfcn.h>
 #include <string.h>
 
 #include <mutex>
@@ -53,6 +54,15 @@ struct rtx_ctx {
     float4* d_trace_o = nullptr; float4* d_trace_d = nullptr; float4* d_trace_ha = nullptr; uint32_t* d_trace_hi = nullptr;
     rtx_hit* d_trace_out = nullptr; uint32_t trace_cap = 0;
     TraceStats* d_stats = nullptr;
+    unsigned int* d_overflow = nullptr;     // raised by a traversal whose stack overflowed (SceneAS::overflow); checked + cleared by check_overflow
+    unsigned int* h_overflow = nullptr;     // pinned copy written behind every asynchronous read-back (rtx_wait_output looks at it)
+    void* d_trace_rays = nullptr; size_t cap_trace_rays = 0; void* d_trace_hits = nullptr; size_t cap_trace_hits = 0;   // rtx_trace staging
+    size_t cap_material_ids = 0, cap_materials = 0, cap_lights = 0;
+    int num_sms = 148, fetch_th = 0, sched = 0, waves = 0;     // traversal launch tuning (0 = the built-in defaults, trace.cu)
+    // multi-GPU (rtx_comm_init): one NCCL reduce of gPermanentData per progressive pass, on the side stream
+    void* comm = nullptr; int comm_rank = 0, comm_world = 1;
+    float4* d_total = nullptr;              // root only: the sum over ranks; rtx_read_output* resolve it
+    cudaEvent_t ev_pass = nullptr, ev_reduced = nullptr;
     uint64_t launches = 0;
     PassTiming timing;
     bool trace_stats = false;
@@ -63,10 +73,29 @@ static rtx_status fail(rtx_status code, const char* msg) { set_error(msg); retur
 
 extern "C" const char* rtx_last_error(void) { return g_err.c_str(); }
 
+extern "C" void rtx_destroy(rtx_ctx* c);
+extern "C" rtx_status rtx_comm_destroy(rtx_ctx* c);
+static rtx_status create_resources(rtx_ctx* c) {
+    if (c->cfg.stream) c->stream = (cudaStream_t)c->cfg.stream;
+    else { RTX_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (int i = 0; i < WAVE_MAX_EVENTS; i++) RTX_CK(cudaEventCreate(&c->timing.ev[i]));
+    RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
+    RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
+    RTX_CK(cudaMalloc((void**)&c->d_overflow, sizeof(unsigned int)));
+    RTX_CK(cudaMemset(c->d_overflow, 0, sizeof(unsigned int)));
+    RTX_CK(cudaMallocHost((void**)&c->h_overflow, sizeof(unsigned int)));
+    *c->h_overflow = 0u;
+    return RTX_OK;
+}
+
 extern "C" rtx_status rtx_create(const rtx_config* cfg, rtx_ctx** out) {
     if (!cfg || !out) return fail(RTX_ERR_ARG, "rtx_create: null argument");
     if (cfg->struct_size != sizeof(rtx_config)) return fail(RTX_ERR_ARG, "rtx_create: rtx_config.struct_size mismatch");
     if (cfg->width == 0 || cfg->height == 0) return fail(RTX_ERR_ARG, "rtx_create: zero-sized image");
+    // every path range owns a block of 128 queue counters of which the indirect queues take 5 + bounces (wavefront.cu); the legacy
+    // estimator keeps its per-bounce bookkeeping in 64 slots (legacy.cu)
+    if ((cfg->flags & RTX_FLAG_LEGACY_RR) ? cfg->bounces > 60u : cfg->bounces > 120u)
+        return fail(RTX_ERR_ARG, "rtx_create: bounces out of range (<= 120, <= 60 with RTX_FLAG_LEGACY_RR)");
     int ndev = 0;
     RTX_CK(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(RTX_ERR_CUDA, "rtx_create: no such CUDA device (no CPU fallback exists)");
@@ -77,12 +106,10 @@ extern "C" rtx_status rtx_create(const rtx_config* cfg, rtx_ctx** out) {
     rtx_ctx* c = new rtx_ctx();
     c->cfg = *cfg;
     if (c->cfg.samples_per_pass == 0) c->cfg.samples_per_pass = 1;
-    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
-    else { RTX_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    for (int i = 0; i < WAVE_MAX_EVENTS; i++) RTX_CK(cudaEventCreate(&c->timing.ev[i]));
-    RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
-    RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
+    c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     memset(&c->cam, 0, sizeof c->cam);
+    const rtx_status st = create_resources(c);
+    if (st != RTX_OK) { const std::string keep = g_err; rtx_destroy(c); g_err = keep; return st; }     // nothing leaks on a failed create
     *out = c;
     return RTX_OK;
 }
@@ -97,11 +124,14 @@ static void free_tables(rtx_ctx* c) {
 extern "C" void rtx_destroy(rtx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    rtx_comm_destroy(c);
     for (auto& m : c->models) { if (m.d_verts) cudaFree(m.d_verts); if (m.d_idx) cudaFree(m.d_idx); free_bvh(&m.bvh); }
     void* ptrs[] = {c->d_material_ids, c->d_materials, c->d_descs, c->d_props, c->d_inst_model, c->d_inst_recs, c->d_lights,
-                    c->d_trace_o, c->d_trace_d, c->d_trace_ha, c->d_trace_hi, c->d_trace_out, c->d_stats};
+                    c->d_trace_o, c->d_trace_d, c->d_trace_ha, c->d_trace_hi, c->d_trace_out, c->d_stats, c->d_overflow, c->d_trace_rays,
+                    c->d_trace_hits};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->h_overflow) cudaFreeHost(c->h_overflow);
     free_bvh(&c->tlas);
     free_tables(c);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -112,16 +142,21 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     if (c->wb_ready) wave_free(&c->wb);
     if (c->rs_ready) restir_free(&c->rs);
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
+// host array -> device buffer; the buffer is reallocated only when it has to grow (*cap, in elements; nullptr = always fresh)
 template <typename T>
-static rtx_status upload(T** dptr, const T* host, size_t n, cudaStream_t s) {
-    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-    RTX_CK(cudaMalloc((void**)dptr, (n ? n : 1) * sizeof(T)));
+static rtx_status upload(T** dptr, const T* host, size_t n, cudaStream_t s, size_t* cap = nullptr) {
+    const size_t want = n ? n : 1;
+    if (!*dptr || !cap || *cap < want) {
+        if (*dptr) { RTX_CK(cudaStreamSynchronize(s)); cudaFree(*dptr); *dptr = nullptr; }
+        RTX_CK(cudaMalloc((void**)dptr, want * sizeof(T)));
+        if (cap) *cap = want;
+    }
     if (n) RTX_CK(cudaMemcpyAsync(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
-    RTX_CK(cudaStreamSynchronize(s));
+    RTX_CK(cudaStreamSynchronize(s));       // the caller's (pageable) array may be reused as soon as the call returns
     return RTX_OK;
 }
 
@@ -139,7 +174,10 @@ extern "C" rtx_status rtx_upload_model(rtx_ctx* c, const rtx_vertex* v, uint32_t
     RTX_CK(build_blas(m.d_verts, nv, m.d_idx, m.n_tris, &m.bvh, c->stream));
     c->launches += 8;
     c->models.push_back(m);
+    // the per-model tables are rebuilt by the next rtx_set_instances; until then there is no valid TLAS (rendering or tracing in
+    // between returns RTX_ERR_STATE instead of handing freed tables to the kernels)
     free_tables(c);
+    c->n_instances = 0; c->tlas_models.clear();
     if (model_id_out) *model_id_out = (uint32_t)c->models.size() - 1;
     return RTX_OK;
 }
@@ -157,14 +195,14 @@ extern "C" rtx_status rtx_set_material_ids(rtx_ctx* c, const uint32_t* ids, uint
     if (!c || (!ids && n)) return fail(RTX_ERR_ARG, "rtx_set_material_ids: null argument");
     RTX_CK(cudaSetDevice(c->cfg.device));
     c->n_material_ids = n;
-    return upload(&c->d_material_ids, ids, n, c->stream);
+    return upload(&c->d_material_ids, ids, n, c->stream, &c->cap_material_ids);
 }
 
 extern "C" rtx_status rtx_set_materials(rtx_ctx* c, const rtx_material* m, uint32_t n) {
     if (!c || (!m && n)) return fail(RTX_ERR_ARG, "rtx_set_materials: null argument");
     RTX_CK(cudaSetDevice(c->cfg.device));
     c->n_materials = n;
-    return upload(&c->d_materials, m, n, c->stream);
+    return upload(&c->d_materials, m, n, c->stream, &c->cap_materials);
 }
 
 static rtx_status ensure_tables(rtx_ctx* c) {
@@ -175,7 +213,8 @@ static rtx_status ensure_tables(rtx_ctx* c) {
     for (size_t i = 0; i < n; i++) {
         const ModelRec& m = c->models[i];
         br[i].nodes = m.bvh.nodes; br[i].tris = m.bvh.prims;
-        for (int k = 0; k < 3; k++) { bb[i].lo[k] = m.bvh.lo[k]; bb[i].hi[k] = m.bvh.hi[k]; }
+        for (int k = 0; k < 3; k++) { bb[i].lo[k] = br[i].lo[k] = m.bvh.lo[k]; bb[i].hi[k] = br[i].hi[k] = m.bvh.hi[k]; }
+        br[i].pad_[0] = br[i].pad_[1] = 0.0f;
         bb[i].verts = m.d_verts; bb[i].n_verts = m.n_verts;
         mr[i].verts = m.d_verts; mr[i].idx = m.d_idx; mr[i].mat_offset = m.mat_offset; mr[i].n_tris = m.n_tris;
     }
@@ -266,18 +305,14 @@ extern "C" rtx_status rtx_set_emissive_triangles(rtx_ctx* c, const rtx_light_tri
     c->n_lights = n;
     if (n == 0) {   // an out-of-bounds read of t6 returns zeros: keep one zero record
         rtx_light_triangle z; memset(&z, 0, sizeof z);
-        return upload(&c->d_lights, &z, 1, c->stream);
+        return upload(&c->d_lights, &z, 1, c->stream, &c->cap_lights);
     }
-    return upload(&c->d_lights, l, n, c->stream);
+    return upload(&c->d_lights, l, n, c->stream, &c->cap_lights);
 }
 
 static rtx_status ensure_wave(rtx_ctx* c) {
     if (c->wb_ready) return RTX_OK;
     RTX_CK(wave_alloc(&c->wb, c->cfg.width, c->cfg.height, c->cfg.samples_per_pass));
-    if (const char* e = getenv("RTX_PARTS")) {      // tuning override of RTX_OPT_PASS_PARTS
-        const int v = atoi(e);
-        if (v >= 1 && v <= WAVE_MAX_PARTS) c->wb.parts = v;
-    }
     c->wb_ready = true;
     return RTX_OK;
 }
@@ -288,9 +323,13 @@ extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     // Pass_spat_di_v7.hlsl:407-423: any element of view differing from the previous view by more than s_bias resets the accumulation
+    // The shader compares view with prevView of the SAME constant buffer; a host that does not maintain prevView (all zeros, or a copy of
+    // view) is covered by also comparing with the view of the previous call.
     bool different = !c->have_cam;
-    if (c->have_cam)
-        for (int i = 0; i < 16; i++) if (fabsf(cam->view[i] - c->cam.view[i]) > RTX_S_BIAS) { different = true; break; }
+    for (int i = 0; i < 16 && !different; i++) {
+        if (fabsf(cam->view[i] - cam->prevView[i]) > RTX_S_BIAS) different = true;
+        if (c->have_cam && fabsf(cam->view[i] - c->cam.view[i]) > RTX_S_BIAS) different = true;
+    }
     c->cam = *cam; c->have_cam = true;
     RTX_CK(cudaMemcpyAsync(c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, c->stream));
     if (different) RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
@@ -301,13 +340,21 @@ static SceneAS make_as(rtx_ctx* c) {
     SceneAS a;
     a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
     a.one_bits = 0x3F800000u;
+    a.overflow = c->d_overflow;
+    a.num_sms = c->num_sms; a.fetch_th = c->fetch_th; a.sched = c->sched; a.waves = c->waves;
     return a;
 }
 
+// Reads the context's overflow word behind everything queued on the stream; a raised word fails the call ONCE and is cleared, so that
+// the context is usable again after the offending scene has been replaced.
 static rtx_status check_overflow(rtx_ctx* c) {
     unsigned int flag = 0;
-    RTX_CK(read_stack_overflow(&flag, c->stream));
-    if (flag) return fail(RTX_ERR_STATE, "traversal stack overflow (BVH deeper than RTX_STACK_SIZE)");
+    RTX_CK(cudaMemcpyAsync(&flag, c->d_overflow, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+    RTX_CK(cudaStreamSynchronize(c->stream));
+    if (flag) {
+        RTX_CK(cudaMemsetAsync(c->d_overflow, 0, sizeof flag, c->stream));
+        return fail(RTX_ERR_STATE, "traversal stack overflow (BVH deeper than RTX_STACK_SIZE): the results of this pass are invalid");
+    }
     return RTX_OK;
 }
 
@@ -369,6 +416,7 @@ extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
     S.width = c->cfg.width; S.height = c->cfg.height;
     const SceneAS AS = make_as(c);
     c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
+    if (c->wb.wait_before_accumulate) RTX_CK(cudaStreamWaitEvent(c->stream, c->wb.wait_before_accumulate, 0));   // a pending reduce reads gPermanentData
     RTX_CK(wave_render_pass(c->wb, S, AS, frame_index, 1, c->stream, &c->launches, &c->timing, false));     // RayGen
     RTX_CK(restir_store_pass1(c->rs, c->wb, S, c->stream, &c->launches));
     RTX_CK(restir_reuse_passes(c->rs, c->wb, S, AS, frame_index, c->stream, &c->launches));                 // RayGen2, RayGen3
@@ -427,30 +475,42 @@ extern "C" rtx_status rtx_read_output(rtx_ctx* c, uint8_t* rgba8_out) {
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     const uint32_t npx = c->cfg.width * c->cfg.height;
     if (c->copy_pending) { RTX_CK(cudaEventSynchronize(c->ev_copied)); c->copy_pending = false; }
+    if (c->comm && c->ev_reduced) RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_reduced, 0));      // the reduced buffer must be complete
     RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
     RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->stream));
-    RTX_CK(cudaStreamSynchronize(c->stream));
+    return check_overflow(c);       // synchronises the stream
+}
+
+static rtx_status ensure_side_stream(rtx_ctx* c) {
+    if (c->copy_stream) return RTX_OK;
+    RTX_CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming));
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     return RTX_OK;
 }
 
-// Resolve + read-back without stalling the caller: the D2H copy runs on a copy stream behind the resolve kernel, the next frame's
+// Resolve + read-back without stalling the caller: the D2H copy runs on a side stream behind the resolve kernel, the next frame's
 // kernels overlap it.  rtx_wait_output blocks until the image of the LAST rtx_read_output_async call is in rgba8_out.
+// With a communicator (rtx_comm_init) the root resolves the REDUCED buffer, and the resolve itself runs on the side stream behind the
+// reduce: the render stream never waits for NCCL, the next pass overlaps reduce + resolve + copy.
 extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
     if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output_async: null argument");
     RTX_CK(cudaSetDevice(c->cfg.device));
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
-    if (!c->copy_stream) {
-        RTX_CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        RTX_CK(cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming));
-        RTX_CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
-    }
+    if ((st = ensure_side_stream(c)) != RTX_OK) return st;
     const uint32_t npx = c->cfg.width * c->cfg.height;
-    if (c->copy_pending) RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));      // gOutput is rewritten by the resolve below
-    RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
-    RTX_CK(cudaEventRecord(c->ev_resolved, c->stream));
-    RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+    if (c->comm && c->comm_rank == 0 && c->wb.resolve_source == c->d_total) {
+        // side stream order: reduce(k) -> resolve(k) -> copy(k) -> reduce(k+1) ...: nothing else touches d_total or gOutput
+        RTX_CK(wave_resolve(c->wb, npx, c->copy_stream, &c->launches));
+    } else {
+        if (c->copy_pending) RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));      // gOutput is rewritten by the resolve below
+        RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
+        RTX_CK(cudaEventRecord(c->ev_resolved, c->stream));
+        RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+    }
     RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    RTX_CK(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->copy_stream));   // for rtx_wait_output
     RTX_CK(cudaEventRecord(c->ev_copied, c->copy_stream));
     c->copy_pending = true;
     return RTX_OK;
@@ -460,6 +520,7 @@ extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
 // per-pass ncclReduce) instead of this context's private partial sum.  nullptr restores the context's own buffer.
 extern "C" rtx_status rtx_set_resolve_source(rtx_ctx* c, const void* d_accum_float4) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_CK(cudaSetDevice(c->cfg.device));
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     c->wb.resolve_source = (const float4*)d_accum_float4;
@@ -469,7 +530,15 @@ extern "C" rtx_status rtx_set_resolve_source(rtx_ctx* c, const void* d_accum_flo
 extern "C" rtx_status rtx_wait_output(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
     RTX_CK(cudaSetDevice(c->cfg.device));
-    if (c->copy_pending) RTX_CK(cudaEventSynchronize(c->ev_copied));
+    if (c->copy_pending) {
+        RTX_CK(cudaEventSynchronize(c->ev_copied));
+        c->copy_pending = false;
+        if (*c->h_overflow) {
+            *c->h_overflow = 0u;
+            RTX_CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(unsigned int), c->stream));
+            return fail(RTX_ERR_STATE, "traversal stack overflow (BVH deeper than RTX_STACK_SIZE): the image just read back is invalid");
+        }
+    }
     return RTX_OK;
 }
 
@@ -547,9 +616,10 @@ extern "C" rtx_status rtx_trace(rtx_ctx* c, const rtx_ray* rays, uint32_t n, rtx
     if (!c || (!rays && n) || (!out && n)) return fail(RTX_ERR_ARG, "rtx_trace: null argument");
     if (n == 0) return RTX_OK;
     RTX_CK(cudaSetDevice(c->cfg.device));
-    void* d_rays = nullptr; void* d_hits = nullptr;
-    RTX_CK(cudaMalloc(&d_rays, (size_t)n * sizeof(rtx_ray)));
-    RTX_CK(cudaMalloc(&d_hits, (size_t)n * sizeof(rtx_hit)));
+    rtx_status rs;       // staging buffers are kept between calls and only grow
+    if ((rs = reserve((uint8_t**)&c->d_trace_rays, &c->cap_trace_rays, (size_t)n * sizeof(rtx_ray))) != RTX_OK) return rs;
+    if ((rs = reserve((uint8_t**)&c->d_trace_hits, &c->cap_trace_hits, (size_t)n * sizeof(rtx_hit))) != RTX_OK) return rs;
+    void* d_rays = c->d_trace_rays; void* d_hits = c->d_trace_hits;
     RTX_CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(rtx_ray), cudaMemcpyHostToDevice, c->stream));
     rtx_status st = trace_device_impl(c, d_rays, n, d_hits, any_hit, false);
     if (st == RTX_OK) {
@@ -557,9 +627,125 @@ extern "C" rtx_status rtx_trace(rtx_ctx* c, const rtx_ray* rays, uint32_t n, rtx
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); st = RTX_ERR_CUDA; }
     }
-    cudaFree(d_rays); cudaFree(d_hits);
     if (st != RTX_OK) return st;
     return check_overflow(c);
+}
+
+// ---- multi-GPU: the single collective of the path behind the C ABI ---------------------------------------------------
+// NCCL is bound at run time (dlopen): a process that already carries NCCL (PyTorch's bundled copy) keeps exactly one instance, a plain
+// C++ host gets the system libnccl.so.2.  Prototypes restated from nccl.h (ncclUniqueId = 128 opaque bytes, passed by value).
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false; std::string err;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // the copy the process already loaded, if any
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { api.err = std::string("NCCL not found: ") + dlerror(); return; }
+        api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+        api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(h, "ncclReduce");
+        api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.Reduce && api.CommDestroy;
+        if (!api.ok) api.err = "NCCL symbols missing";
+    });
+    return api;
+}
+rtx_status nccl_fail(const char* what, int code) {
+    NcclApi& n = nccl();
+    set_error(std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(code) : "NCCL error"));
+    return RTX_ERR_CUDA;
+}
+}  // namespace
+
+extern "C" rtx_status rtx_comm_unique_id(void* out128) {
+    if (!out128) return fail(RTX_ERR_ARG, "rtx_comm_unique_id: null argument");
+    NcclApi& n = nccl();
+    if (!n.ok) return fail(RTX_ERR_STATE, n.err.c_str());
+    NcclId id;
+    const int r = n.GetUniqueId(&id);
+    if (r != 0) return nccl_fail("ncclGetUniqueId", r);
+    memcpy(out128, &id, sizeof id);
+    return RTX_OK;
+}
+
+extern "C" rtx_status rtx_comm_destroy(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    if (!c->comm) return RTX_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    nccl().CommDestroy(c->comm);
+    c->comm = nullptr; c->comm_world = 1; c->comm_rank = 0;
+    if (c->wb_ready) { if (c->wb.resolve_source == c->d_total) c->wb.resolve_source = nullptr; c->wb.wait_before_accumulate = nullptr; }
+    if (c->d_total) { cudaFree(c->d_total); c->d_total = nullptr; }
+    if (c->ev_pass) { cudaEventDestroy(c->ev_pass); c->ev_pass = nullptr; }
+    if (c->ev_reduced) { cudaEventDestroy(c->ev_reduced); c->ev_reduced = nullptr; }
+    return RTX_OK;
+}
+
+// Collective over all ranks of the job (one context per GPU, one process or thread per context).  unique_id128 comes from
+// rtx_comm_unique_id on one rank and reaches the others through the host's own channel (a file, MPI, torch.distributed ...).
+extern "C" rtx_status rtx_comm_init(rtx_ctx* c, const void* unique_id128, int rank, int world) {
+    if (!c || !unique_id128 || world < 1 || rank < 0 || rank >= world) return fail(RTX_ERR_ARG, "rtx_comm_init: bad argument");
+    if (c->comm) return fail(RTX_ERR_STATE, "rtx_comm_init: the context already has a communicator");
+    NcclApi& n = nccl();
+    if (!n.ok) return fail(RTX_ERR_STATE, n.err.c_str());
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    rtx_status st;
+    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    if ((st = ensure_side_stream(c)) != RTX_OK) return st;
+    NcclId id; memcpy(&id, unique_id128, sizeof id);
+    const int r = n.CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) { c->comm = nullptr; return nccl_fail("ncclCommInitRank", r); }
+    c->comm_rank = rank; c->comm_world = world;
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_pass, cudaEventDisableTiming));
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_reduced, cudaEventDisableTiming));
+    if (rank == 0) {
+        const size_t bytes = (size_t)c->cfg.width * c->cfg.height * 16;
+        RTX_CK(cudaMalloc((void**)&c->d_total, bytes));
+        RTX_CK(cudaMemsetAsync(c->d_total, 0, bytes, c->stream));
+        c->wb.resolve_source = c->d_total;          // "rank 0 then runs F20's divide + sRGB" on the sum
+    }
+    return RTX_OK;
+}
+
+// One ncclReduce(sum, fp32, W*H*4, root 0) straight from gPermanentData into the root's reduced buffer (no staging copy), queued on the
+// side stream behind everything rendered so far.  The render stream goes on immediately; only the NEXT accumulation (the last kernel of
+// the next pass, which rewrites gPermanentData) waits for the reduce to have read it.
+extern "C" rtx_status rtx_reduce_accum(rtx_ctx* c) {
+    if (!c) return fail(RTX_ERR_ARG, "null context");
+    if (!c->comm) return fail(RTX_ERR_STATE, "rtx_reduce_accum: no communicator (rtx_comm_init)");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_CK(cudaEventRecord(c->ev_pass, c->stream));
+    RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_pass, 0));
+    const size_t count = (size_t)c->cfg.width * c->cfg.height * 4;
+    const int r = nccl().Reduce(c->wb.accum, c->comm_rank == 0 ? (void*)c->d_total : (void*)c->wb.accum, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0,
+                                c->comm, c->copy_stream);
+    if (r != 0) return nccl_fail("ncclReduce", r);
+    RTX_CK(cudaEventRecord(c->ev_reduced, c->copy_stream));
+    c->wb.wait_before_accumulate = c->ev_reduced;
+    return RTX_OK;
+}
+
+// the root's reduced accumulation buffer (float4 per pixel), complete up to the last rtx_reduce_accum
+extern "C" rtx_status rtx_read_reduced_accum(rtx_ctx* c, float* host_out) {
+    if (!c || !host_out) return fail(RTX_ERR_ARG, "rtx_read_reduced_accum: null argument");
+    if (!c->comm || c->comm_rank != 0) return fail(RTX_ERR_STATE, "rtx_read_reduced_accum: only on rank 0 of a communicator");
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_CK(cudaMemcpyAsync(host_out, c->d_total, (size_t)c->cfg.width * c->cfg.height * 16, cudaMemcpyDeviceToHost, c->copy_stream));
+    RTX_CK(cudaStreamSynchronize(c->copy_stream));
+    return RTX_OK;
 }
 
 extern "C" rtx_status rtx_get_counters(rtx_ctx* c, rtx_counters* out) {
@@ -633,6 +819,9 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
         if (value < 1u || value > (uint32_t)WAVE_MAX_PARTS) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PASS_PARTS must be 1..4");
         c->wb.parts = (int)value;
     }
+    else if (option == RTX_OPT_TRACE_FETCH_TH) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_FETCH_TH must be 0..32"); c->fetch_th = (int)value; }
+    else if (option == RTX_OPT_TRACE_SCHED) c->sched = (int)(value & 0xffffffu);
+    else if (option == RTX_OPT_TRACE_WAVES) { if (value > 8u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_WAVES must be 0..8"); c->waves = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;
 }

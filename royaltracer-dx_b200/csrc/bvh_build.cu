@@ -16,7 +16,6 @@
 //      in the node's local power-of-two grid.
 // Boxes are padded by 2^-15 of the model's coordinate scale so that the (bit-exact, contract-defining)
 // ray/triangle test never reports a hit the conservative box tests culled.
-#include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -30,7 +29,11 @@ namespace rtx {
         if (e__ != cudaSuccess) return e__;  \
     } while (0)
 
-#define MAX_LEAF 3
+// primitives per leaf child: 3 triangles in a BLAS; ONE instance in the TLAS, so that every instance sits behind its own quantised box and a
+// ray only enters the instances whose boxes it hits (with up to 3 instances per leaf box the C3 scene entered 2.69 instances per ray, and the
+// one-node TLAS of C2 put both instances behind one box: 2.000)
+#define MAX_LEAF 3          // the largest leaf any instantiation uses (array bounds)
+#define SINGLE_NODE_MAX 8   // n <= 8 primitives: one node, one primitive per child slot
 
 struct BuildCounters {
     unsigned int nodes, prims, tasks_out, hier_nodes;
@@ -198,6 +201,7 @@ __device__ __forceinline__ void node_costs(const Hier& H, int id, float out[7]) 
     }
 }
 
+template <int MAXL>
 __global__ void k_ploc_merge(const int* __restrict__ clusters, int nc, const int* __restrict__ nn, Hier H, BuildCounters* ctr,
                              int* __restrict__ out_val, int* __restrict__ valid) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,7 +237,7 @@ __global__ void k_ploc_merge(const int* __restrict__ clusters, int nc, const int
             }
             float* C = H.cost + (size_t)k * 7;
             unsigned char* D = H.dec + (size_t)k * 8;
-            const float c_leaf = (P <= MAX_LEAF) ? A * (float)P * C_PRIM : INFINITY;
+            const float c_leaf = (P <= MAXL) ? A * (float)P * C_PRIM : INFINITY;
             const float c_inner = A * C_NODE + dist[8];
             C[0] = fminf(c_leaf, c_inner);
             D[0] = (c_leaf <= c_inner) ? 1 : 0;
@@ -415,7 +419,7 @@ __global__ void k_collapse(CollapseArgs A, Source src, const uint2* __restrict__
     emit_node<PRIM_F4, Source>(A, src, cid, leaf, cnt, H.nlo[root], H.nhi[root], task.y, tasks_out);
 }
 
-// n <= MAX_LEAF: one node, one leaf child holding everything
+// n <= SINGLE_NODE_MAX: one node, primitive i alone in child slot i behind its own quantised box
 template <int PRIM_F4, typename Source>
 __global__ void k_single_node(Source src, const float4* __restrict__ plo, const float4* __restrict__ phi, int n, uint4* out_nodes,
                               float4* out_prims, BuildCounters* c) {
@@ -423,19 +427,38 @@ __global__ void k_single_node(Source src, const float4* __restrict__ plo, const 
     float s = 0.0f;
     for (int k = 0; k < 6; k++) s = fmaxf(s, fabsf(dec_f(c->bounds[k])));
     const float pad = s * 3.0517578125e-5f + 1e-30f;
-    float4 l = make_float4(INFINITY, INFINITY, INFINITY, 0), h = make_float4(-INFINITY, -INFINITY, -INFINITY, 0);
+    float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < n; i++) {
-        l.x = fminf(l.x, plo[i].x - pad); l.y = fminf(l.y, plo[i].y - pad); l.z = fminf(l.z, plo[i].z - pad);
-        h.x = fmaxf(h.x, phi[i].x + pad); h.y = fmaxf(h.y, phi[i].y + pad); h.z = fmaxf(h.z, phi[i].z + pad);
+        const float4 a = plo[i], b = phi[i];
+        l[0] = fminf(l[0], a.x - pad); l[1] = fminf(l[1], a.y - pad); l[2] = fminf(l[2], a.z - pad);
+        h[0] = fmaxf(h[0], b.x + pad); h[1] = fmaxf(h[1], b.y + pad); h[2] = fmaxf(h[2], b.z + pad);
     }
-    const int ex = exp_for_extent(h.x - l.x), ey = exp_for_extent(h.y - l.y), ez = exp_for_extent(h.z - l.z);
-    const unsigned W0 = (1u << n) - 1u;
-    for (int i = 0; i < n; i++) src.write(out_prims + (size_t)i * PRIM_F4, (uint32_t)i);
-    out_nodes[0] = make_uint4(__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), (unsigned)ex | ((unsigned)ey << 8) | ((unsigned)ez << 16));
-    out_nodes[1] = make_uint4(0u, 0u, W0, 0u);
-    out_nodes[2] = make_uint4(0u, 0u, 0u, 0u);               // qlo_x, qlo_y = 0
-    out_nodes[3] = make_uint4(0u, 0u, 0xffu, 0u);            // qlo_z = 0, qhi_x[0] = 255
-    out_nodes[4] = make_uint4(0xffu, 0u, 0xffu, 0u);         // qhi_y[0] = qhi_z[0] = 255
+    int e[3]; float sv[3];
+    for (int a = 0; a < 3; a++) { e[a] = exp_for_extent(h[a] - l[a]); sv[a] = __uint_as_float((unsigned)e[a] << 23); }
+    unsigned char qlo[3][8], qhi[3][8];
+    unsigned W = 0;
+    for (int i = 0; i < 8; i++) {
+        for (int a = 0; a < 3; a++) { qlo[a][i] = 0; qhi[a][i] = 0; }
+        if (i >= n) continue;
+        W |= 1u << (3 * i);
+        src.write(out_prims + (size_t)i * PRIM_F4, (uint32_t)i);
+        const float4 a4 = plo[i], b4 = phi[i];
+        const float lov[3] = {a4.x - pad, a4.y - pad, a4.z - pad}, hiv[3] = {b4.x + pad, b4.y + pad, b4.z + pad};
+        for (int a = 0; a < 3; a++) {
+            int ql = (int)floorf((lov[a] - l[a]) / sv[a]);
+            int qh = (int)ceilf((hiv[a] - l[a]) / sv[a]);
+            ql = max(0, min(255, ql)); qh = max(0, min(255, qh));
+            while (ql > 0 && l[a] + (float)ql * sv[a] > lov[a]) ql--;
+            while (qh < 255 && l[a] + (float)qh * sv[a] < hiv[a]) qh++;
+            qlo[a][i] = (unsigned char)ql; qhi[a][i] = (unsigned char)qh;
+        }
+    }
+    auto pack4 = [](const unsigned char* b) { return (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24); };
+    out_nodes[0] = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), (unsigned)e[0] | ((unsigned)e[1] << 8) | ((unsigned)e[2] << 16));
+    out_nodes[1] = make_uint4(0u, 0u, W, 0u);
+    out_nodes[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    out_nodes[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    out_nodes[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
     c->nodes = 1; c->prims = (unsigned)n;
 }
 
@@ -445,12 +468,12 @@ struct Scratch {
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
 };
 
-template <int PRIM_F4, typename Source>
+template <int PRIM_F4, int MAXL, typename Source>
 static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint32_t n, Source src, BuildCounters* d_ctr, Bvh8* out,
                                  cudaStream_t stream) {
     const int TB = 256;
     auto grid = [&](size_t k) { return (unsigned)((k + TB - 1) / TB); };
-    const uint32_t max_nodes = n <= MAX_LEAF ? 1u : n;
+    const uint32_t max_nodes = n <= SINGLE_NODE_MAX ? 1u : n;
     Scratch nodes_s, prims_s;
     CKE(nodes_s.alloc((size_t)max_nodes * 80));
     CKE(prims_s.alloc((size_t)n * PRIM_F4 * 16));
@@ -459,7 +482,7 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
     BuildCounters h_ctr;
     out->sah_cost = 0.0f;
 
-    if (n <= MAX_LEAF) {
+    if (n <= SINGLE_NODE_MAX) {
         out->n_levels = 1; out->level_start[0] = 0; out->level_start[1] = 1;
         k_single_node<PRIM_F4, Source><<<1, 32, 0, stream>>>(src, d_plo, d_phi, (int)n, d_nodes, d_prims, d_ctr);
     } else {
@@ -490,7 +513,7 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
         int nc = (int)n;
         while (nc > 1) {
             k_ploc_nn<<<grid(nc), TB, 0, stream>>>(cin, nc, H.nlo, H.nhi, (int*)nn_s.p);
-            k_ploc_merge<<<grid(nc), TB, 0, stream>>>(cin, nc, (int*)nn_s.p, H, d_ctr, (int*)val_s.p, (int*)valid_s.p);
+            k_ploc_merge<MAXL><<<grid(nc), TB, 0, stream>>>(cin, nc, (int*)nn_s.p, H, d_ctr, (int*)val_s.p, (int*)valid_s.p);
             CKE(cub::DeviceScan::ExclusiveSum(tmp2_s.p, tmp2_bytes, (int*)valid_s.p, (int*)pos_s.p, nc, stream));
             k_ploc_compact<<<grid(nc), TB, 0, stream>>>((int*)val_s.p, (int*)valid_s.p, (int*)pos_s.p, nc, cout);
             CKE(cudaMemcpyAsync(&h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, stream));
@@ -555,7 +578,7 @@ cudaError_t build_blas(const uint8_t* d_vertices, uint32_t n_vertices, const uin
     k_init_counters<<<1, 1, 0, stream>>>((BuildCounters*)ctr.p);
     if (n_tris) k_tri_boxes<<<(n_tris + 255) / 256, 256, 0, stream>>>(d_vertices, d_indices, n_tris, (float4*)plo.p, (float4*)phi.p, (BuildCounters*)ctr.p);
     TriSource src{d_vertices, d_indices};
-    cudaError_t e = build_generic<3, TriSource>((float4*)plo.p, (float4*)phi.p, n_tris, src, (BuildCounters*)ctr.p, out, stream);
+    cudaError_t e = build_generic<3, 3, TriSource>((float4*)plo.p, (float4*)phi.p, n_tris, src, (BuildCounters*)ctr.p, out, stream);
     if (e == cudaSuccess) {
         cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&out->build_ms, e0, e1);
@@ -571,7 +594,7 @@ cudaError_t build_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
     k_init_counters<<<1, 1, 0, stream>>>((BuildCounters*)ctr.p);
     if (n_instances) k_box_bounds<<<(n_instances + 255) / 256, 256, 0, stream>>>(d_box_lo, d_box_hi, n_instances, (BuildCounters*)ctr.p);
     RecSource src{d_inst_recs};
-    return build_generic<4, RecSource>(d_box_lo, d_box_hi, n_instances, src, (BuildCounters*)ctr.p, out, stream);
+    return build_generic<4, 1, RecSource>(d_box_lo, d_box_hi, n_instances, src, (BuildCounters*)ctr.p, out, stream);
 }
 
 // ---- TLAS refit ------------------------------------------------------------------------------------------------------
@@ -667,7 +690,7 @@ cudaError_t refit_tlas(const float4* d_inst_recs, const float4* d_box_lo, const 
     return cudaGetLastError();
 }
 
-bool tlas_fits_one_node(uint32_t n_instances) { return n_instances >= 1u && n_instances <= (uint32_t)MAX_LEAF; }
+bool tlas_fits_one_node(uint32_t n_instances) { return n_instances >= 1u && n_instances <= (uint32_t)SINGLE_NODE_MAX; }
 
 cudaError_t update_tlas_one_node(const float4* d_inst_recs, const float4* d_box_lo, const float4* d_box_hi, uint32_t n_instances, Bvh8* out,
                                  void* d_ctr, cudaStream_t stream) {
@@ -731,14 +754,14 @@ __global__ void k_tight_init(uint32_t n, unsigned int* __restrict__ acc) {
 __global__ void __launch_bounds__(256)
 k_instance_tight_boxes(const rtx_instance_desc* __restrict__ descs, const BlasBounds* __restrict__ bounds, uint32_t n,
                        unsigned int* __restrict__ acc) {
-    const uint32_t i = blockIdx.y;
+    const uint32_t i = blockIdx.x;          // instance in grid.x (up to 2^31-1), vertex chunk in grid.y
     if (i >= n) return;
     const BlasBounds b = bounds[(uint32_t)descs[i].blas];
-    if (blockIdx.x * 256u >= b.n_verts) return;
+    if (blockIdx.y * 256u >= b.n_verts) return;
     float t[3][4];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) t[r][c] = descs[i].transform[r][c];
     float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t v = blockIdx.x * 256u + threadIdx.x; v < b.n_verts; v += gridDim.x * 256u) {
+    for (uint32_t v = blockIdx.y * 256u + threadIdx.x; v < b.n_verts; v += gridDim.y * 256u) {
         const float* p = reinterpret_cast<const float*>(b.verts + (size_t)v * 28);
         const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
         for (int r = 0; r < 3; r++) {
@@ -778,11 +801,9 @@ cudaError_t launch_instance_records(const rtx_instance_desc* d_descs, const rtx_
                                     uint32_t n, float4* d_recs, float4* d_lo, float4* d_hi, unsigned int* d_scratch6, cudaStream_t stream) {
     if (n) {
         k_instance_records<<<(n + 127) / 128, 128, 0, stream>>>(d_descs, d_props, d_bounds, n, d_recs, d_lo, d_hi);
-        static int tight = -1;
-        if (tight < 0) { const char* e = getenv("RTX_TIGHT_INSTANCE_BOXES"); tight = e ? atoi(e) : 1; }
-        if (tight && d_scratch6) {
+        if (d_scratch6) {
             k_tight_init<<<(6 * n + 255) / 256, 256, 0, stream>>>(n, d_scratch6);
-            k_instance_tight_boxes<<<dim3(TIGHT_CHUNKS, n), 256, 0, stream>>>(d_descs, d_bounds, n, d_scratch6);
+            k_instance_tight_boxes<<<dim3(n, TIGHT_CHUNKS), 256, 0, stream>>>(d_descs, d_bounds, n, d_scratch6);
             k_tight_finish<<<(n + 255) / 256, 256, 0, stream>>>(n, d_scratch6, d_lo, d_hi);
         }
     }

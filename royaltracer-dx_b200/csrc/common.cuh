@@ -40,9 +40,11 @@ void set_error(const std::string& s);
 // children are stored densely from child_base in slot order.  An empty slot has neither.
 // 48-B triangle = 3 x float4: (v0.xyz, bits(prim)), (v1.xyz, 0), (v2.xyz, 0).
 // 64-B instance record = 4 x float4: rows 0..2 of world->object (from objectToWorldInverse), (blas, instance, 0, 0).
-struct BlasRef {
+struct alignas(16) BlasRef {
     const uint4* nodes;
     const float4* tris;
+    float lo[3], hi[3];   // padded object-space bounds of the model: an instance whose object-space ray misses them is not entered
+    float pad_[2];
 };
 
 struct SceneAS {
@@ -53,6 +55,12 @@ struct SceneAS {
     uint32_t one_bits;    // 0x3F800000, passed as a run-time value: keeps it in a register so that the byte->float PRMT of the node test takes its
                           // selector as an immediate (with the constant folded in, ptxas re-materialised a selector register per PRMT: 43 extra
                           // IMAD.U32 per node test)
+    unsigned int* overflow;   // per-context word raised when a traversal stack overflows (checked and cleared by the API, api.cu check_overflow)
+    // launch tuning of the traversal kernels (rtx_set_option RTX_OPT_TRACE_*; defaults = the measured optimum, trace.cu)
+    int num_sms;          // of the context's device
+    int fetch_th;         // refill the warp's idle lanes when fewer than this many lanes are still traversing
+    int sched;            // th_tri | th_inst << 8 | th_node << 16 (phase scheduling, traverse.cuh)
+    int waves;            // persistent grid = num_sms * resident CTAs * waves
 };
 
 // Ray queue entry layout (SoA): o_tmin[j] = (o.xyz, tmin), d_tmax[j] = (d.xyz, tmax).

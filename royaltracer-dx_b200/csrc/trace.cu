@@ -5,8 +5,6 @@
 // idle lanes as soon as fewer than FETCH_THRESHOLD lanes are still traversing, so long-running incoherent rays do
 // not strand the other 31 lanes (B200 has no RT cores; warp-execution efficiency is the second-order term after
 // memory latency — see DESIGN.md §Kernels).
-#include <stdlib.h>
-
 #include <algorithm>
 using std::max;
 
@@ -21,13 +19,9 @@ namespace rtx {
 #ifndef RTX_TRACE_MINB
 #define RTX_TRACE_MINB (1024 / TRACE_BLOCK)   // resident CTAs per SM the register budget is set for (64 registers, 1024 threads)
 #endif
-#define FETCH_THRESHOLD 20     // refill the warp's idle lanes when fewer than this many lanes are still traversing
-#ifndef RTX_FETCH_CHUNK
-#define RTX_FETCH_CHUNK 32     // rays a warp claims from the global cursor with one atomic
+#ifndef FETCH_THRESHOLD
+#define FETCH_THRESHOLD 24     // refill the warp's idle lanes when fewer than this many lanes are still traversing
 #endif
-#ifndef RTX_FETCH_MIN
-#define RTX_FETCH_MIN 32u      // guided self-scheduling (claims shrinking to this many rays as the queue runs out) measured slower than
-#endif                         // constant claims: 8.94 against 8.82 ms per C2 pass with a minimum of 4; kept as a build knob
 #ifndef RTX_SCHED_DEFAULT
 #define RTX_SCHED_DEFAULT 0x060808   // th_tri | th_inst << 8 | th_node << 16: run the triangle (instance) phase when >= th lanes are parked,
 #endif                               // or whenever fewer than th_node lanes have node work left (sweep: profiles/r01_s4_sched_sweep.txt)
@@ -51,11 +45,10 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     const int th_tri = sched & 0xff, th_inst = (sched >> 8) & 0xff, th_node = (sched >> 16) & 0xff;
     bool active = false;
     bool exhausted = (S.n_instances == 0u);
-    // the warp's private pool of claimed rays [pool_next, pool_end) and one chunk claimed ahead of need (its atomic
-    // is in flight while the warp traverses): all warp-uniform
-    uint32_t pool_next = 0, pool_end = 0, ahead = 0, ahead_sz = 0, claim_sz = RTX_FETCH_CHUNK;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    bool have_ahead = false;
+    // Ray claims: a warp claims EXACTLY the rays its idle lanes need, when they need them (one atomic per refill).  Claiming 32 at a time
+    // plus one chunk ahead (to hide the atomic's latency) left ~48 unstarted rays in every warp's private pool when the cursor ran out:
+    // at 1080p 11 % of a queue sat in private pools while other warps already idled ("queue found drained" 434 .. 547 us of a 638 us
+    // launch, profiles/r01_s4_trace_timeline.txt).  Exact claims: closest-hit launches -3.3 % on C2, -4.6 % on C3 (profiles/r02_*).
     unsigned int c_nodes = 0, c_tris = 0, c_insts = 0;
 
 #ifdef RTX_TRACE_TIMELINE
@@ -63,43 +56,23 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_t0));
 #endif
     for (;;) {
-        // ---- refill idle lanes from the pool
+        // ---- refill idle lanes from the queue
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted) {
-            uint32_t need = (uint32_t)__popc(idle);
-            const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
-            uint32_t take = min(need, pool_end - pool_next);
-            uint32_t mine = pool_next + rank;
-            pool_next += take;
-            if (take < need) {                                   // pool empty: switch to the chunk claimed ahead (or claim one now)
-                const uint32_t sz = have_ahead ? ahead_sz : claim_sz;
-                if (!have_ahead) { if (lane == 0) ahead = atomicAdd(cursor, (unsigned)sz); }
-                const uint32_t base = __shfl_sync(0xffffffffu, ahead, 0);
-                have_ahead = false;
-                if (base >= n) {
-                    exhausted = true; pool_next = pool_end = 0; need = take;
+            const uint32_t need = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + need >= n) {
+                exhausted = true;                                // this claim took the last rays (or came too late)
 #ifdef RTX_TRACE_TIMELINE
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_tex));
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_tex));
 #endif
-                }
-                else {
-                    pool_end = min(base + sz, n);
-                    // optional guided self-scheduling (RTX_FETCH_MIN < RTX_FETCH_CHUNK): the claims shrink as the queue runs out
-                    claim_sz = min((uint32_t)RTX_FETCH_CHUNK, max(RTX_FETCH_MIN, (n - pool_end) / (2u * n_warps)));
-                    const uint32_t take2 = min(need - take, pool_end - base);
-                    if (rank >= take) mine = base + (rank - take);
-                    pool_next = base + take2;
-                    need = take + take2;
-                }
             }
-            if (!active && rank < need) {
+            const uint32_t mine = base + (uint32_t)__popc(idle & lt_mask);
+            if (!active && mine < n) {
                 trav_init(T, C, S, __ldg(o_tmin + mine), __ldg(d_tmax + mine), mine);
                 active = true;
-            }
-            if (!exhausted && !have_ahead && pool_end - pool_next < 32u) {   // claim the next chunk now, use it later
-                if (lane == 0) ahead = atomicAdd(cursor, (unsigned)claim_sz);
-                ahead_sz = claim_sz;
-                have_ahead = true;
             }
         }
         const unsigned act = __ballot_sync(0xffffffffu, active);
@@ -128,10 +101,14 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
                 else done = trav_pop(T, C, S, stack);                                                          \
                 if (done) {                                                                                    \
                     active = false;                                                                            \
-                    const uint32_t j = __float_as_uint(C.wo->w);                                               \
-                    if (!ANY_HIT) { const float4 h = *C.hit; hit_a[j] = make_float4(T.ht, h.x, h.y, h.z); }    \
-                    hit_inst[j] = T.hinst;                                                                     \
+                    RTX_WRITE_RESULT                                                                           \
                 }                                                                                              \
+            }
+#define RTX_WRITE_RESULT                                                                                       \
+            {                                                                                                  \
+                const uint32_t j = __float_as_uint(C.wo->w);                                                   \
+                if (!ANY_HIT) { const float4 h = *C.hit; hit_a[j] = make_float4(T.ht, h.x, h.y, h.z); }        \
+                hit_inst[j] = T.hinst;                                                                         \
             }
             if (pend == PEND_TRI) {
                 if (do_tri) {
@@ -141,13 +118,18 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
                 }
             } else if (pend == PEND_INST) {
                 if (do_inst) {
-                    trav_enter_instance<STATS>(T, C, S, stack, leaf_base, leaf_bits, leaf_W, &c_insts);
-                    pend = PEND_NONE;
+                    const bool entered = trav_enter_instance<ANY_HIT, STATS>(T, C, S, stack, leaf_base, leaf_bits, leaf_W, &c_insts);
+                    if (entered) pend = PEND_NONE;
+                    else if (leaf_bits == 0u) {          // every instance of the group rejected: back to the node work (pop if the group is used up)
+                        pend = PEND_NONE;
+                        RTX_FINISH(false)
+                    }                                    // else: stays parked with the remaining instance leaves
                 }
             } else if (active) {
                 RTX_FINISH(false)
             }
 #undef RTX_FINISH
+#undef RTX_WRITE_RESULT
 #ifdef RTX_TRACE_TIMELINE
             tl_steps++; if (exhausted) tl_drain_steps++;
 #endif
@@ -169,6 +151,12 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
             hit_inst[i] = 0xFFFFFFFFu;
         }
     }
+    // the last CTA to finish leaves the cursor at 0 for the next launch (cursor[1] counts finished CTAs and wraps to 0 by itself)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicInc(cursor + 1, gridDim.x - 1u) == gridDim.x - 1u) { cursor[0] = 0u; __threadfence(); }
+    }
     if (STATS) {
         atomicAdd(&st->nodes, (unsigned long long)c_nodes);
         atomicAdd(&st->tris, (unsigned long long)c_tris);
@@ -176,32 +164,16 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     }
 }
 
-static int g_num_sms = 0;
-
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
-
 cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
                          unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
                          cudaStream_t stream, int grid_share) {
-    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), stream);
-    if (e != cudaSuccess) return e;
-    static int fetch_th = -1, waves = -1, sched = 0;
-    if (fetch_th < 0) {   // tuning knobs (defaults are the measured optimum on C2, see profiles/)
-        const char* e = getenv("RTX_FETCH_TH"); fetch_th = e ? atoi(e) : FETCH_THRESHOLD;
-        e = getenv("RTX_SCHED"); sched = e ? (int)strtol(e, nullptr, 0) : RTX_SCHED_DEFAULT;
-        e = getenv("RTX_TRACE_WAVES"); waves = e ? atoi(e) : 1;
-    }
+    // `cursor` = two words, both 0 between launches: [0] the ray cursor, [1] the count of finished CTAs; the last CTA of a launch
+    // resets [0] (and atomicInc wraps [1]), so no memset precedes the launch.
+    const int sms = S.num_sms > 0 ? S.num_sms : 148;
+    const int fetch_th = S.fetch_th > 0 ? S.fetch_th : FETCH_THRESHOLD, sched = S.sched ? S.sched : RTX_SCHED_DEFAULT, waves = S.waves > 0 ? S.waves : 1;
     // persistent: the resident CTAs of the machine (x waves), or this launch's share of them when several traversals run concurrently
     // (wave_render_pass: the parts' kernels are then co-resident and one part's drain phase overlaps the other's work)
-    const int grid = max(num_sms(), num_sms() * RTX_TRACE_MINB * waves / max(grid_share, 1));
+    const int grid = max(sms, sms * RTX_TRACE_MINB * waves / max(grid_share, 1));
     if (stats) {
         if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched);
         else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched);
@@ -210,12 +182,6 @@ cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d
         else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched);
     }
     return cudaGetLastError();
-}
-
-cudaError_t read_stack_overflow(unsigned int* host_flag, cudaStream_t stream) {
-    cudaError_t e = cudaMemcpyFromSymbolAsync(host_flag, g_stack_overflow, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(stream);
 }
 
 }  // namespace rtx

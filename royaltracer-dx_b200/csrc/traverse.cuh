@@ -23,12 +23,13 @@
 namespace rtx {
 
 #define RTX_STACK_SIZE 40
-// A full stack drops the entry (wrong image, no memory fault) and raises g_stack_overflow, which every API call checks.
-__device__ unsigned int g_stack_overflow;
+// A full stack drops the entry (no memory fault) and raises the context's overflow word (SceneAS::overflow): every API call that hands
+// results to the caller checks it, fails with RTX_ERR_STATE and clears it (api.cu check_overflow).  rtx_set_instances also rejects a
+// TLAS + BLAS pair whose level counts could exceed the stack before anything is traced.
 #define RTX_PUSH(v)                                                   \
     do {                                                              \
         if (sp < RTX_STACK_SIZE) stack[sp++] = (v);                   \
-        else g_stack_overflow = 1u;                                   \
+        else *S.overflow = 1u;                                        \
     } while (0)
 
 #ifndef RTX_CONV_MODE
@@ -367,28 +368,21 @@ __device__ __forceinline__ bool trav_tris(Trav& T, const TravCold& C, uint32_t l
     return false;
 }
 
-// (I)
-template <bool STATS>
-__device__ __forceinline__ void trav_enter_instance(Trav& T, const TravCold& C, const SceneAS& S, uint2* stack, uint32_t leaf_base,
-                                                    uint32_t leaf_bits, uint32_t leaf_W, unsigned int* c_insts) {
-    uint2 G = T.G;
-    int sp = T.sp;
+// (I)  Takes the next instance leaf of the parked group.  The ray is transformed into the instance's object space and first tested against
+// the model's object-space bounds (the world box of a rotated instance is up to sqrt(3) larger per axis than the geometry): on a miss the
+// lane stays where it is (returns false; leaf_bits holds what is left of the group) and saves the shear set-up (an IEEE divide), the fetch
+// and test of the BLAS root node and a stack round trip.
+template <bool ANY_HIT, bool STATS>
+__device__ __forceinline__ bool trav_enter_instance(Trav& T, const TravCold& C, const SceneAS& S, uint2* stack, uint32_t leaf_base,
+                                                    uint32_t& leaf_bits, uint32_t leaf_W, unsigned int* c_insts) {
     const uint32_t bit = 31u - __clz(leaf_bits);
     leaf_bits &= ~(1u << bit);
     const float4* ip = T.prims + (size_t)(leaf_base + leaf_prim_index(leaf_W, bit)) * 4;
     const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
     if (STATS) (*c_insts)++;
-    if (leaf_bits) {                       // park the other instance leaves with their bits made dense
-        uint32_t dense = 0u;
-        do {
-            const uint32_t b = 31u - __clz(leaf_bits);
-            leaf_bits &= ~(1u << b);
-            dense |= 1u << leaf_prim_index(leaf_W, b);
-        } while (leaf_bits);
-        RTX_PUSH(make_uint2(leaf_base, dense));
-    }
-    if (G.y & 0xff000000u) RTX_PUSH(G);
-    T.blas_sp = sp;
+    const BlasRef* bp = S.blas + __float_as_uint(r3.x);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+    const float2 b2 = __ldg(reinterpret_cast<const float2*>(bp) + 4);
     const float4 wo = *C.wo, wd = *C.wd;
     const float tox = ((r0.x * wo.x + r0.y * wo.y) + r0.z * wo.z) + r0.w * 1.0f;
     const float toy = ((r1.x * wo.x + r1.y * wo.y) + r1.z * wo.z) + r1.w * 1.0f;
@@ -398,13 +392,37 @@ __device__ __forceinline__ void trav_enter_instance(Trav& T, const TravCold& C, 
     const float tdz = ((r2.x * wd.x + r2.y * wd.y) + r2.z * wd.z) + r2.w * 0.0f;
     RaySpace r;
     setup_box(r, tox, toy, toz, tdx, tdy, tdz);
+    {   // slab test against (lo, hi) = (b1.x, b1.y, b1.z), (b1.w, b2.x, b2.y); conservative like the node test (approximate reciprocal
+        // against bounds padded by 2^-15 of the model's scale)
+        const float ax = (b1.x - tox) * r.ix, bx = (b1.w - tox) * r.ix;
+        const float ay = (b1.y - toy) * r.iy, by = (b2.x - toy) * r.iy;
+        const float az = (b1.z - toz) * r.iz, bz = (b2.y - toz) * r.iz;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), T.tmin));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), ANY_HIT ? T.tmax : T.ht));
+        // widened by a relative 2^-20 on either side for the rounding of the reciprocal and the products (a few 2^-23 of t)
+        if (!(tn * 0.999999f <= tf * 1.000001f) && !(tn <= tf)) return false;
+    }
+    uint2 G = T.G;
+    int sp = T.sp;
+    if (leaf_bits) {                       // park the other instance leaves with their bits made dense
+        uint32_t dense = 0u, lb = leaf_bits;
+        do {
+            const uint32_t b = 31u - __clz(lb);
+            lb &= ~(1u << b);
+            dense |= 1u << leaf_prim_index(leaf_W, b);
+        } while (lb);
+        RTX_PUSH(make_uint2(leaf_base, dense));
+    }
+    if (G.y & 0xff000000u) RTX_PUSH(G);
+    T.blas_sp = sp;
     setup_tri(r, tdx, tdy, tdz);
     store_box(T, r);
     *C.tri = make_float4(r.Sx, r.Sy, r.Sz, __uint_as_float(r.ksel));
-    const BlasRef br = S.blas[__float_as_uint(r3.x)];
-    T.nodes = br.nodes; T.prims = br.tris;
+    T.nodes = reinterpret_cast<const uint4*>(__float_as_uint(b0.x) | ((unsigned long long)__float_as_uint(b0.y) << 32));
+    T.prims = reinterpret_cast<const float4*>(__float_as_uint(b0.z) | ((unsigned long long)__float_as_uint(b0.w) << 32));
     T.cur_inst = __float_as_uint(r3.y);
     T.G = make_uint2(0u, 0x80000000u); T.sp = sp;
+    return true;
 }
 
 // (P) pops the next group when the current one is used up; returns true when the ray is finished

@@ -572,6 +572,7 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMalloc((void**)&B->vis_gi, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->counts, WAVE_MAX_PARTS * 128 * 4));
     CKE(cudaMalloc((void**)&B->cursor, WAVE_MAX_PARTS * 16));
+    CKE(cudaMemset(B->cursor, 0, WAVE_MAX_PARTS * 16));      // launch_trace keeps the cursor words at zero between launches
     CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
     CKE(cudaMemset(B->ray_counters, 0, 64));
     CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
@@ -735,6 +736,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         CKE(cudaStreamWaitEvent(stream, B.ev_join[h - 1], 0));
     }
     if (accumulate) {       // E0: the pass's samples go straight to gPermanentData; the ReSTIR frame accumulates after RayGen3
+        if (B.wait_before_accumulate) CKE(cudaStreamWaitEvent(stream, B.wait_before_accumulate, 0));
         CKE(mark(SK_ACCUMULATE));
         k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
     }

@@ -47,6 +47,7 @@ struct WaveBuffers {
     unsigned int* cursor = nullptr;    // 4 words per part (launch_trace)
     unsigned long long* ray_counters = nullptr;   // [0] closest, [1] shadow, [2] paths
     const float4* resolve_source = nullptr;   // rtx_set_resolve_source: an external accumulation buffer (the multi-GPU sum) to resolve instead
+    cudaEvent_t wait_before_accumulate = nullptr;   // multi-GPU: the pending reduce of gPermanentData (k_accumulate rewrites it)
     float4* accum = nullptr;           // gPermanentData
     uint8_t* output = nullptr;         // gOutput slice 0
     rtx_camera_params* cam = nullptr;  // b0 (device copy)

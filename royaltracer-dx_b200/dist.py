@@ -1,7 +1,18 @@
 """Multi-GPU plumbing: the scene and its BVH are replicated on every GPU, samples are partitioned across
 ranks, and the accumulation buffers (gPermanentData, float4 per pixel) are combined with ONE reduce per progressive pass.
-The path shards with no data-path collective other than that reduce; torch.distributed supplies it (NCCL over NVLink on
-the GPU box, gloo in the CPU tests)."""
+The path shards with no data-path collective other than that reduce.  On the GPU the reduce lives behind the C ABI
+(rtx_comm_init / rtx_reduce_accum: ncclReduce straight from gPermanentData on a side stream, overlapped with the next pass);
+torch.distributed only carries the 128-byte NCCL id between the ranks.  reduce_accum() below is the same plumbing on torch
+tensors for the CPU tests (gloo)."""
+
+
+def init_engine_comm(ctx, rank, world):
+    """Collective: rank 0 draws the NCCL unique id through the engine, every rank joins the engine's communicator.
+    Needs an initialised torch.distributed process group (any backend) for the broadcast of the id."""
+    import torch.distributed as dist
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world)
 
 
 def sample_for(step, rank, world):

@@ -250,6 +250,9 @@ static void camera_params(const float* eye, const float* center, const float* up
 }
 
 // ------------------------------------------------------------------------------------------ Renderer
+// (left out of librdx_prep.so, the engine-free build of the host-side data preparation that the CPU arms of bench.py and the
+// Python scene builders load: -DRDX_PREP_ONLY)
+#ifndef RDX_PREP_ONLY
 Renderer::Renderer(uint32_t width, uint32_t height) : m_width(width), m_height(height), m_aspectRatio((float)width / (float)height) {
     memset(&m_camera, 0, sizeof m_camera);
     m_prevViewMatrix = XMMatrixIdentity(); m_prevProjMatrix = XMMatrixIdentity();
@@ -338,7 +341,13 @@ void Renderer::OnUpdate() {
 
 void Renderer::OnRender(uint32_t first_sample, uint32_t n_samples) {
     Check(rtx_render_pass(m_ctx, first_sample, n_samples), "rtx_render_pass");
+    if (m_world > 1) Check(rtx_reduce_accum(m_ctx), "rtx_reduce_accum");   // one ncclReduce of gPermanentData per pass
     Check(rtx_synchronize(m_ctx), "rtx_synchronize");          // WaitForPreviousFrame, Renderer.cpp:717-735
+}
+// multi-GPU: every rank runs one Renderer on its own device over the replicated scene and renders the samples s = rank (mod world)
+void Renderer::InitComm(const void* nccl_unique_id128, int rank, int world) {
+    Check(rtx_comm_init(m_ctx, nccl_unique_id128, rank, world), "rtx_comm_init");
+    m_rank = rank; m_world = world;
 }
 // PopulateCommandList's three DispatchRays (RayGen, RayGen2, RayGen3), rdn/Renderer.cpp:611-673; needs flags |= RTX_FLAG_RESTIR
 void Renderer::OnRenderFrame(uint32_t frame_index) {
@@ -347,6 +356,7 @@ void Renderer::OnRenderFrame(uint32_t frame_index) {
 }
 void Renderer::ReadAccumulation(std::vector<float>& out) { out.resize((size_t)m_width * m_height * 4); Check(rtx_read_accum(m_ctx, out.data()), "rtx_read_accum"); }
 void Renderer::ReadOutput(std::vector<uint8_t>& out) { out.resize((size_t)m_width * m_height * 4); Check(rtx_read_output(m_ctx, out.data()), "rtx_read_output"); }
+#endif  // RDX_PREP_ONLY
 
 }  // namespace rdx
 

@@ -59,6 +59,8 @@ public:
     void OnRenderFrame(uint32_t frame_index);   // the reference's full frame incl. ReSTIR reuse (flags |= RTX_FLAG_RESTIR)
     // CreateVB(std::string) of the reference: OBJ/MTL ingest through ObjLoader.h, materials appended to the global list
     uint32_t CreateVB(const std::string& obj_path);
+    // multi-GPU (after OnInit): join the job's communicator; OnRender then ends with the per-pass reduce to rank 0
+    void InitComm(const void* nccl_unique_id128, int rank, int world);
     void ReadAccumulation(std::vector<float>& rgba32f);
     void ReadOutput(std::vector<uint8_t>& rgba8);
 
@@ -87,6 +89,7 @@ private:
     float m_eye[3] = {-1.5f, 1.5f, 3.5f}, m_center[3] = {0.f, 1.f, 0.f}, m_up[3] = {0.f, 1.f, 0.f};   // rdn/Renderer.cpp:47-48
     rtx_ctx* m_ctx = nullptr;
     bool m_first = true;
+    int m_rank = 0, m_world = 1;
     void Check(int status, const char* what);
 };
 

@@ -58,3 +58,33 @@ def load_scene_npz(rtdx, path):
     cam = z["camera"]
     sc.eye, sc.center, sc.up = tuple(cam[0]), tuple(cam[1]), tuple(cam[2])
     return sc
+
+
+def oracle_trace_threads(osc, rays, any_hit=False, mode=1, n_threads=None):
+    """osc.trace over all host threads (ctypes releases the GIL; the oracle scene is read-only while tracing)."""
+    import os
+    import threading
+    n_threads = n_threads or min(os.cpu_count() or 1, 32)
+    rays = np.ascontiguousarray(rays)
+    bounds = np.linspace(0, rays.size, n_threads + 1).astype(np.int64)
+    parts = [None] * n_threads
+
+    def work(i):
+        parts[i] = osc.trace(rays[bounds[i]:bounds[i + 1]], any_hit=any_hit, mode=mode)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return np.concatenate(parts)
+
+
+def bounce_rays(rtdx, rays, hits, rng, tmin=1e-3, tmax=1e4):
+    """Incoherent secondary rays: from the hit points of `rays`, uniformly random directions (seeded)."""
+    hit = hits["inst"] != 0xFFFFFFFF
+    o = rays["origin"][hit] + rays["direction"][hit] * hits["t"][hit][:, None]
+    d = rng.normal(size=o.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    out = np.zeros(o.shape[0], dtype=rtdx.ray_dt)
+    out["origin"] = o.astype(np.float32); out["direction"] = d.astype(np.float32)
+    out["tmin"] = tmin; out["tmax"] = tmax
+    return out

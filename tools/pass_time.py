@@ -1,5 +1,5 @@
 """Whole-pass device time of a bench scene (CUDA events around N passes on the engine's stream; no per-launch events, so the pass runs with
-its concurrent parts).  usage: [RTX_PARTS=k] python tools/pass_time.py [--scene mesh|inst] [--passes N] [--tag T]"""
+its concurrent parts).  usage: python tools/pass_time.py [--opt PASS_PARTS=k] [--scene mesh|inst] [--passes N] [--tag T]"""
 import argparse
 import os
 import sys
@@ -21,11 +21,15 @@ ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--spp", type=int, default=1, help="samples per pass (paths in flight = W*H*spp)")
 ap.add_argument("--refit", type=int, default=0, help="call rtx_set_instances this many times after the upload (TLAS refit)")
 ap.add_argument("--tag", default="")
+ap.add_argument("--opt", action="append", default=[], help="engine option NAME=VALUE (rtdx.OPT_<NAME>), e.g. PASS_PARTS=1 TRACE_SCHED=0x060808")
 a = ap.parse_args()
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 sc = rtdx.scenes.mesh_room(n=a.side) if a.scene == "mesh" else rtdx.scenes.instanced_blobs()
 ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags, samples_per_pass=a.spp, stream=stream.cuda_stream)
 up = ctx.upload_scene(sc)
+for o in a.opt:
+    k, v = o.split("=")
+    ctx.set_option(getattr(rtdx, "OPT_" + k), int(v, 0))
 for _ in range(a.refit):
     ctx.set_instances(up["descs"], up["props"])
 for p in range(3):
