@@ -6,11 +6,11 @@
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference/Pathtracer/).  Numerics contract: oracle/det_math.h.
 //
-// PARITY STATUS: "parity unpinned" against reference outputs — the reference has no tests, golden
-// vectors or fixtures and is a Windows/DX12 app that cannot execute here.  The
-// traversal + ray/triangle test has no reference source at all (closed D3D12 driver / RT cores);
-// the contract is defined HERE (orc_trace mode 0 = brute force) from the DXR semantics the
-// reference's call sites rely on.
+// PARITY STATUS: pinned to the reference's own shader text.  oracle/_ref/libref.so = Pathtracer/shaders/*.hlsl compiled for the CPU
+// (oracle/ref/make_ref.py + hlsl_shim.h); tests/test_ref_pins.py runs RayGen / RayGen2 / RayGen3 and the leaf functions from it and
+// demands bit-identical results from the functions below.  The traversal + ray/triangle test has no reference source at all (closed
+// D3D12 driver / RT cores): that contract is defined HERE (orc_trace mode 0 = brute force) from the DXR semantics the reference's
+// call sites rely on and is the one part that remains "parity unpinned".
 //
 // Deliberate deviations from reference undefined behaviour (DESIGN.md §"Deviations"):
 //   D1 miss => path terminates, radiance 0 (ref: Miss_v7.hlsl:3-8 leaves the payload uninitialised)

@@ -2,10 +2,11 @@
  *
  * C interface of the single-threaded CPU restatement of the reference's hot path.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
- * load this library.  Parity status: the reference (Windows/DX12, HLSL) ships no tests, golden
- * vectors or fixtures for this path and cannot be compiled or run here, so
- * this oracle is "parity unpinned" against reference *outputs*; it is pinned against the
- * closed-form identities of the reference's own source (tests/test_oracle_*.py).
+ * load this library.  Parity status: PINNED to the reference's own shader text — oracle/_ref/libref.so
+ * is Pathtracer/shaders/*.hlsl compiled for the CPU (oracle/ref/make_ref.py) and tests/test_ref_pins.py
+ * demands bit-identical results from this library for RayGen/RayGen2/RayGen3 and their leaf
+ * functions.  Unpinned (no reference source or output exists): which triangle TraceRay returns —
+ * that contract is defined here (orc_trace mode 0).
  */
 #pragma once
 #include <stdint.h>
