@@ -3,7 +3,7 @@
  * C interface of the single-threaded CPU restatement of the reference's hot path.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  Parity status: PINNED to the reference's own shader text — oracle/_ref/libref.so
- * is Pathtracer/shaders/*.hlsl compiled for the CPU (oracle/ref/make_ref.py) and tests/test_ref_pins.py
+ * is the HLSL of Pathtracer/shaders compiled for the CPU (oracle/ref/make_ref.py) and tests/test_ref_pins.py
  * demands bit-identical results from this library for RayGen/RayGen2/RayGen3 and their leaf
  * functions.  Unpinned (no reference source or output exists): which triangle TraceRay returns —
  * that contract is defined here (orc_trace mode 0).
