@@ -499,7 +499,6 @@ def run_trace(rtdx, D, cfg, args, steps, warmup):
     d = torch.randn((n, 3), device="cuda", generator=gen); d = d / d.norm(dim=1, keepdim=True)
     inc = torch.cat([o, torch.full((n, 1), 1e-3, device="cuda"), d, torch.full((n, 1), 1e4, device="cuda")], dim=1)
     inc = inc[hits[:, 4].view(torch.int32) != -1].contiguous()
-    inc = inc[torch.randperm(inc.shape[0], device="cuda", generator=gen)].contiguous()       # no spatial order left
     peak, peak_src = peaks()
     out = {}
     for name, r in (("coherent", rays), ("incoherent", inc)):
