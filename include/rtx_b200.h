@@ -175,6 +175,9 @@ rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stage
 #define RTX_OPT_TRACE_FETCH_TH 5u  /* a warp refills its idle lanes when fewer than this many lanes are still traversing (default 24) */
 #define RTX_OPT_TRACE_SCHED    6u  /* phase scheduling thresholds th_tri | th_inst << 8 | th_node << 16 (default 0x060808) */
 #define RTX_OPT_TRACE_WAVES    7u  /* persistent grid = SMs x resident CTAs x waves (default 1) */
+#define RTX_OPT_QUEUE_LPT       8u  /* 1 (default): closest-hit queues are traced longest-processing-time-first (rays that cross the bounds of the
+                                    * scene's large instances before the others); 0: in emission order.  The image does not depend on it. */
+#define RTX_OPT_TRACE_CTAS      9u  /* resident CTAs per SM of the persistent traversal grid (0 = default: all the register budget allows) */
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);

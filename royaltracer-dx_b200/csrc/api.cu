@@ -58,11 +58,12 @@ struct rtx_ctx {
     unsigned int* h_overflow = nullptr;     // pinned copy written behind every asynchronous read-back (rtx_wait_output looks at it)
     void* d_trace_rays = nullptr; size_t cap_trace_rays = 0; void* d_trace_hits = nullptr; size_t cap_trace_hits = 0;   // rtx_trace staging
     size_t cap_material_ids = 0, cap_materials = 0, cap_lights = 0;
-    int num_sms = 148, fetch_th = 0, sched = 0, waves = 0;     // traversal launch tuning (0 = the built-in defaults, trace.cu)
+    int num_sms = 148, fetch_th = 0, sched = 0, waves = 0, ctas_per_sm = 0;     // traversal launch tuning (0 = the built-in defaults, trace.cu)
     // multi-GPU (rtx_comm_init): one NCCL reduce of gPermanentData per progressive pass, on the side stream
     void* comm = nullptr; int comm_rank = 0, comm_world = 1;
     float4* d_total = nullptr;              // root only: the sum over ranks; rtx_read_output* resolve it
     cudaEvent_t ev_pass = nullptr, ev_reduced = nullptr;
+    float heavy_lo[3] = {0, 0, 0}, heavy_hi[3] = {0, 0, 0}; bool heavy_valid = false, lpt = true;   // SceneData::heavy_* (queue order only)
     uint64_t launches = 0;
     PassTiming timing;
     bool trace_stats = false;
@@ -243,6 +244,41 @@ extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* des
         if (descs[i].blas >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_set_instances: instance references an unknown model");
         if (c->models[descs[i].blas].n_tris == 0) return fail(RTX_ERR_ARG, "rtx_set_instances: instance of an empty model");
     }
+    {   // bounds of the "heavy" instances (BLAS with >= 1/4 of the largest BLAS's triangles): rays crossing them go to the front of the
+        // wavefront's queues (wavefront.h RayQueue).  Corner boxes through the desc's objectToWorld: conservative, host arithmetic only.
+        uint32_t max_tris = 0;
+        for (uint32_t i = 0; i < n; i++) max_tris = std::max(max_tris, c->models[descs[i].blas].n_tris);
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = 0; i < n; i++) {
+            const ModelRec& m = c->models[descs[i].blas];
+            if ((uint64_t)m.n_tris * 4u < max_tris) continue;
+            for (int k = 0; k < 8; k++) {
+                const float x = (k & 1) ? m.bvh.hi[0] : m.bvh.lo[0], y = (k & 2) ? m.bvh.hi[1] : m.bvh.lo[1], z = (k & 4) ? m.bvh.hi[2] : m.bvh.lo[2];
+                for (int r = 0; r < 3; r++) {
+                    const float* t = descs[i].transform[r];
+                    const float v = t[0] * x + t[1] * y + t[2] * z + t[3];
+                    lo[r] = fminf(lo[r], v); hi[r] = fmaxf(hi[r], v);
+                }
+            }
+        }
+        // ... and the bounds of everything: the classification is only worth its atomics when it separates something (in a scene whose
+        // instances are all of one size every ray that hits anything is "heavy": C3 lost 2 % to it)
+        float slo[3] = {INFINITY, INFINITY, INFINITY}, shi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = 0; i < n; i++) {
+            const ModelRec& m = c->models[descs[i].blas];
+            for (int k = 0; k < 8; k++) {
+                const float x = (k & 1) ? m.bvh.hi[0] : m.bvh.lo[0], y = (k & 2) ? m.bvh.hi[1] : m.bvh.lo[1], z = (k & 4) ? m.bvh.hi[2] : m.bvh.lo[2];
+                for (int r = 0; r < 3; r++) {
+                    const float* t = descs[i].transform[r];
+                    const float v = t[0] * x + t[1] * y + t[2] * z + t[3];
+                    slo[r] = fminf(slo[r], v); shi[r] = fmaxf(shi[r], v);
+                }
+            }
+        }
+        const float vh = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]), vs = (shi[0] - slo[0]) * (shi[1] - slo[1]) * (shi[2] - slo[2]);
+        c->heavy_valid = n > 0 && lo[0] <= hi[0] && vh < 0.5f * vs;
+        for (int r = 0; r < 3; r++) { c->heavy_lo[r] = lo[r]; c->heavy_hi[r] = hi[r]; }
+    }
     rtx_status st;
     if ((st = ensure_tables(c)) != RTX_OK) return st;
     if ((st = reserve(&c->d_descs, &c->cap_descs, n)) != RTX_OK) return st;
@@ -341,7 +377,7 @@ static SceneAS make_as(rtx_ctx* c) {
     a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
     a.one_bits = 0x3F800000u;
     a.overflow = c->d_overflow;
-    a.num_sms = c->num_sms; a.fetch_th = c->fetch_th; a.sched = c->sched; a.waves = c->waves;
+    a.num_sms = c->num_sms; a.fetch_th = c->fetch_th; a.sched = c->sched; a.waves = c->waves; a.ctas_per_sm = c->ctas_per_sm;
     return a;
 }
 
@@ -374,6 +410,8 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
     S.lights = c->d_lights;
     S.cfg_flags = c->cfg.flags; S.bounces = c->cfg.bounces; S.nee_samples = c->cfg.nee_samples; S.nee_samples_di = c->cfg.nee_samples_di;
     S.width = c->cfg.width; S.height = c->cfg.height;
+    for (int r = 0; r < 3; r++) { S.heavy_lo[r] = c->heavy_lo[r]; S.heavy_hi[r] = c->heavy_hi[r]; }
+    S.heavy_valid = c->heavy_valid && c->lpt ? 1u : 0u;
     const SceneAS AS = make_as(c);
     uint32_t done = 0;
     while (done < n_samples) {
@@ -414,6 +452,8 @@ extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
     S.lights = c->d_lights;
     S.cfg_flags = c->cfg.flags; S.bounces = c->cfg.bounces; S.nee_samples = c->cfg.nee_samples; S.nee_samples_di = c->cfg.nee_samples_di;
     S.width = c->cfg.width; S.height = c->cfg.height;
+    for (int r = 0; r < 3; r++) { S.heavy_lo[r] = c->heavy_lo[r]; S.heavy_hi[r] = c->heavy_hi[r]; }
+    S.heavy_valid = c->heavy_valid && c->lpt ? 1u : 0u;
     const SceneAS AS = make_as(c);
     c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
     if (c->wb.wait_before_accumulate) RTX_CK(cudaStreamWaitEvent(c->stream, c->wb.wait_before_accumulate, 0));   // a pending reduce reads gPermanentData
@@ -822,6 +862,8 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     else if (option == RTX_OPT_TRACE_FETCH_TH) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_FETCH_TH must be 0..32"); c->fetch_th = (int)value; }
     else if (option == RTX_OPT_TRACE_SCHED) c->sched = (int)(value & 0xffffffu);
     else if (option == RTX_OPT_TRACE_WAVES) { if (value > 8u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_WAVES must be 0..8"); c->waves = (int)value; }
+    else if (option == RTX_OPT_QUEUE_LPT) c->lpt = value != 0;
+    else if (option == RTX_OPT_TRACE_CTAS) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_CTAS must be 0..32"); c->ctas_per_sm = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;
 }

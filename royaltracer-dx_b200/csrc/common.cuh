@@ -61,6 +61,7 @@ struct SceneAS {
     int fetch_th;         // refill the warp's idle lanes when fewer than this many lanes are still traversing
     int sched;            // th_tri | th_inst << 8 | th_node << 16 (phase scheduling, traverse.cuh)
     int waves;            // persistent grid = num_sms * resident CTAs * waves
+    int ctas_per_sm;      // resident CTAs per SM the persistent grid uses (0 = all the register budget allows)
 };
 
 // Ray queue entry layout (SoA): o_tmin[j] = (o.xyz, tmin), d_tmax[j] = (d.xyz, tmax).

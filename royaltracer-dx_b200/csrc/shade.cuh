@@ -24,6 +24,9 @@ struct SceneData {              // global root signature (rdn/Renderer.cpp:953-9
     const rtx_light_triangle* lights;                         // t6 (never empty: a zero light stands in)
     uint32_t cfg_flags, bounces, nee_samples, nee_samples_di;
     uint32_t width, height;
+    // world bounds of the instances whose BLAS holds at least a quarter of the largest BLAS's triangles (api.cu rtx_set_instances);
+    // heavy_valid = 0: queues are filled from one end only
+    float heavy_lo[3], heavy_hi[3]; uint32_t heavy_valid;
 };
 
 struct MatOpt {                 // shaders/Common_v7.hlsl:62-66 — every float holds a binary16 value

@@ -7,6 +7,7 @@
 // memory latency — see DESIGN.md §Kernels).
 #include <algorithm>
 using std::max;
+using std::min;
 
 #include "trace.h"
 #include "traverse.cuh"
@@ -30,8 +31,11 @@ template <bool ANY_HIT, bool STATS>
 __global__ void __launch_bounds__(TRACE_BLOCK, RTX_TRACE_MINB)
 trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restrict__ d_tmax,
              const uint32_t* __restrict__ n_ptr, uint32_t n_fixed, unsigned int* __restrict__ cursor,
-             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int sched) {
+             float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int sched,
+             const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_heavy_ptr, uint32_t cap) {
+    // trace order (wavefront.h RayQueue): claim k -> slot order[k] (k < n_heavy) or order[cap-1-(k-n_heavy)]: expensive rays first
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    const uint32_t n_heavy = order ? *n_heavy_ptr : 0u;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint2 stack[RTX_STACK_SIZE];
@@ -71,7 +75,8 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
             }
             const uint32_t mine = base + (uint32_t)__popc(idle & lt_mask);
             if (!active && mine < n) {
-                trav_init(T, C, S, __ldg(o_tmin + mine), __ldg(d_tmax + mine), mine);
+                const uint32_t slot = order ? __ldg(order + (mine < n_heavy ? mine : cap - 1u - (mine - n_heavy))) : mine;
+                trav_init(T, C, S, __ldg(o_tmin + slot), __ldg(d_tmax + slot), slot);
                 active = true;
             }
         }
@@ -166,20 +171,21 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
 
 cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
                          unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
-                         cudaStream_t stream, int grid_share) {
+                         cudaStream_t stream, int grid_share, const uint32_t* order, const uint32_t* n_heavy_ptr, uint32_t cap) {
     // `cursor` = two words, both 0 between launches: [0] the ray cursor, [1] the count of finished CTAs; the last CTA of a launch
     // resets [0] (and atomicInc wraps [1]), so no memset precedes the launch.
     const int sms = S.num_sms > 0 ? S.num_sms : 148;
     const int fetch_th = S.fetch_th > 0 ? S.fetch_th : FETCH_THRESHOLD, sched = S.sched ? S.sched : RTX_SCHED_DEFAULT, waves = S.waves > 0 ? S.waves : 1;
     // persistent: the resident CTAs of the machine (x waves), or this launch's share of them when several traversals run concurrently
     // (wave_render_pass: the parts' kernels are then co-resident and one part's drain phase overlaps the other's work)
-    const int grid = max(sms, sms * RTX_TRACE_MINB * waves / max(grid_share, 1));
+    const int ctas = S.ctas_per_sm > 0 ? min(S.ctas_per_sm, RTX_TRACE_MINB) : RTX_TRACE_MINB;
+    const int grid = max(sms, sms * ctas * waves / max(grid_share, 1));
     if (stats) {
-        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched);
-        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched);
+        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap);
+        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap);
     } else {
-        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched);
-        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched);
+        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap);
+        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap);
     }
     return cudaGetLastError();
 }

@@ -47,28 +47,34 @@ __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t
 }
 
 __global__ void __launch_bounds__(WF_BLOCK)
-k_generate(StateView st, uint32_t p0, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
+k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
            uint32_t first_sample, uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi, unsigned long long* ray_counters) {
     // paths [p0, p0 + np) of the pass (one part of the frame, see wave_render_pass); queue slot = index within the part
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) { *q0.count = np; atomicAdd(&ray_counters[2], (unsigned long long)np); }
-    if (k >= np) return;
-    const uint32_t p = p0 + k;
-    const uint32_t npx = W * H;
-    const uint32_t pixel = p % npx, s = p / npx;
-    const uint32_t x = pixel % W, y = pixel / W;
-    uint2 seed = init_seed(x, y, 1u, first_sample + s);
-    float jx = 0.0f, jy = 0.0f;
-    if (flags & RTX_FLAG_JITTER) { jx = RandomFloat(seed); jy = RandomFloat(seed); }
-    f3 o, dir;
-    CameraRay(cam, W, H, x, y, jx, jy, o, dir);
-    q0.o_tmin[k] = f4(o, 0.0001f);
-    q0.d_tmax[k] = f4(dir, 10000.0f);
-    q0.pid[k] = p;
-    st.at(SP_N1, p) = make_float4(0, 0, 0, __uint_as_float(seed.x));
-    st.at(SP_O, p) = f4u(-dir, seed.y);
-    st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
-    vis_di[p] = 1.0f; vis_gi[p] = 1.0f;
+    const bool live = k < np;
+    f3 o = mk3(0, 0, 0), dir = mk3(0, 0, 1);
+    if (live) {
+        const uint32_t p = p0 + k;
+        const uint32_t npx = W * H;
+        const uint32_t pixel = p % npx, s = p / npx;
+        const uint32_t x = pixel % W, y = pixel / W;
+        uint2 seed = init_seed(x, y, 1u, first_sample + s);
+        float jx = 0.0f, jy = 0.0f;
+        if (flags & RTX_FLAG_JITTER) { jx = RandomFloat(seed); jy = RandomFloat(seed); }
+        CameraRay(cam, W, H, x, y, jx, jy, o, dir);
+        q0.o_tmin[k] = f4(o, 0.0001f);
+        q0.d_tmax[k] = f4(dir, 10000.0f);
+        q0.pid[k] = p;
+        st.at(SP_N1, p) = make_float4(0, 0, 0, __uint_as_float(seed.x));
+        st.at(SP_O, p) = f4u(-dir, seed.y);
+        st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
+        vis_di[p] = 1.0f; vis_gi[p] = 1.0f;
+    }
+    if (q0.order) {             // trace order of the primary rays (every lane of the warp reaches this point)
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (mask) record_order(q0, mask, live, live && ray_is_heavy(S, o, 0.0001f, dir, 10000.0f), k);
+    }
 }
 
 // shaders/Reservoir_v7.hlsl:57-80 / :30-53 on unpacked fields
@@ -148,7 +154,7 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
             }
         }
     }
-    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+    push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
 }
 
 // ---- stage: BSDF candidate of the DI reservoir, DI visibility ray, first indirect ray
@@ -231,8 +237,8 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         // the path state of SamplePathSimple's start (origin = x1, normal, outgoing = normalize(o), acc_f = 1, empty GI reservoir) is not
         // stored: k_gi_step<ITER0> derives it from SP_X1 / SP_N1 / SP_O and constants
     }
-    push_ray(q_shadow, emit_sh, so, 0.0f, sd, stmax, pid);
-    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+    push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.0f, sd, stmax), so, 0.0f, sd, stmax, pid);
+    push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
 }
 
 // SampleLightNEE_GI with useVisibility=false, Sampler_v7.hlsl:508-647 (call site Path_Sampler_v7.hlsl:133-151)
@@ -414,8 +420,8 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         st.at(SP_N1, pid) = make_float4(a1.x, a1.y, a1.z, __uint_as_float(seed.x));
         st.at(SP_O, pid) = make_float4(a2.x, a2.y, a2.z, __uint_as_float(seed.y));
     }
-    push_ray(q_shadow, emit_sh, so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
-    push_ray(qout, emit, ro, RTX_S_BIAS, rd, 10000.0f, pid);
+    push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
+    push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
 }
 
 // ---- stage: estimator E0 (Pass_init_di_v7.hlsl:166-181 + Pass_spat_di_v7.hlsl:334-372 with no accepted neighbours)
@@ -549,14 +555,16 @@ static cudaError_t alloc_queue(RayQueue* q, uint32_t n) {
     CKE(cudaMalloc((void**)&q->o_tmin, (size_t)n * 16));
     CKE(cudaMalloc((void**)&q->d_tmax, (size_t)n * 16));
     CKE(cudaMalloc((void**)&q->pid, (size_t)n * 4));
-    q->count = nullptr;
+    CKE(cudaMalloc((void**)&q->order, (size_t)n * 4));
+    q->count = nullptr; q->n_heavy = q->n_light = nullptr; q->cap = n;
     return cudaSuccess;
 }
 static void free_queue(RayQueue* q) {
     if (q->o_tmin) cudaFree(q->o_tmin);
     if (q->d_tmax) cudaFree(q->d_tmax);
     if (q->pid) cudaFree(q->pid);
-    q->o_tmin = q->d_tmax = nullptr; q->pid = nullptr;
+    if (q->order) cudaFree(q->order);
+    q->o_tmin = q->d_tmax = nullptr; q->pid = nullptr; q->order = nullptr;
 }
 
 cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp) {
@@ -570,7 +578,7 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMalloc((void**)&B->hit_inst, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->vis_di, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->vis_gi, (size_t)n * 4));
-    CKE(cudaMalloc((void**)&B->counts, WAVE_MAX_PARTS * 128 * 4));
+    CKE(cudaMalloc((void**)&B->counts, WAVE_MAX_PARTS * 384 * 4));     // per part: 128 queue counters + their heavy / light counts
     CKE(cudaMalloc((void**)&B->cursor, WAVE_MAX_PARTS * 16));
     CKE(cudaMemset(B->cursor, 0, WAVE_MAX_PARTS * 16));      // launch_trace keeps the cursor words at zero between launches
     CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
@@ -636,17 +644,26 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         RayQueue q[2], sdi, sgi, qin, qout;
         int cur;
     } P[WAVE_MAX_PARTS];
-    auto view = [](const RayQueue& q, uint32_t off) { RayQueue v = q; v.o_tmin += off; v.d_tmax += off; v.pid += off; return v; };
+    // `ordered` views carry the queue's trace order (wavefront.h RayQueue); the heavy / light counts of queue counter i are counters
+    // 128 + i / 256 + i of the part's block
+    const bool lpt = S.heavy_valid != 0u;
+    auto view = [lpt](const RayQueue& q, uint32_t off, uint32_t cap, bool ordered) {
+        RayQueue v = q; v.o_tmin += off; v.d_tmax += off; v.pid += off; v.cap = cap;
+        v.order = (ordered && lpt) ? q.order + off : nullptr; v.n_heavy = v.n_light = nullptr;
+        return v;
+    };
+    auto counters = [](RayQueue& q, uint32_t* block, int i) { q.count = block + i; q.n_heavy = block + 128 + i; q.n_light = block + 256 + i; };
     for (int h = 0; h < parts; h++) {
         Part& p = P[h];
         p.stream = h == 0 ? stream : B.aux[h - 1];
         p.p0 = (uint32_t)((uint64_t)n * h / parts); p.np = (uint32_t)((uint64_t)n * (h + 1) / parts) - p.p0;
         p.grid = (p.np + WF_BLOCK - 1) / WF_BLOCK; p.ggrid = (p.np + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
-        p.counts = B.counts + 128 * h; p.cursor = B.cursor + 4 * h;
+        p.counts = B.counts + 384 * h; p.cursor = B.cursor + 4 * h;
         p.hit_a = B.hit_a + p.p0; p.hit_inst = B.hit_inst + p.p0;
         // counter slots: 0 = primary queue, 1 = DI BSDF queue, 2 = DI shadow, 3 = GI shadow, 4.. = indirect queues
-        p.q[0] = view(B.q[0], p.p0); p.q[1] = view(B.q[1], p.p0); p.sdi = view(B.sq[0], p.p0); p.sgi = view(B.sq[1], p.p0);
-        p.sdi.count = p.counts + 2; p.sgi.count = p.counts + 3;
+        p.q[0] = view(B.q[0], p.p0, p.np, true); p.q[1] = view(B.q[1], p.p0, p.np, true);
+        p.sdi = view(B.sq[0], p.p0, p.np, true); p.sgi = view(B.sq[1], p.p0, p.np, true);
+        counters(p.sdi, p.counts, 2); counters(p.sgi, p.counts, 3);
         p.cur = 0;
     }
     auto mark = [&](StageKind k) -> cudaError_t {       // per-launch CUDA events (RTX_OPT_STAGE_TIMING only: one part)
@@ -660,11 +677,11 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     };
     auto closest = [&](Part& p, const RayQueue& q) -> cudaError_t {
         CKE(mark(SK_CLOSEST));
-        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, parts);
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, parts, q.order, q.n_heavy, q.cap);
     };
     auto shadow = [&](Part& p, const RayQueue& q, float* vis) -> cudaError_t {
         CKE(mark(SK_ANY));
-        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts));
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts, q.order, q.n_heavy, q.cap));
         CKE(mark(SK_SCATTER));
         k_scatter_vis<<<p.grid, WF_BLOCK, 0, p.stream>>>(q.count, q.pid, p.hit_inst, vis);
         return cudaSuccess;
@@ -673,12 +690,12 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     const int n_stages = 7 + 2 * ((int)S.bounces + 1) + 2;
     auto stage = [&](Part& p, int s) -> cudaError_t {
         RayQueue q0 = p.q[0], q1 = p.q[1], qa = p.q[0];
-        q0.count = p.counts + 0; q1.count = p.counts + 1; qa.count = p.counts + 4;
+        counters(q0, p.counts, 0); counters(q1, p.counts, 1); counters(qa, p.counts, 4);
         const int last = 7 + 2 * ((int)S.bounces + 1);
         if (s == 0) {
-            CKE(cudaMemsetAsync(p.counts, 0, 128 * 4, p.stream));
+            CKE(cudaMemsetAsync(p.counts, 0, 384 * 4, p.stream));
             CKE(mark(SK_GENERATE));
-            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.p0, p.np, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
+            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, p.p0, p.np, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
                                                           B.ray_counters);
         } else if (s == 1) {
             CKE(closest(p, q0));
@@ -698,7 +715,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         } else if (s < last) {
             const uint32_t iter = (uint32_t)(s - 7) / 2u;
             if (((s - 7) & 1) == 0) {               // k_gi_step(iter)
-                p.qout = p.q[p.cur ^ 1]; p.qout.count = p.counts + 5 + iter;
+                p.qout = p.q[p.cur ^ 1]; counters(p.qout, p.counts, 5 + (int)iter);
                 const uint32_t* perm = nullptr;
                 if (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) {
                     CKE(mark(SK_SORT));

@@ -29,8 +29,18 @@ enum StatePlane {
     NSTATE
 };
 
+// Ray queue: slots are claimed in emission order (warp-compacted, so the path ids of a queue stay in pixel order and the shading stages'
+// structure-of-arrays state accesses stay coalesced).  A queue can carry a TRACE ORDER beside it (wave_dev.cuh push_ray2): order[] holds
+// slot indices, those of rays expected to be expensive ("heavy": their segment crosses the bounds of the scene's large instances) from
+// entry 0 upwards, the others from entry cap-1 downwards.  The persistent traversal kernel claims order entries front to back, i.e. it
+// starts the long rays first and the queue runs out among the short ones (longest-processing-time-first: what the last-started long rays
+// leave behind was a third of a 1080p launch); hit records land in the ray's own slot.  order == nullptr: traced in slot order.
+// (Filling the QUEUE itself from both ends was measured first: traversal -12 %, but the shading stage then reads its state at a fifth of
+// the density for the heavy rays: k_gi_step 3.66 -> 6.05 ms per C2 pass; an array-of-structures state made that order-independent at
+// 4.15 ms and cost the streaming stages 3x — profiles/r02_lpt_queue_layouts.txt.)
 struct RayQueue {
     float4* o_tmin; float4* d_tmax; uint32_t* pid; uint32_t* count;   // count lives on the device
+    uint32_t* order; uint32_t* n_heavy; uint32_t* n_light; uint32_t cap;
 };
 
 #define WAVE_MAX_PARTS 4

@@ -12,6 +12,6 @@ name, defs = sys.argv[1], sys.argv[2:]
 out = os.path.join(ROOT, "build", "variants")
 os.makedirs(out, exist_ok=True)
 cu = B._sources(B.CSRC, (".cu",))
-cmd = ["nvcc"] + B.NVCC_FLAGS + defs + ["-o", os.path.join(out, name + ".so")] + cu
+cmd = ["nvcc", "-shared"] + B.NVCC_FLAGS + defs + ["-o", os.path.join(out, name + ".so")] + cu
 print(" ".join(cmd), flush=True)
 subprocess.check_call(cmd)

@@ -57,13 +57,25 @@ def keys(r, bits):
     return (octant << (3 * bits)) | k, (k << 3) | octant
 
 
+def hits_box(r, lo, hi):
+    """slab test of rays against one world box (the displaced sphere of the C2 scene)"""
+    inv = 1.0 / r[:, 4:7]
+    t0 = (torch.tensor(lo, device="cuda") - r[:, 0:3]) * inv; t1 = (torch.tensor(hi, device="cuda") - r[:, 0:3]) * inv
+    tn = torch.minimum(t0, t1).max(1).values.clamp(min=1e-3); tf = torch.maximum(t0, t1).min(1).values
+    return tn <= tf
+
+
 ctx.trace_device(rays.data_ptr(), n, hits.data_ptr()); torch.cuda.synchronize()
 timed(rays, "primaries")
 b1 = bounce(rays, hits)
 for gen_i in range(3):
     h1 = timed(b1, "bounce %d emission order" % (gen_i + 1))
     timed(b1[torch.randperm(b1.shape[0], device="cuda", generator=gen)].contiguous(), "bounce %d shuffled" % (gen_i + 1))
-    for bits in (2, 3, 4, 6):
+    heavy = hits_box(b1, (-1.75, 0.25, -1.75), (1.75, 3.75, 1.75))
+    print("   rays that hit the mesh's box: %.1f %%" % (100.0 * heavy.float().mean().item()))
+    timed(b1[torch.argsort(heavy.to(torch.int32), descending=True, stable=True)].contiguous(), "bounce %d heavy rays FIRST" % (gen_i + 1))
+    timed(b1[torch.argsort(heavy.to(torch.int32), descending=False, stable=True)].contiguous(), "bounce %d heavy rays LAST" % (gen_i + 1))
+    for bits in (4,):
         ko, kc = keys(b1, bits)
         timed(b1[torch.argsort(ko)].contiguous(), "bounce %d sorted oct|cell%d" % (gen_i + 1, bits))
         timed(b1[torch.argsort(kc)].contiguous(), "bounce %d sorted cell%d|oct" % (gen_i + 1, bits))
