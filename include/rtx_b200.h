@@ -53,6 +53,11 @@ typedef struct { float t, u, v; uint32_t prim; uint32_t inst; } rtx_hit;      /*
 #define RTX_FLAG_LEGACY_RR       16u /* rtx_render_pass runs the reference's legacy estimator (include/RayGen.hlsl:60-137 + include/Hit.hlsl:
                                        * RIS-10 NEE with one shadow ray per bounce, MIS on emitter hits, Russian roulette after depth 3);
                                        * cfg.bounces (<= 60) caps the number of closest-hit rays per path */
+#define RTX_FLAG_FAST_MATH       32u /* rtx_render_pass (estimator E0) runs the shading stages built with FMA contraction and approximate
+                                       * division / sqrt / rsqrt / sincos (-use_fast_math): ~19 % faster on BASELINE config C2, no longer
+                                       * bit-identical to the CPU oracle — paths diverge at discrete decisions; the converged image agrees within
+                                       * the tolerance tests/test_gpu_parity.py::test_fast_math_mode_converges_to_the_exact_image states.
+                                       * Default (flag clear): every float operation in IEEE binary32 source order, bit-exact parity. */
 #define RTX_FLAG_RESTIR          8u  /* allocate the reservoir / sample buffers u2..u7 (rdn/Renderer.cpp:1331-1577) for rtx_render_frame */
 
 /* Compile-time #defines of shaders/Common_v7.hlsl:1-28 that BASELINE configs vary, as runtime fields. */

@@ -39,10 +39,11 @@ def build(force=False, verbose=False):
         os.makedirs(OBJ, exist_ok=True)
         hdrs = [d for d in deps if not d.endswith(".cu")]
 
-        def compile_one(src):
-            obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        def compile_one(job):
+            src, suffix, extra = job
+            obj = os.path.join(OBJ, os.path.basename(src)[:-3] + suffix + ".o")
             if force or _newer(obj, [src] + hdrs):
-                cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+                cmd = ["nvcc"] + [f for f in NVCC_FLAGS if not (extra and f == "-fmad=false")] + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
                 print(" ".join(cmd), flush=True)
                 r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
                 if verbose or r.returncode:
@@ -50,8 +51,11 @@ def build(force=False, verbose=False):
                 if r.returncode:
                     raise subprocess.CalledProcessError(r.returncode, cmd)
             return obj
-        with ThreadPoolExecutor(max_workers=min(len(cu), os.cpu_count() or 1)) as ex:
-            objs = list(ex.map(compile_one, cu))
+        jobs = [(c, "", []) for c in cu]
+        # the shading stages a second time with fast math, into namespace rtx::fast (RTX_FLAG_FAST_MATH; wavefront.cu)
+        jobs.append((os.path.join(CSRC, "wavefront.cu"), "_fast", ["-DRTX_FAST_MATH", "-fmad=true", "-use_fast_math"]))
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, jobs))
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -418,6 +418,7 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
         const uint32_t spp = std::min(c->cfg.samples_per_pass, n_samples - done);
         c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
         if (c->cfg.flags & RTX_FLAG_LEGACY_RR) RTX_CK(wave_render_pass_legacy(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
+        else if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
         else RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
         done += spp;
     }

@@ -15,6 +15,12 @@
 #include "wave_dev.cuh"
 
 namespace rtx {
+// This file is compiled twice (build.py): as is — every float operation an IEEE binary32 operation in source order (-fmad=false), the
+// parity mode whose results are bit-identical to the CPU oracle — and with -DRTX_FAST_MATH -fmad=true -use_fast_math into rtx::fast
+// (FMA contraction, approximate division / sqrt / rsqrt / sincos), the opt-in RTX_FLAG_FAST_MATH mode of rtx_render_pass.
+#ifdef RTX_FAST_MATH
+namespace fast {
+#endif
 
 #define CKE(call)                            \
     do {                                     \
@@ -806,4 +812,7 @@ cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uin
     return cudaStreamSynchronize(stream);
 }
 
+#ifdef RTX_FAST_MATH
+}  // namespace fast
+#endif
 }  // namespace rtx

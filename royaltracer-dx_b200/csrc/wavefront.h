@@ -82,6 +82,11 @@ struct PassTiming {
 // One DispatchRays-equivalent: samples [first_sample, first_sample + spp) of every pixel.
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
                              cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true);
+// the same stage sequence built with fast math (wavefront.cu compiled with -DRTX_FAST_MATH): RTX_FLAG_FAST_MATH
+namespace fast {
+cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
+                             cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true);
+}
 // The reference's legacy estimator (include/RayGen.hlsl + include/Hit.hlsl) as a wavefront: legacy.cu.  S.bounces caps the path length.
 cudaError_t wave_render_pass_legacy(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
                                     cudaStream_t stream, uint64_t* launches, PassTiming* timing);
