@@ -467,6 +467,14 @@ struct Scratch {
     ~Scratch() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
 };
+// all the scratch of one build in ONE allocation, carved up front (a build used to make 20 cudaMallocs)
+struct Arena {
+    char* base = nullptr; size_t used = 0, cap = 0;
+    ~Arena() { if (base) cudaFree(base); }
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    cudaError_t reserve(size_t bytes) { cap = bytes; return cudaMalloc((void**)&base, bytes ? bytes : 256); }
+    void* take(size_t bytes) { void* p = base + used; used += pad(bytes); return used <= cap ? p : nullptr; }
+};
 
 template <int PRIM_F4, int MAXL, typename Source>
 static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint32_t n, Source src, BuildCounters* d_ctr, Bvh8* out,
@@ -486,22 +494,23 @@ static cudaError_t build_generic(const float4* d_plo, const float4* d_phi, uint3
         out->n_levels = 1; out->level_start[0] = 0; out->level_start[1] = 1;
         k_single_node<PRIM_F4, Source><<<1, 32, 0, stream>>>(src, d_plo, d_phi, (int)n, d_nodes, d_prims, d_ctr);
     } else {
-        Scratch keys_a, keys_b, vals_a, vals_b, child_s, cnt_s, cost_s, dec_s, nlo_s, nhi_s, cl_a, cl_b, nn_s, val_s, valid_s, pos_s,
-            tasks_a, tasks_b, tmp_s, tmp2_s;
-        CKE(keys_a.alloc((size_t)n * 8)); CKE(keys_b.alloc((size_t)n * 8));
-        CKE(vals_a.alloc((size_t)n * 4)); CKE(vals_b.alloc((size_t)n * 4));
-        CKE(child_s.alloc((size_t)n * 8)); CKE(cnt_s.alloc((size_t)n * 4));
-        CKE(cost_s.alloc((size_t)n * 28)); CKE(dec_s.alloc((size_t)n * 8));
-        CKE(nlo_s.alloc((size_t)2 * n * 16)); CKE(nhi_s.alloc((size_t)2 * n * 16));
-        CKE(cl_a.alloc((size_t)n * 4)); CKE(cl_b.alloc((size_t)n * 4)); CKE(nn_s.alloc((size_t)n * 4));
-        CKE(val_s.alloc((size_t)n * 4)); CKE(valid_s.alloc((size_t)n * 4)); CKE(pos_s.alloc((size_t)n * 4));
-        CKE(tasks_a.alloc((size_t)n * 8)); CKE(tasks_b.alloc((size_t)n * 8));
         size_t tmp_bytes = 0, tmp2_bytes = 0;
-        CKE(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
-                                            (uint32_t*)vals_a.p, (uint32_t*)vals_b.p, (int)n, 0, 63, stream));
-        CKE(tmp_s.alloc(tmp_bytes));
-        CKE(cub::DeviceScan::ExclusiveSum(nullptr, tmp2_bytes, (int*)valid_s.p, (int*)pos_s.p, (int)n, stream));
-        CKE(tmp2_s.alloc(tmp2_bytes));
+        CKE(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                            (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63, stream));
+        CKE(cub::DeviceScan::ExclusiveSum(nullptr, tmp2_bytes, (int*)nullptr, (int*)nullptr, (int)n, stream));
+        struct Buf { void* p; };
+        Arena arena;
+        const size_t sizes[] = {(size_t)n * 8, (size_t)n * 8, (size_t)n * 4, (size_t)n * 4, (size_t)n * 8, (size_t)n * 4, (size_t)n * 28, (size_t)n * 8,
+                                (size_t)2 * n * 16, (size_t)2 * n * 16, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
+                                (size_t)n * 4, (size_t)n * 8, (size_t)n * 8, tmp_bytes, tmp2_bytes};
+        size_t total = 0;
+        for (size_t b : sizes) total += Arena::pad(b);
+        CKE(arena.reserve(total));
+        Buf keys_a{arena.take(sizes[0])}, keys_b{arena.take(sizes[1])}, vals_a{arena.take(sizes[2])}, vals_b{arena.take(sizes[3])},
+            child_s{arena.take(sizes[4])}, cnt_s{arena.take(sizes[5])}, cost_s{arena.take(sizes[6])}, dec_s{arena.take(sizes[7])},
+            nlo_s{arena.take(sizes[8])}, nhi_s{arena.take(sizes[9])}, cl_a{arena.take(sizes[10])}, cl_b{arena.take(sizes[11])},
+            nn_s{arena.take(sizes[12])}, val_s{arena.take(sizes[13])}, valid_s{arena.take(sizes[14])}, pos_s{arena.take(sizes[15])},
+            tasks_a{arena.take(sizes[16])}, tasks_b{arena.take(sizes[17])}, tmp_s{arena.take(sizes[18])}, tmp2_s{arena.take(sizes[19])};
         k_morton<<<grid(n), TB, 0, stream>>>(d_plo, d_phi, n, d_ctr, (unsigned long long*)keys_a.p, (uint32_t*)vals_a.p);
         CKE(cub::DeviceRadixSort::SortPairs(tmp_s.p, tmp_bytes, (unsigned long long*)keys_a.p, (unsigned long long*)keys_b.p,
                                             (uint32_t*)vals_a.p, (uint32_t*)vals_b.p, (int)n, 0, 63, stream));

@@ -39,6 +39,11 @@ namespace fast {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
+#define GI_STAGED 12        // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 12 x 16 B x RTX_GI_BLOCK per CTA
+#ifndef RTX_GI_STAGE
+#define RTX_GI_STAGE 0      // 1: stage them (cp.async into per-thread shared-memory slots).  Bit-identical either way.  Measured on B200
+#endif                      // (profiles/r02_gi_step_staging.txt): k_gi_step 3.81 -> 4.11 ms per C2 pass (the 144 KB of shared memory per SM are
+                            // taken from the L1 that holds vertices, materials and lights), 2.81 -> 2.73 ms on C3: off by default
 
 // camera ray, shaders/Pass_init_di_v7.hlsl:59,80-95
 __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t W, uint32_t H, uint32_t x, uint32_t y, float jx, float jy,
@@ -287,33 +292,55 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
         pid = qin.pid[j];
-        float4 a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
+        // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the twelve 16-byte planes of this path are requested with
+        // cp.async straight into this thread's shared-memory slots — no registers are held while they are in flight (at 80 registers the
+        // compiler could keep two or three of the twelve float4 loads outstanding and serialised the rest next to their uses) — and they
+        // land while the hit's attributes (instance -> model -> indices -> vertices -> material) are fetched, a chain of four dependent
+        // loads that does not need the state.  Each thread reads back only its own slots, so no CTA barrier is needed.
+        extern __shared__ float4 s_stage[];
+        constexpr bool STAGE = RTX_GI_STAGE && !ITER0;
+        if (STAGE) {
+            const int planes[GI_STAGED] = {SP_N1, SP_O, SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_F, SP_ACC_FR, SP_GI_XN, SP_GI_NN, SP_GI_E3, SP_SH2, SP_SH1};
+#pragma unroll
+            for (int k = 0; k < GI_STAGED; k++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_stage[k * RTX_GI_BLOCK + threadIdx.x]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(&st.at(planes[k], pid)));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const f3 sample = xyz(qin.d_tmax[j]);
+        const uint32_t inst = hit_inst[j];
+        float4 ha = make_float4(0, 0, 0, 0);
+        HitInfo sp; MatOpt hm; f3 ke_full = mk3(0, 0, 0);
+        if (inst != 0xFFFFFFFFu) {                                  // hit attributes: independent of the path state (hitPosition is set below)
+            ha = hit_a[j];
+            ClosestHit(S, mk3(0, 0, 0), sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
+            hm = load_matopt(S, sp.materialID, &ke_full);
+        }
+        if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#define GI_STATE(K, PLANE) (!STAGE ? st.at(PLANE, pid) : s_stage[(K) * RTX_GI_BLOCK + threadIdx.x])
+        float4 a1 = GI_STATE(0, SP_N1), a2 = GI_STATE(1, SP_O);
         // iteration 0 starts from the state SamplePathSimple begins with (Path_Sampler_v7.hlsl:9-23): the path vertex is the primary hit
         // (SP_X1 / SP_N1 / SP_O), acc_f = acc_f_reconnection = 1, an empty GI reservoir, acc_pdf = 1 — k_di_finish does not write those
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
         const float4 one3 = make_float4(1, 1, 1, 0), zero4 = make_float4(0, 0, 0, 0);
-        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : st.at(SP_ORIGIN, pid);
-        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(st.at(SP_NORMAL, pid));
-        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(st.at(SP_OUTGOING, pid));
-        f3 acc_f = xyz(ITER0 ? one3 : st.at(SP_ACC_F, pid)), acc_fr = xyz(ITER0 ? one3 : st.at(SP_ACC_FR, pid));
-        float4 c0 = ITER0 ? zero4 : st.at(SP_GI_XN, pid), c1 = ITER0 ? make_float4(0, 0, 0, 1.0f) : st.at(SP_GI_NN, pid);
-        f3 xn = xyz(c0), nn = xyz(c1), E3 = xyz(ITER0 ? zero4 : st.at(SP_GI_E3, pid));
+        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(2, SP_ORIGIN);
+        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(GI_STATE(3, SP_NORMAL));
+        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(GI_STATE(4, SP_OUTGOING));
+        f3 acc_f = xyz(ITER0 ? one3 : GI_STATE(5, SP_ACC_F)), acc_fr = xyz(ITER0 ? one3 : GI_STATE(6, SP_ACC_FR));
+        float4 c0 = ITER0 ? zero4 : GI_STATE(7, SP_GI_XN), c1 = ITER0 ? make_float4(0, 0, 0, 1.0f) : GI_STATE(8, SP_GI_NN);
+        f3 xn = xyz(c0), nn = xyz(c1), E3 = xyz(ITER0 ? zero4 : GI_STATE(9, SP_GI_E3));
         float w_sum = c0.w, acc_pdf = c1.w;
-        const float4 sh2 = ITER0 ? zero4 : st.at(SP_SH2, pid);
-        f3 x1s = xyz(ITER0 ? zero4 : st.at(SP_SH1, pid)), x2s = xyz(sh2);
+        const float4 sh2 = ITER0 ? zero4 : GI_STATE(10, SP_SH2);
+        f3 x1s = xyz(ITER0 ? zero4 : GI_STATE(11, SP_SH1)), x2s = xyz(sh2);
+#undef GI_STATE
         float gi_has = sh2.w;                                       // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
         uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
         MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
-        const f3 sample = xyz(qin.d_tmax[j]);
-        const uint32_t inst = hit_inst[j];
         const float fnee = (float)S.nee_samples;
         bool cont = false;
         if (inst != 0xFFFFFFFFu) {                                  // miss: path ends (deviation D1)
-            const float4 ha = hit_a[j];
-            HitInfo sp;
-            ClosestHit(S, origin, sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
-            f3 ke_full;
-            const MatOpt hm = load_matopt(S, sp.materialID, &ke_full);
+            sp.hitPosition = origin + ha.x * sample;                // Hit_v7.hlsl:15 (the one line of ClosestHit that needs the path state)
             if (ITER0) {
                 if (!(length3(ke_full) > 0.0f)) {                   // Path_Sampler_v7.hlsl:55-98
                     const f3 incoming = normalize3(-sample);
@@ -734,7 +761,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
                 }
                 CKE(mark(SK_GI_STEP));
                 if (iter == 0u) k_gi_step<true><<<p.ggrid, RTX_GI_BLOCK, 0, p.stream>>>(st, S, p.qin, p.hit_a, p.hit_inst, p.sgi, p.qout, iter, B.ray_counters, perm);
-                else k_gi_step<false><<<p.ggrid, RTX_GI_BLOCK, 0, p.stream>>>(st, S, p.qin, p.hit_a, p.hit_inst, p.sgi, p.qout, iter, B.ray_counters, perm);
+                else k_gi_step<false><<<p.ggrid, RTX_GI_BLOCK, RTX_GI_STAGE ? GI_STAGED * RTX_GI_BLOCK * sizeof(float4) : 0, p.stream>>>(st, S, p.qin, p.hit_a, p.hit_inst, p.sgi, p.qout, iter, B.ray_counters, perm);
             } else if (iter < S.bounces) {
                 CKE(closest(p, p.qout));
                 p.qin = p.qout; p.cur ^= 1;
@@ -747,6 +774,11 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         }
         return cudaSuccess;
     };
+    static bool smem_opt_in = false;       // 72 KB of dynamic shared memory per CTA: above the 48 KB a kernel gets without asking
+    if (RTX_GI_STAGE && !smem_opt_in) {
+        CKE(cudaFuncSetAttribute(k_gi_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GI_STAGED * RTX_GI_BLOCK * sizeof(float4))));
+        smem_opt_in = true;
+    }
     CKE(cudaEventRecord(T->ev[0], stream));
     if (parts > 1) {
         CKE(cudaEventRecord(B.ev_fork, stream));

@@ -305,6 +305,27 @@ def test_legacy_rr_estimator_bit_exact(rtdx, orc, scene_name):
     ctx.close()
 
 
+def test_call_order_violations_return_state_errors_not_faults(rtdx):
+    """rtx_upload_model after rtx_set_instances invalidates the per-model tables; rendering or tracing before the
+    next rtx_set_instances must fail with RTX_ERR_STATE, not hand freed tables to the kernels — and the context stays usable."""
+    sc = rtdx.scenes.cornell()
+    ctx, up = _upload(rtdx, sc, 32, 32, bounces=2)
+    ctx.render_pass(0, 1); ctx.synchronize()
+    m = sc.models[0]
+    ctx.upload_model(m["vertices"], m["indices"], m["material_id_offset"])           # a second model arrives late
+    for call in (lambda: ctx.render_pass(1, 1), lambda: ctx.trace(rtdx.scenes.camera_rays(up["camera"], 8, 8))):
+        with pytest.raises(rtdx.RtxError) as e:
+            call()
+        assert "rtx error 3" in str(e.value)
+    ctx.set_instances(up["descs"], up["props"])                                       # OnUpdate again: everything is valid again
+    ctx.reset_accum(); ctx.render_pass(0, 1); ctx.synchronize()
+    a = ctx.read_accum()
+    ctx2, _ = _upload(rtdx, sc, 32, 32, bounces=2)
+    ctx2.render_pass(0, 1); ctx2.synchronize()
+    assert np.array_equal(bits(a), bits(ctx2.read_accum()))
+    ctx.close(); ctx2.close()
+
+
 def test_fast_math_mode_converges_to_the_exact_image(rtdx, orc):
     """RTX_FLAG_FAST_MATH (shading stages built with FMA contraction and approximate div / sqrt / rsqrt / sincos): not bit-identical —
     a path diverges where a rounding flips a discrete decision — but the same estimator: BASELINE.json asks for radiance "within a

@@ -129,6 +129,30 @@ def test_no_cpu_fallback(rtdx):
     assert lib.rtx_create(C.byref(cfg), C.byref(h)) == 1 and b"struct_size" in lib.rtx_last_error()
 
 
+def test_create_validates_the_path_length_before_touching_a_device(rtdx):
+    """bounces is bounded by the per-part queue-counter block (E0) and by the legacy estimator's bookkeeping."""
+    lib = rtdx.load_library()
+    for bounces, flags, ok_arg in ((120, 0, True), (121, 0, False), (61, rtdx.FLAG_LEGACY_RR, False), (60, rtdx.FLAG_LEGACY_RR, True)):
+        cfg = rtdx.RtxConfig(C.sizeof(rtdx.RtxConfig), 0, 16, 16, bounces, 4, 4, flags, 1, None)
+        h = C.c_void_p()
+        st = lib.rtx_create(C.byref(cfg), C.byref(h))
+        if h:
+            lib.rtx_destroy(h)
+        if ok_arg:
+            assert st != 1, lib.rtx_last_error()             # passes the argument check (fails later only for want of a GPU)
+        else:
+            assert st == 1 and b"bounces" in lib.rtx_last_error()
+
+
+def test_engine_free_host_library_has_no_cuda_dependency(rtdx):
+    """The CPU arms of bench.py and the scene builders prepare their inputs through librdx_prep.so, which must not pull in the engine."""
+    import subprocess
+    out = subprocess.run(["ldd", rtdx.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "librtx_b200" not in out and "libcuda" not in out and "libcudart" not in out
+    out = subprocess.run(["ldd", rtdx.HOST_FULL_LIB_PATH], capture_output=True, text=True).stdout
+    assert "librtx_b200" in out                                # the C++ Renderer class does link the engine
+
+
 def test_product_does_not_reference_the_oracle():
     """The product path may not import, link or call anything under oracle/."""
     pkg = os.path.join(ROOT, "royaltracer-dx_b200")
