@@ -73,10 +73,13 @@ __device__ __forceinline__ uint2 tea4_body(uint2 seed) {
     }
     return make_uint2(v0, v1);
 }
-#ifdef RTX_TEA_NOINLINE
-static __device__ __noinline__ uint2 tea4(uint2 seed) { return tea4_body(seed); }
-#else
+// One out-of-line copy per kernel: the shading stages draw ~20 numbers per bounce, inlined that is ~1200 of k_gi_step's 4000 SASS
+// instructions, and the kernel stalls on instruction fetch (ncu: no_instruction 1.65 stall cycles per issue).  k_gi_step 3.78 -> 3.70 ms
+// per C2 pass (profiles/r02_s1_stage_times.txt); -DRTX_TEA_INLINE restores the inlined form.
+#ifdef RTX_TEA_INLINE
 __device__ __forceinline__ uint2 tea4(uint2 seed) { return tea4_body(seed); }
+#else
+static __device__ __noinline__ uint2 tea4(uint2 seed) { return tea4_body(seed); }
 #endif
 __device__ __forceinline__ float RandomFloat(uint2& seed) {
     seed = tea4(seed);

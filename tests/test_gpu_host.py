@@ -122,3 +122,39 @@ def test_cpp_host_renderer_end_to_end(rtdx, orc, tmp_path):
     assert int(tail[1]) == zlib.crc32(ctx.read_output().tobytes())
     osc.free_frames(frames)
     ctx.close()
+
+
+def test_cpp_host_two_ranks_with_the_engine_side_reduce(rtdx, tmp_path):
+    """Two host_main processes, one per GPU, joined through rtx_comm_init (NCCL id handed over in a file) render the samples
+    s = rank (mod 2) and reduce gPermanentData to rank 0 after every pass (rtx_reduce_accum): rank 0's reduced buffer must equal the sum
+    of the two ranks' partial sums rendered here in one process (a + b is the same in either order)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    paths = write_scene(tmp_path)
+    W, H, FRAMES = 96, 64, 3
+    xms = [rtdx.xmmatrix_from_colvec(np.eye(4)), rtdx.xmmatrix_from_colvec(np.eye(4))]
+    np.ascontiguousarray(np.stack(xms), dtype=np.float32).tofile(str(tmp_path / "xforms.bin"))
+    exe = build_host_main(tmp_path)
+    idf = str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RTX_HOST_NCCL_ID=idf, RTX_HOST_RANK=str(r), RTX_HOST_WORLD="2")
+        procs.append(subprocess.Popen([exe, str(W), str(H), str(FRAMES), str(tmp_path / "xforms.bin")] + paths, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1] for o in outs]
+    rank0 = [dict(zip(l.split()[2::2], (int(x) for x in l.split()[3::2]))) for l in outs[0][0].splitlines() if l.startswith("frame")]
+    sc = rtdx.scenes.from_obj_files(paths, name="host")
+    parts = []
+    for r in range(2):
+        ctx = rtdx.Context(W, H, bounces=3)
+        ctx.upload_scene(sc)
+        acc = []
+        for f in range(FRAMES):
+            ctx.render_pass(f * 2 + r, 1); ctx.synchronize()
+            acc.append(ctx.read_accum())
+        parts.append(acc); ctx.close()
+    for f in range(FRAMES):
+        total = parts[0][f] + parts[1][f]
+        assert rank0[f]["accum_crc"] == zlib.crc32(total.tobytes()), f

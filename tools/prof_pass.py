@@ -15,6 +15,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--bounces", type=int, default=6)
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--opt", action="append", default=[], help="engine option NAME=VALUE, e.g. PASS_PARTS=1")
 a = ap.parse_args()
 if a.scene == "mesh":
     sc = rtdx.scenes.mesh_room(n=a.side)
@@ -24,6 +25,9 @@ else:
     sc = rtdx.scenes.cornell()
 ctx = rtdx.Context(a.width, a.height, bounces=a.bounces, flags=a.flags)
 ctx.upload_scene(sc)
+for o in a.opt:
+    k, v = o.split("=")
+    ctx.set_option(getattr(rtdx, "OPT_" + k), int(v, 0))
 for p in range(a.passes):
     ctx.render_pass(p, 1)
 ctx.synchronize()
