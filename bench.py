@@ -641,7 +641,7 @@ def main():
             for tris in (1_000_000, 10_000_000):
                 a2 = argparse.Namespace(**vars(args)); a2.tris = tris; a2.no_cpu_baseline = args.no_cpu_baseline or tris > 2_000_000
                 r = run_trace(rtdx, D, config_of("C5", a2), a2, 5, 2)
-                extras["C5_%dM" % (tris // 1_000_000)] = {k: r.get(k) for k in ("config", "value", "ms_per_step", "batches", "roofline", "cpu_baseline", "parity")}
+                extras["C5_%dM" % (tris // 1_000_000)] = {k: r.get(k) for k in ("config", "value", "ms_per_step", "batches", "roofline", "cpu_baseline", "parity", "blas")}
         c4 = run_c4_strong(rtdx, D, args)
     if D.rank == 0:
         line = {

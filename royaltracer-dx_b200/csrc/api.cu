@@ -329,6 +329,13 @@ extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* des
         }
         c->tlas_models.resize(n);
         for (uint32_t i = 0; i < n; i++) c->tlas_models[i] = (uint32_t)descs[i].blas;
+        // The traversal stack (RTX_STACK_SIZE = 40 entries per ray) holds at most one entry per level of the node path being descended
+        // plus one parked instance-leaf group per TLAS level: reject a TLAS + BLAS pair that could overflow it before anything is traced
+        // (the kernels still raise the context's overflow word if it ever happens, check_overflow).
+        uint32_t blas_levels = 0;
+        for (uint32_t i = 0; i < n; i++) blas_levels = std::max(blas_levels, c->models[descs[i].blas].bvh.n_levels);
+        if (e == cudaSuccess && 2u * c->tlas.n_levels + blas_levels + 2u > 40u)
+            return fail(RTX_ERR_STATE, "rtx_set_instances: TLAS + BLAS too deep for the traversal stack (RTX_STACK_SIZE)");
     }
     c->launches += 6;
     RTX_CK(e);

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, RTX_TRACE_MINB)
 trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restrict__ d_tmax,
              const uint32_t* __restrict__ n_ptr, uint32_t n_fixed, unsigned int* __restrict__ cursor,
              float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int sched,
-             const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_heavy_ptr, uint32_t cap) {
+             const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_heavy_ptr, uint32_t cap,
+             const uint32_t* __restrict__ vis_pid, float* __restrict__ vis) {
     // trace order (wavefront.h RayQueue): claim k -> slot order[k] (k < n_heavy) or order[cap-1-(k-n_heavy)]: expensive rays first
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
     const uint32_t n_heavy = order ? *n_heavy_ptr : 0u;
@@ -113,7 +114,9 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
             {                                                                                                  \
                 const uint32_t j = __float_as_uint(C.wo->w);                                                   \
                 if (!ANY_HIT) { const float4 h = *C.hit; hit_a[j] = make_float4(T.ht, h.x, h.y, h.z); }        \
-                hit_inst[j] = T.hinst;                                                                         \
+                /* any-hit with a visibility array: an occluded ray clears its path's entry (no scatter kernel) */ \
+                if (ANY_HIT && vis) { if (T.hinst != 0xFFFFFFFFu) vis[__ldg(vis_pid + j)] = 0.0f; }            \
+                else hit_inst[j] = T.hinst;                                                                    \
             }
             if (pend == PEND_TRI) {
                 if (do_tri) {
@@ -171,7 +174,8 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
 
 cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
                          unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
-                         cudaStream_t stream, int grid_share, const uint32_t* order, const uint32_t* n_heavy_ptr, uint32_t cap) {
+                         cudaStream_t stream, int grid_share, const uint32_t* order, const uint32_t* n_heavy_ptr, uint32_t cap,
+                         const uint32_t* vis_pid, float* vis) {
     // `cursor` = two words, both 0 between launches: [0] the ray cursor, [1] the count of finished CTAs; the last CTA of a launch
     // resets [0] (and atomicInc wraps [1]), so no memset precedes the launch.
     const int sms = S.num_sms > 0 ? S.num_sms : 148;
@@ -181,11 +185,11 @@ cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d
     const int ctas = S.ctas_per_sm > 0 ? min(S.ctas_per_sm, RTX_TRACE_MINB) : RTX_TRACE_MINB;
     const int grid = max(sms, sms * ctas * waves / max(grid_share, 1));
     if (stats) {
-        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap);
-        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap);
+        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
+        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
     } else {
-        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap);
-        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap);
+        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
+        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
     }
     return cudaGetLastError();
 }

@@ -640,14 +640,6 @@ void wave_free(WaveBuffers* B) {
     *B = WaveBuffers();
 }
 
-// any-hit trace whose result is scattered to a per-path visibility array
-__global__ void __launch_bounds__(WF_BLOCK)
-k_scatter_vis(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ pid, const uint32_t* __restrict__ hit_inst, float* __restrict__ vis) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= *n_ptr) return;
-    if (hit_inst[j] != 0xFFFFFFFFu) vis[pid[j]] = 0.0f;
-}
-
 // One DispatchRays-equivalent.  The frame's paths are cut into `parts` contiguous ranges that run the whole stage sequence independently,
 // part 0 on the caller's stream and the others on auxiliary streams (forked from and joined back into the caller's stream with events):
 // every persistent traversal launch ends in a tail in which a few warps finish the longest rays on an otherwise empty GPU (0.14 ms of a
@@ -714,10 +706,9 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     };
     auto shadow = [&](Part& p, const RayQueue& q, float* vis) -> cudaError_t {
         CKE(mark(SK_ANY));
-        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts, q.order, q.n_heavy, q.cap));
-        CKE(mark(SK_SCATTER));
-        k_scatter_vis<<<p.grid, WF_BLOCK, 0, p.stream>>>(q.count, q.pid, p.hit_inst, vis);
-        return cudaSuccess;
+        // the occlusion result goes straight to the per-path visibility array (the separate scatter kernel of round 1 is gone)
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts, q.order, q.n_heavy, q.cap,
+                            q.pid, vis);
     };
     // stage s of one part; the parts are issued round-robin stage by stage so that every stream always has work queued
     const int n_stages = 7 + 2 * ((int)S.bounces + 1) + 2;

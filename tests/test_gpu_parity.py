@@ -305,6 +305,37 @@ def test_legacy_rr_estimator_bit_exact(rtdx, orc, scene_name):
     ctx.close()
 
 
+def test_builder_quality_and_shape(rtdx):
+    """The GPU builder (Morton -> PLOC with the SAH programme -> 8-wide collapse) beyond "the hits are right": node fan-out, leaf size,
+    SAH cost and the per-ray work it leads to stay inside bounds a regression in any stage would break; a TLAS holds ONE instance per leaf
+    slot (a ray enters only the instances whose own boxes it hits)."""
+    sc = rtdx.scenes.mesh_room(n=64)                      # 49 152 triangles + the 14-triangle room
+    ctx, up = _upload(rtdx, sc, 256, 144)
+    info = ctx.blas_info(up["model_ids"][0])
+    n_tris = sc.models[0]["indices"].size // 3
+    assert info["n_tris"] == n_tris
+    assert n_tris / 24 <= info["n_nodes"] <= n_tris / 4          # 8 children of <= 3 triangles: between full and a quarter full
+    assert 0.5 < info["build_ms"] < 2000
+    rays = rtdx.scenes.camera_rays(up["camera"], 256, 144)
+    import torch
+    r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda(); h = torch.empty((r.shape[0], 5), dtype=torch.float32, device="cuda")
+    ctx.reset_counters(); ctx.trace_device(r.data_ptr(), r.shape[0], h.data_ptr(), stats=True); ctx.synchronize()
+    c = ctx.counters(); n = r.shape[0]
+    nodes, tris, inst = c["nodes_visited"] / n, c["tris_tested"] / n, c["instances_entered"] / n
+    assert nodes < 9.0 and tris < 8.0, (nodes, tris)             # measured 5.3 / 4.9: a broken SAH collapse or slot order doubles them
+    assert 1.0 <= inst < 1.6                                     # the room always, the mesh only when its own box is hit (round 1: 2.000)
+    ctx.close()
+    sc = rtdx.scenes.instanced_blobs(n_models=3, n_side=6, lattice=6)      # 216 instances: a multi-level TLAS
+    ctx, up = _upload(rtdx, sc, 128, 128)
+    rays = rtdx.scenes.camera_rays(up["camera"], 128, 128)
+    r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda(); h = torch.empty((r.shape[0], 5), dtype=torch.float32, device="cuda")
+    ctx.reset_counters(); ctx.trace_device(r.data_ptr(), r.shape[0], h.data_ptr(), stats=True); ctx.synchronize()
+    c = ctx.counters()
+    hit = (h[:, 4].view(torch.int32) != -1).float().mean().item()
+    assert c["instances_entered"] / r.shape[0] < 1.5 + 2.0 * hit  # a few instance records per ray that hits something, not the leaf's neighbours too
+    ctx.close()
+
+
 def test_call_order_violations_return_state_errors_not_faults(rtdx):
     """rtx_upload_model after rtx_set_instances invalidates the per-model tables; rendering or tracing before the
     next rtx_set_instances must fail with RTX_ERR_STATE, not hand freed tables to the kernels — and the context stays usable."""

@@ -75,7 +75,19 @@ for gen_i in range(3):
     print("   rays that hit the mesh's box: %.1f %%" % (100.0 * heavy.float().mean().item()))
     timed(b1[torch.argsort(heavy.to(torch.int32), descending=True, stable=True)].contiguous(), "bounce %d heavy rays FIRST" % (gen_i + 1))
     timed(b1[torch.argsort(heavy.to(torch.int32), descending=False, stable=True)].contiguous(), "bounce %d heavy rays LAST" % (gen_i + 1))
-    for bits in (4,):
+    # finer cost classes inside the heavy rays: chord length of the segment inside the box, origin inside the box
+    lo_t, hi_t = torch.tensor((-1.75, 0.25, -1.75), device="cuda"), torch.tensor((1.75, 3.75, 1.75), device="cuda")
+    inv = 1.0 / b1[:, 4:7]
+    t0 = (lo_t - b1[:, 0:3]) * inv; t1 = (hi_t - b1[:, 0:3]) * inv
+    tn = torch.minimum(t0, t1).max(1).values.clamp(min=1e-3); tf = torch.maximum(t0, t1).min(1).values
+    chord = (tf - tn).clamp(min=0) * heavy
+    inside = ((b1[:, 0:3] > lo_t) & (b1[:, 0:3] < hi_t)).all(1)
+    timed(b1[torch.argsort(chord, descending=True, stable=True)].contiguous(), "bounce %d by chord in box, desc" % (gen_i + 1))
+    cls = heavy.to(torch.int32) + (heavy & inside).to(torch.int32)
+    timed(b1[torch.argsort(cls, descending=True, stable=True)].contiguous(), "bounce %d 3 classes (inside first)" % (gen_i + 1))
+    cls2 = heavy.to(torch.int32) + (heavy & ~inside).to(torch.int32)
+    timed(b1[torch.argsort(cls2, descending=True, stable=True)].contiguous(), "bounce %d 3 classes (outside first)" % (gen_i + 1))
+    for bits in ():
         ko, kc = keys(b1, bits)
         timed(b1[torch.argsort(ko)].contiguous(), "bounce %d sorted oct|cell%d" % (gen_i + 1, bits))
         timed(b1[torch.argsort(kc)].contiguous(), "bounce %d sorted cell%d|oct" % (gen_i + 1, bits))
