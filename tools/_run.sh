@@ -1,6 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc $?"
-tail -12 gpurun_out/pytest_gpu.txt
-python tools/stage_times.py --tag "C2" 2>&1 | cut -c1-220
-python tools/pass_time.py --tag "C2 2parts" 2>&1
+N=${1:-8}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_s1_scale_n$N.json 2> gpurun_out/r02_scale_n$N.err
+echo "bench n$N rc $?"; tail -3 gpurun_out/r02_scale_n$N.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02_s1_scale_n$N.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step","n_gpus","gpu_launches")}, d["e2e"], d["c4_strong"])
+PY
