@@ -381,6 +381,7 @@ extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
 
 static SceneAS make_as(rtx_ctx* c) {
     SceneAS a;
+    memset(&a, 0, sizeof a);            // (padding bytes too: the wavefront compares these structs bytewise to reuse a captured pass)
     a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
     a.one_bits = 0x3F800000u;
     a.overflow = c->d_overflow;
@@ -411,6 +412,7 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
     if (!c->d_lights && (st = rtx_set_emissive_triangles(c, nullptr, 0)) != RTX_OK) return st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     SceneData S;
+    memset(&S, 0, sizeof S);
     S.models = c->d_model_refs; S.inst_model = c->d_inst_model; S.props = c->d_props;
     S.material_ids = c->d_material_ids; S.n_material_ids = c->n_material_ids;
     S.materials = c->d_materials; S.n_materials = c->n_materials;
@@ -454,6 +456,7 @@ extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     if ((st = ensure_restir(c)) != RTX_OK) return st;
     SceneData S;
+    memset(&S, 0, sizeof S);
     S.models = c->d_model_refs; S.inst_model = c->d_inst_model; S.props = c->d_props;
     S.material_ids = c->d_material_ids; S.n_material_ids = c->n_material_ids;
     S.materials = c->d_materials; S.n_materials = c->n_materials;
@@ -871,6 +874,7 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     else if (option == RTX_OPT_TRACE_SCHED) c->sched = (int)(value & 0xffffffu);
     else if (option == RTX_OPT_TRACE_WAVES) { if (value > 8u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_WAVES must be 0..8"); c->waves = (int)value; }
     else if (option == RTX_OPT_QUEUE_LPT) c->lpt = value != 0;
+    else if (option == RTX_OPT_PASS_GRAPH) c->wb.use_graph = value != 0;
     else if (option == RTX_OPT_TRACE_CTAS) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_CTAS must be 0..32"); c->ctas_per_sm = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;

@@ -59,7 +59,9 @@ __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t
 
 __global__ void __launch_bounds__(WF_BLOCK)
 k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
-           uint32_t first_sample, uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi, unsigned long long* ray_counters) {
+           const uint32_t* __restrict__ first_sample_ptr, uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi,
+           unsigned long long* ray_counters) {
+    const uint32_t first_sample = *first_sample_ptr;     // a device word, so that a captured pass (CUDA graph) can be replayed for any sample
     // paths [p0, p0 + np) of the pass (one part of the frame, see wave_render_pass); queue slot = index within the part
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) { *q0.count = np; atomicAdd(&ray_counters[2], (unsigned long long)np); }
@@ -620,6 +622,7 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMemset(B->accum, 0, (size_t)npx * 16));
     CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
     CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
+    CKE(cudaMalloc((void**)&B->first_sample, 4));
     CKE(cudaMalloc((void**)&B->debug, 64 * 4));
     CKE(cudaMalloc((void**)&B->perm, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->bin_keys, (size_t)n));
@@ -635,7 +638,8 @@ void wave_free(WaveBuffers* B) {
     if (B->ev_fork) cudaEventDestroy(B->ev_fork);
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
-    void* ptrs[] = {B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
+    if (B->graph_exec) cudaGraphExecDestroy(B->graph_exec);
+    void* ptrs[] = {B->first_sample, B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
     for (void* p : ptrs) if (p) cudaFree(p);
     *B = WaveBuffers();
 }
@@ -645,23 +649,26 @@ void wave_free(WaveBuffers* B) {
 // every persistent traversal launch ends in a tail in which a few warps finish the longest rays on an otherwise empty GPU (0.14 ms of a
 // 0.43 ms launch at 1080p, profiles/r01_s4_*), and the other parts' kernels fill it.  Paths never interact before the accumulation, so the
 // result does not depend on `parts`.
-cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
-                             uint64_t* launches, PassTiming* T, bool accumulate) {
-    const uint32_t npx = S.width * S.height;
-    const uint32_t n = npx * spp;
-    if (n > B.n_paths) return cudaErrorInvalidValue;
-    StateView st{B.state, n};
-    uint64_t L = 0;
-    T->n_marks = 0;
+static int pass_parts(const WaveBuffers& B, const SceneData& S, const PassTiming* T, uint32_t n, bool accumulate) {
     int parts = B.parts < 1 ? 1 : (B.parts > WAVE_MAX_PARTS ? WAVE_MAX_PARTS : B.parts);
     // per-launch events, the counting traversal variant, the material-binned queues and the ReSTIR frame (which reads the hit records
     // of the whole frame afterwards) run as one part
     if (T->stage_timing || T->stats || !accumulate || (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) || n < 65536u) parts = 1;
-    for (int h = 1; h < parts; h++) {
-        if (!B.aux[h - 1]) CKE(cudaStreamCreateWithFlags(&B.aux[h - 1], cudaStreamNonBlocking));
-        if (!B.ev_join[h - 1]) CKE(cudaEventCreateWithFlags(&B.ev_join[h - 1], cudaEventDisableTiming));
-    }
-    if (parts > 1 && !B.ev_fork) CKE(cudaEventCreateWithFlags(&B.ev_fork, cudaEventDisableTiming));
+    return parts;
+}
+
+__global__ void k_set_word(uint32_t* p, uint32_t v) { *p = v; }
+
+// the launches of one pass on `stream` (+ the auxiliary streams); the sample index comes from B.first_sample, so the same sequence serves
+// every pass of a static configuration: wave_render_pass captures it into a CUDA graph
+static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t spp, cudaStream_t stream, uint64_t* launches,
+                                  PassTiming* T, bool accumulate) {
+    const uint32_t npx = S.width * S.height;
+    const uint32_t n = npx * spp;
+    StateView st{B.state, n};
+    uint64_t L = 0;
+    T->n_marks = 0;
+    const int parts = pass_parts(B, S, T, n, accumulate);
 
     struct Part {
         cudaStream_t stream; uint32_t p0, np; unsigned grid, ggrid;
@@ -719,7 +726,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         if (s == 0) {
             CKE(cudaMemsetAsync(p.counts, 0, 384 * 4, p.stream));
             CKE(mark(SK_GENERATE));
-            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, p.p0, p.np, q0, B.cam, S.width, S.height, first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
+            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, p.p0, p.np, q0, B.cam, S.width, S.height, B.first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
                                                           B.ray_counters);
         } else if (s == 1) {
             CKE(closest(p, q0));
@@ -765,12 +772,6 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         }
         return cudaSuccess;
     };
-    static bool smem_opt_in = false;       // 72 KB of dynamic shared memory per CTA: above the 48 KB a kernel gets without asking
-    if (RTX_GI_STAGE && !smem_opt_in) {
-        CKE(cudaFuncSetAttribute(k_gi_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GI_STAGED * RTX_GI_BLOCK * sizeof(float4))));
-        smem_opt_in = true;
-    }
-    CKE(cudaEventRecord(T->ev[0], stream));
     if (parts > 1) {
         CKE(cudaEventRecord(B.ev_fork, stream));
         for (int h = 1; h < parts; h++) CKE(cudaStreamWaitEvent(P[h].stream, B.ev_fork, 0));
@@ -786,10 +787,81 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         CKE(mark(SK_ACCUMULATE));
         k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
     }
-    CKE(cudaEventRecord(T->ev[1], stream));
     CKE(cudaGetLastError());
     if (launches) *launches += L;
     return cudaSuccess;
+}
+
+// What a captured pass depends on besides the sample index: every kernel argument is in here (device pointers, counts, flags, bounds).
+struct GraphKey { SceneData S; SceneAS AS; uint32_t spp; int parts; int variant; cudaStream_t stream; };
+static_assert(sizeof(GraphKey) <= sizeof(WaveBuffers().graph_key), "WaveBuffers::graph_key too small");
+
+cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
+                             uint64_t* launches, PassTiming* T, bool accumulate) {
+    const uint32_t n = S.width * S.height * spp;
+    if (n > B.n_paths) return cudaErrorInvalidValue;
+    const int parts = pass_parts(B, S, T, n, accumulate);
+    for (int h = 1; h < parts; h++) {       // (never inside a capture)
+        if (!B.aux[h - 1]) CKE(cudaStreamCreateWithFlags(&B.aux[h - 1], cudaStreamNonBlocking));
+        if (!B.ev_join[h - 1]) CKE(cudaEventCreateWithFlags(&B.ev_join[h - 1], cudaEventDisableTiming));
+    }
+    if (parts > 1 && !B.ev_fork) CKE(cudaEventCreateWithFlags(&B.ev_fork, cudaEventDisableTiming));
+    static bool smem_opt_in = false;       // 72 KB of dynamic shared memory per CTA: above the 48 KB a kernel gets without asking
+    if (RTX_GI_STAGE && !smem_opt_in) {
+        CKE(cudaFuncSetAttribute(k_gi_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GI_STAGED * RTX_GI_BLOCK * sizeof(float4))));
+        smem_opt_in = true;
+    }
+    k_set_word<<<1, 1, 0, stream>>>(B.first_sample, first_sample);
+    if (launches) *launches += 1;
+
+    // ---- CUDA graph of the pass.  A pass is ~50 dependent launches per path range plus memsets and the fork / join of the auxiliary
+    // streams; for a static configuration (same buffers, counts, flags, bounds as the pass before) the sequence is captured once and
+    // replayed: one graph launch per pass instead of ~100 stream operations.  The first pass of a new configuration runs directly, the
+    // second one captures (a scene whose instances move every frame never pays for captures).  Passes with per-launch events, the
+    // counting variant, the ReSTIR frame or a pending multi-GPU reduce (an event from outside the capture) always run directly.
+    const bool graph_ok = B.use_graph && accumulate && !T->stage_timing && !T->stats && !B.wait_before_accumulate;
+    GraphKey key;
+    memset(&key, 0, sizeof key);
+    memcpy(&key.S, &S, sizeof S); memcpy(&key.AS, &AS, sizeof AS);
+    key.spp = spp; key.parts = parts; key.stream = stream;
+#ifdef RTX_FAST_MATH
+    key.variant = 1;
+#endif
+    CKE(cudaEventRecord(T->ev[0], stream));
+    bool done = false;
+    if (graph_ok) {
+        if (B.graph_exec && memcmp(&key, B.graph_key, sizeof key) != 0 && B.have_last_key && memcmp(&key, B.last_key, sizeof key) == 0) {
+            cudaGraphExecDestroy(B.graph_exec); B.graph_exec = nullptr;        // the configuration changed and has settled again
+        }
+        if (!B.graph_exec && B.have_last_key && memcmp(&key, B.last_key, sizeof key) == 0) {
+            cudaGraph_t g = nullptr;
+            uint64_t L = 0;
+            cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                e = wave_pass_body(B, S, AS, spp, stream, &L, T, accumulate);
+                const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
+                if (e == cudaSuccess) e = e2;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&B.graph_exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess) {            // no graph for this context then: the direct path below is always valid
+                cudaGetLastError();
+                B.graph_exec = nullptr; B.use_graph = false;
+            } else {
+                memcpy(B.graph_key, &key, sizeof key); B.graph_launches = L;
+            }
+        }
+        if (B.graph_exec && memcmp(&key, B.graph_key, sizeof key) == 0) {
+            CKE(cudaGraphLaunch(B.graph_exec, stream));
+            if (launches) *launches += B.graph_launches;
+            T->n_marks = 0;
+            done = true;
+        }
+    }
+    memcpy(B.last_key, &key, sizeof key); B.have_last_key = true;
+    if (!done) CKE(wave_pass_body(B, S, AS, spp, stream, launches, T, accumulate));
+    CKE(cudaEventRecord(T->ev[1], stream));
+    return cudaGetLastError();
 }
 
 cudaError_t wave_accumulate(WaveBuffers& B, uint32_t npx, uint32_t spp, cudaStream_t stream) {

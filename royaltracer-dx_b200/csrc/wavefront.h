@@ -57,6 +57,10 @@ struct WaveBuffers {
     unsigned int* cursor = nullptr;    // 4 words per part (launch_trace)
     unsigned long long* ray_counters = nullptr;   // [0] closest, [1] shadow, [2] paths
     const float4* resolve_source = nullptr;   // rtx_set_resolve_source: an external accumulation buffer (the multi-GPU sum) to resolve instead
+    uint32_t* first_sample = nullptr;  // device word: the sample index of the pass being rendered (k_generate reads it)
+    // CUDA graph of a pass (wavefront.cu wave_render_pass): replayed while the configuration (graph_key) stays what was captured
+    bool use_graph = true, have_last_key = false; cudaGraphExec_t graph_exec = nullptr; uint64_t graph_launches = 0;
+    unsigned char graph_key[512] = {}, last_key[512] = {};
     cudaEvent_t wait_before_accumulate = nullptr;   // multi-GPU: the pending reduce of gPermanentData (k_accumulate rewrites it)
     float4* accum = nullptr;           // gPermanentData
     uint8_t* output = nullptr;         // gOutput slice 0

@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=${1:-8}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_s1_scale_n$N.json 2> gpurun_out/r02_scale_n$N.err
-echo "bench n$N rc $?"; tail -3 gpurun_out/r02_scale_n$N.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/r02_s1_scale_n$N.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ("value","ms_per_step","n_gpus","gpu_launches")}, d["e2e"], d["c4_strong"])
-PY
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc $?"
+tail -6 gpurun_out/pytest_gpu.txt
+python tools/pass_time.py --opt PASS_GRAPH=0 --tag "C2 2parts nograph" 2>&1
+python tools/pass_time.py --opt PASS_GRAPH=1 --tag "C2 2parts graph" 2>&1
+python tools/pass_time.py --opt PASS_GRAPH=1 --opt PASS_PARTS=1 --tag "C2 1part graph" 2>&1
+python tools/pass_time.py --opt PASS_GRAPH=0 --opt PASS_PARTS=1 --tag "C2 1part nograph" 2>&1
+python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'])"
