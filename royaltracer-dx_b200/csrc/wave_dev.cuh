@@ -6,6 +6,8 @@ namespace rtx {
 
 struct StateView {
     float4* base; uint32_t n;
+    uint2* seed;          // the path's RNG state in its own 8-byte plane: every stage updates it, and as the .w of two float4 planes it cost a
+                          // 32-byte read and a 32-byte write per path and stage to move 8 bytes (E0 stages only; nullptr elsewhere)
 #ifdef RTX_STATE_AOS
     // one 288-byte record per path (9 whole 32-byte sectors): a thread's accesses use every byte of the sectors it touches whatever the
     // order of the path ids in its warp — queues that are not in pixel order (two-ended LPT queues, material bins) cost no extra sectors

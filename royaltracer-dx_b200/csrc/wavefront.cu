@@ -79,8 +79,8 @@ k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, con
         q0.o_tmin[k] = f4(o, 0.0001f);
         q0.d_tmax[k] = f4(dir, 10000.0f);
         q0.pid[k] = p;
-        st.at(SP_N1, p) = make_float4(0, 0, 0, __uint_as_float(seed.x));
-        st.at(SP_O, p) = f4u(-dir, seed.y);
+        st.seed[p] = seed;
+        st.at(SP_O, p) = f4(-dir, 0.0f);
         st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
         vis_di[p] = 1.0f; vis_gi[p] = 1.0f;
     }
@@ -139,7 +139,7 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
                 st.at(SP_X1, pid) = f4u(mk3(0, 0, 0), payload.materialID);
                 st.at(SP_DI_L2, pid) = f4u(mk3(0, 0, 0), inst);
             } else {
-                uint2 seed = make_uint2(__float_as_uint(st.at(SP_N1, pid).w), __float_as_uint(st.at(SP_O, pid).w));
+                uint2 seed = st.seed[pid];
                 const f3 outgoing = -d;
                 const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, payload.hitNormal, seed);
                 f3 rx = mk3(0, 0, 0), rn = mk3(0, 0, 0), rL = mk3(0, 0, 0); float w_sum = 0.0f;
@@ -158,8 +158,9 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
                 const f3 sample = SampleBRDF(strategy, mat, outgoing, payload.hitNormal, seed);   // Sampler_v7.hlsl:218-220
                 emit = true; ro = payload.hitPosition; rd = sample;
                 st.at(SP_X1, pid) = f4u(payload.hitPosition, payload.materialID);
-                st.at(SP_N1, pid) = f4u(payload.hitNormal, seed.x);
-                st.at(SP_O, pid) = f4u(outgoing, seed.y);
+                st.at(SP_N1, pid) = f4(payload.hitNormal, 0.0f);
+                st.at(SP_O, pid) = f4(outgoing, 0.0f);
+                st.seed[pid] = seed;
                 st.at(SP_DI_X2, pid) = f4(rx, w_sum);
                 st.at(SP_DI_N2, pid) = f4(rn, 0.0f);
                 st.at(SP_DI_L2, pid) = f4u(rL, inst);              // .w: primary-hit instance (SampleData::objID)
@@ -185,7 +186,7 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         const float4 a0 = st.at(SP_X1, pid), a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
         const f3 x1 = xyz(a0), hitNormal = xyz(a1), o = xyz(a2);
         const uint32_t mID = __float_as_uint(a0.w);
-        uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
+        uint2 seed = st.seed[pid];
         const MatOpt mat = load_matopt(S, mID, nullptr);
         float4 b0 = st.at(SP_DI_X2, pid);
         const float4 b2 = st.at(SP_DI_L2, pid);
@@ -245,8 +246,7 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, hitNormal, seed);
         const f3 s2 = SampleBRDF(strategy, mat, outgoing, hitNormal, seed);
         emit = true; ro = x1; rd = s2;
-        st.at(SP_N1, pid) = f4u(hitNormal, seed.x);
-        st.at(SP_O, pid) = f4u(o, seed.y);
+        st.seed[pid] = seed;            // (SP_N1 / SP_O keep what k_shade_primary wrote)
         // the path state of SamplePathSimple's start (origin = x1, normal, outgoing = normalize(o), acc_f = 1, empty GI reservoir) is not
         // stored: k_gi_step<ITER0> derives it from SP_X1 / SP_N1 / SP_O and constants
     }
@@ -321,11 +321,13 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         }
         if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #define GI_STATE(K, PLANE) (!STAGE ? st.at(PLANE, pid) : s_stage[(K) * RTX_GI_BLOCK + threadIdx.x])
-        float4 a1 = GI_STATE(0, SP_N1), a2 = GI_STATE(1, SP_O);
+        const float4 zero4 = make_float4(0, 0, 0, 0);
+        // SP_N1 / SP_O (the primary hit's normal and outgoing direction) are only read by iteration 0
+        const float4 a1 = ITER0 ? st.at(SP_N1, pid) : zero4, a2 = ITER0 ? st.at(SP_O, pid) : zero4;
         // iteration 0 starts from the state SamplePathSimple begins with (Path_Sampler_v7.hlsl:9-23): the path vertex is the primary hit
         // (SP_X1 / SP_N1 / SP_O), acc_f = acc_f_reconnection = 1, an empty GI reservoir, acc_pdf = 1 — k_di_finish does not write those
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
-        const float4 one3 = make_float4(1, 1, 1, 0), zero4 = make_float4(0, 0, 0, 0);
+        const float4 one3 = make_float4(1, 1, 1, 0);
         const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(2, SP_ORIGIN);
         f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(GI_STATE(3, SP_NORMAL));
         f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(GI_STATE(4, SP_OUTGOING));
@@ -337,7 +339,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         f3 x1s = xyz(ITER0 ? zero4 : GI_STATE(11, SP_SH1)), x2s = xyz(sh2);
 #undef GI_STATE
         float gi_has = sh2.w;                                       // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
-        uint2 seed = make_uint2(__float_as_uint(a1.w), __float_as_uint(a2.w));
+        uint2 seed = st.seed[pid];
         MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
         const float fnee = (float)S.nee_samples;
         bool cont = false;
@@ -452,8 +454,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
         st.at(SP_SH1, pid) = f4(x1s, 0.0f);
         st.at(SP_SH2, pid) = f4(x2s, gi_has);
-        st.at(SP_N1, pid) = make_float4(a1.x, a1.y, a1.z, __uint_as_float(seed.x));
-        st.at(SP_O, pid) = make_float4(a2.x, a2.y, a2.z, __uint_as_float(seed.y));
+        st.seed[pid] = seed;
     }
     push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
     push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
@@ -535,7 +536,7 @@ __global__ void k_debug_pixel(StateView st, uint32_t p, const float* vis_di, con
     put3(27, c0); out[30] = c0.w; put3(31, c1); out[34] = c2.w; put3(35, c2);
     out[38] = st.at(SP_SH1, p).w;
     put3(39, st.at(SP_RESULT, p));
-    out[42] = a1.w; out[43] = a2.w;
+    out[42] = __uint_as_float(st.seed[p].x); out[43] = __uint_as_float(st.seed[p].y);
     out[49] = st.at(SP_RESULT, p).w; out[50] = vis_di[p]; out[51] = vis_gi[p]; out[52] = b1.w;
 }
 
@@ -608,6 +609,7 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     B->n_paths = n;
     memset(B->q, 0, sizeof B->q); memset(B->sq, 0, sizeof B->sq);
     CKE(cudaMalloc((void**)&B->state, (size_t)NSTATE * n * 16));
+    CKE(cudaMalloc((void**)&B->seeds, (size_t)n * 8));
     for (int i = 0; i < 2; i++) { CKE(alloc_queue(&B->q[i], n)); CKE(alloc_queue(&B->sq[i], n)); }
     CKE(cudaMalloc((void**)&B->hit_a, (size_t)n * 16));
     CKE(cudaMalloc((void**)&B->hit_inst, (size_t)n * 4));
@@ -639,7 +641,7 @@ void wave_free(WaveBuffers* B) {
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
     if (B->graph_exec) cudaGraphExecDestroy(B->graph_exec);
-    void* ptrs[] = {B->first_sample, B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
+    void* ptrs[] = {B->seeds, B->first_sample, B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
     for (void* p : ptrs) if (p) cudaFree(p);
     *B = WaveBuffers();
 }
@@ -665,7 +667,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
                                   PassTiming* T, bool accumulate) {
     const uint32_t npx = S.width * S.height;
     const uint32_t n = npx * spp;
-    StateView st{B.state, n};
+    StateView st{B.state, n, B.seeds};
     uint64_t L = 0;
     T->n_marks = 0;
     const int parts = pass_parts(B, S, T, n, accumulate);
@@ -865,7 +867,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
 }
 
 cudaError_t wave_accumulate(WaveBuffers& B, uint32_t npx, uint32_t spp, cudaStream_t stream) {
-    StateView st{B.state, npx * spp};
+    StateView st{B.state, npx * spp, B.seeds};
     k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
     return cudaGetLastError();
 }
@@ -901,7 +903,7 @@ cudaError_t wave_selftest_dmath(cudaStream_t stream, unsigned long long* host_ou
 }
 
 cudaError_t wave_debug_pixel(WaveBuffers& B, const SceneData& S, uint32_t x, uint32_t y, cudaStream_t stream, float* host_out64) {
-    StateView st{B.state, B.n_paths};
+    StateView st{B.state, B.n_paths, B.seeds};
     k_debug_pixel<<<1, 32, 0, stream>>>(st, y * S.width + x, B.vis_di, B.vis_gi, B.debug);
     CKE(cudaMemcpyAsync(host_out64, B.debug, 64 * 4, cudaMemcpyDeviceToHost, stream));
     return cudaStreamSynchronize(stream);

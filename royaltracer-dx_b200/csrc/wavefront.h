@@ -9,8 +9,8 @@ namespace rtx {
 // Structure-of-arrays path state: NSTATE float4 planes of n_paths entries each (DESIGN.md §"Data layout in HBM").
 enum StatePlane {
     SP_X1 = 0,      // x1.xyz (payload.hitPosition), bits(mID)
-    SP_N1,          // payload.hitNormal.xyz, bits(seed.x)
-    SP_O,           // o = -direction, bits(seed.y)
+    SP_N1,          // payload.hitNormal.xyz, -  (legacy estimator: bits(seed.x))
+    SP_O,           // o = -direction, -  (legacy estimator: bits(seed.y))
     SP_DI_X2,       // reservoir.x2, w_sum
     SP_DI_N2,       // reservoir.n2, f_g
     SP_DI_L2,       // reservoir.L2 (binary16 values), -
@@ -49,6 +49,7 @@ struct WaveBuffers {
     int parts = 2;                     // path ranges of a pass that run concurrently on separate streams (wave_render_pass)
     cudaStream_t aux[WAVE_MAX_PARTS - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[WAVE_MAX_PARTS - 1] = {};
     float4* state = nullptr;           // NSTATE * n_paths
+    uint2* seeds = nullptr;            // n_paths: RNG state (StateView::seed)
     RayQueue q[2];                     // closest-hit ray queues (ping-pong)
     RayQueue sq[2];                    // shadow queues: [0] DI visibility, [1] GI reservoir winner
     float4* hit_a = nullptr; uint32_t* hit_inst = nullptr;    // hit records of the queue just traced
