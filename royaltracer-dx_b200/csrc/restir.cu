@@ -157,7 +157,7 @@ k_restir_store(StateView st, RsView R) {
         di.x = xyz(b0); di.w_sum = b0.w; di.n = xyz(st.at(SP_DI_N2, p)); di.W = st.at(SP_DI_R, p).w; di.L = xyz(b2); di.M = 1u;
         // reservoir_GI.xn / nn are written by UpdateReservoir_GI only (Path_Sampler_v7.hlsl:175-183,251-259: xn, normalize(nn))
         gi.w_sum = c0.w; gi.W = c2.w; gi.L = xyz(c2); gi.M = 1u;
-        if (st.at(SP_SH2, p).w != 0.0f) { gi.x = xyz(c0); gi.n = normalize3(xyz(st.at(SP_GI_NN, p))); }
+        if (st.at(SP_GI_SC, p).z != 0.0f) { gi.x = xyz(c0); gi.n = normalize3(xyz(st.at(SP_GI_NN, p))); }
     }
     store_res(R.di_cur, R.n, p, di); store_res(R.gi_cur, R.n, p, gi); store_sd(R.sd_cur, R.n, p, sd);
 }

@@ -39,7 +39,8 @@ namespace fast {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
-#define GI_STAGED 12        // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 12 x 16 B x RTX_GI_BLOCK per CTA
+#define GI_STAGED 6         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 6 x 16 B x RTX_GI_BLOCK per CTA
+                            // (12 planes = 72 KB per CTA when the measurement below was made)
 #ifndef RTX_GI_STAGE
 #define RTX_GI_STAGE 0      // 1: stage them (cp.async into per-thread shared-memory slots).  Bit-identical either way.  Measured on B200
 #endif                      // (profiles/r02_gi_step_staging.txt): k_gi_step 3.81 -> 4.11 ms per C2 pass (the 144 KB of shared memory per SM are
@@ -294,15 +295,15 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
         pid = qin.pid[j];
-        // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the twelve 16-byte planes of this path are requested with
+        // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the six 16-byte planes a bounce reads are requested with
         // cp.async straight into this thread's shared-memory slots — no registers are held while they are in flight (at 80 registers the
-        // compiler could keep two or three of the twelve float4 loads outstanding and serialised the rest next to their uses) — and they
+        // compiler could keep two or three of the float4 loads outstanding and serialised the rest next to their uses) — and they
         // land while the hit's attributes (instance -> model -> indices -> vertices -> material) are fetched, a chain of four dependent
         // loads that does not need the state.  Each thread reads back only its own slots, so no CTA barrier is needed.
         extern __shared__ float4 s_stage[];
         constexpr bool STAGE = RTX_GI_STAGE && !ITER0;
         if (STAGE) {
-            const int planes[GI_STAGED] = {SP_N1, SP_O, SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_F, SP_ACC_FR, SP_GI_XN, SP_GI_NN, SP_GI_E3, SP_SH2, SP_SH1};
+            const int planes[GI_STAGED] = {SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_F, SP_ACC_FR, SP_GI_SC};
 #pragma unroll
             for (int k = 0; k < GI_STAGED; k++) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_stage[k * RTX_GI_BLOCK + threadIdx.x]);
@@ -328,17 +329,21 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         // (SP_X1 / SP_N1 / SP_O), acc_f = acc_f_reconnection = 1, an empty GI reservoir, acc_pdf = 1 — k_di_finish does not write those
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
         const float4 one3 = make_float4(1, 1, 1, 0);
-        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(2, SP_ORIGIN);
-        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(GI_STATE(3, SP_NORMAL));
-        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(GI_STATE(4, SP_OUTGOING));
-        f3 acc_f = xyz(ITER0 ? one3 : GI_STATE(5, SP_ACC_F)), acc_fr = xyz(ITER0 ? one3 : GI_STATE(6, SP_ACC_FR));
-        float4 c0 = ITER0 ? zero4 : GI_STATE(7, SP_GI_XN), c1 = ITER0 ? make_float4(0, 0, 0, 1.0f) : GI_STATE(8, SP_GI_NN);
-        f3 xn = xyz(c0), nn = xyz(c1), E3 = xyz(ITER0 ? zero4 : GI_STATE(9, SP_GI_E3));
-        float w_sum = c0.w, acc_pdf = c1.w;
-        const float4 sh2 = ITER0 ? zero4 : GI_STATE(10, SP_SH2);
-        f3 x1s = xyz(ITER0 ? zero4 : GI_STATE(11, SP_SH1)), x2s = xyz(sh2);
+        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);
+        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(GI_STATE(1, SP_NORMAL));
+        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(GI_STATE(2, SP_OUTGOING));
+        f3 acc_f = xyz(ITER0 ? one3 : GI_STATE(3, SP_ACC_F)), acc_fr = xyz(ITER0 ? one3 : GI_STATE(4, SP_ACC_FR));
+        // The GI reservoir of the path.  Per bounce only its scalars change (w_sum, acc_pdf, "a sample was accepted"): they live in their
+        // own plane SP_GI_SC; xn / nn are written once by iteration 0; E3 and the winner's shadow end points are only ever REPLACED, so
+        // later iterations neither load them (the end points: only where the path ends) nor store them unless this bounce replaced them.
+        // (Before: ten planes read and ten written per path and bounce; now six and three to six + what changed.)
+        const float4 sc = ITER0 ? make_float4(0, 1.0f, 0, 0) : GI_STATE(5, SP_GI_SC);
+        f3 xn = mk3(0, 0, 0), nn = mk3(0, 0, 0), E3 = mk3(0, 0, 0);
+        float w_sum = sc.x, acc_pdf = sc.y;
+        f3 x1s = mk3(0, 0, 0), x2s = mk3(0, 0, 0);
+        bool e3_set = false, sh_set = false;
 #undef GI_STATE
-        float gi_has = sh2.w;                                       // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
+        float gi_has = sc.z;                                        // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
         uint2 seed = st.seed[pid];
         MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
         const float fnee = (float)S.nee_samples;
@@ -397,7 +402,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                     float wi = length3(E_path);
                     if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
                     w_sum += wi;
-                    if (RandomFloat(seed) < wi / w_sum) { E3 = q16v(E_reconnection); gi_has = 1.0f; }   // UpdateReservoir_GI; (xn, nn) are the path's
+                    if (RandomFloat(seed) < wi / w_sum) { E3 = q16v(E_reconnection); gi_has = 1.0f; e3_set = true; }   // UpdateReservoir_GI; (xn, nn) are the path's
                 } else if (!emitter) {
                     origin = sp.hitPosition; material = hm; outgoing = -sample; normal = sp.hitNormal;
                     cont = true;
@@ -427,9 +432,9 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 if (isnan1(wi) || isinf1(wi)) wi = 0.0f;
                 w_sum += wi;
                 if (RandomFloat(seed) < wi / w_sum) {
-                    E3 = q16v(E_reconnection); gi_has = 1.0f;
+                    E3 = q16v(E_reconnection); gi_has = 1.0f; e3_set = true;
                     x1s = origin + RTX_S_BIAS * Nn;
-                    x2s = x2;
+                    x2s = x2; sh_set = true;
                 }
             }
             strategy = SelectWithPs(ps_sel, material, seed);
@@ -437,6 +442,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             emit = true; ro = origin; rd = s2;
         } else {
             // the path's sampling is over: one shadow ray for the reservoir winner (Path_Sampler_v7.hlsl:271-283)
+            if (!ITER0) { x1s = xyz(st.at(SP_SH1, pid)); x2s = xyz(st.at(SP_SH2, pid)); }     // the winner's end points, set by an earlier bounce
             const f3 ds = x2s - x1s;
             const float len = length3(ds);
             if (S.nee_samples > 0u && len > RTX_EPS) {
@@ -444,16 +450,20 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 stmax = fmaxf(RTX_S_BIAS, len - (RTX_S_BIAS * 5.0f));
             }
         }
-        st.at(SP_ORIGIN, pid) = f4u(origin, material.mID);
-        st.at(SP_NORMAL, pid) = f4(normal, 0.0f);
-        st.at(SP_OUTGOING, pid) = f4(outgoing, 0.0f);
-        st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
-        st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
-        st.at(SP_GI_XN, pid) = f4(xn, w_sum);
-        st.at(SP_GI_NN, pid) = f4(nn, acc_pdf);
-        st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
-        st.at(SP_SH1, pid) = f4(x1s, 0.0f);
-        st.at(SP_SH2, pid) = f4(x2s, gi_has);
+        if (ITER0 || emit) {                                        // the path vertex: read again only if another bounce follows
+            st.at(SP_ORIGIN, pid) = f4u(origin, material.mID);
+            st.at(SP_NORMAL, pid) = f4(normal, 0.0f);
+            st.at(SP_OUTGOING, pid) = f4(outgoing, 0.0f);
+            st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
+            st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
+        }
+        st.at(SP_GI_SC, pid) = make_float4(w_sum, acc_pdf, gi_has, 0.0f);
+        if (ITER0) {                                                // written once (Path_Sampler_v7.hlsl:104-106)
+            st.at(SP_GI_XN, pid) = f4(xn, 0.0f);
+            st.at(SP_GI_NN, pid) = f4(nn, 0.0f);
+        }
+        if (ITER0 || e3_set) st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
+        if (ITER0 || sh_set) { st.at(SP_SH1, pid) = f4(x1s, 0.0f); st.at(SP_SH2, pid) = f4(x2s, 0.0f); }
         st.seed[pid] = seed;
     }
     push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
@@ -480,7 +490,7 @@ k_finalize(StateView st, uint32_t p0, uint32_t np, SceneData S, const float* __r
     const float W = (p_hat > RTX_EPS) ? w_sum / p_hat : 0.0f;
     const f3 Cdi = rdi * W;
     const float4 c0 = st.at(SP_GI_XN, p);
-    const float w_sum_gi = c0.w * vis_gi[p];
+    const float w_sum_gi = st.at(SP_GI_SC, p).x * vis_gi[p];
     const f3 f_gi = ReconnectGI(S, x1, n1, xyz(c0), xyz(st.at(SP_GI_E3, p)), o, mat);
     const float p_hat_gi = length3(f_gi);
     const float W_GI = (p_hat_gi > RTX_EPS) ? w_sum_gi / p_hat_gi : 0.0f;

@@ -15,8 +15,8 @@ enum StatePlane {
     SP_DI_N2,       // reservoir.n2, f_g
     SP_DI_L2,       // reservoir.L2 (binary16 values), -
     SP_DI_R,        // ReconnectDI(x1,n1,x2,n2,L2,o) vector, -
-    SP_GI_XN,       // reservoir_GI.xn, w_sum
-    SP_GI_NN,       // reservoir_GI.nn, acc_pdf
+    SP_GI_XN,       // reservoir_GI.xn, - (k_finalize: w_sum after the visibility test)
+    SP_GI_NN,       // reservoir_GI.nn, -
     SP_GI_E3,       // reservoir_GI.E3 (binary16 values), -
     SP_ORIGIN,      // path origin, bits(current material id)
     SP_NORMAL,      // path normal
@@ -24,8 +24,9 @@ enum StatePlane {
     SP_ACC_F,       // acc_f
     SP_ACC_FR,      // acc_f_reconnection
     SP_SH1,         // x1_shadow, flag (1 = a reservoir winner exists)
-    SP_SH2,         // x2_shadow
+    SP_SH2,         // x2_shadow, -
     SP_RESULT,      // per-sample radiance C, flag (1 = sampling path: finalize computes C)
+    SP_GI_SC,       // scalars of the GI reservoir, updated every bounce: w_sum, acc_pdf, 1 = a sample was accepted, -
     NSTATE
 };
 
