@@ -39,7 +39,7 @@ namespace fast {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
-#define GI_STAGED 6         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 6 x 16 B x RTX_GI_BLOCK per CTA
+#define GI_STAGED 5         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 5 x 16 B x RTX_GI_BLOCK per CTA
                             // (12 planes = 72 KB per CTA when the measurement below was made)
 #ifndef RTX_GI_STAGE
 #define RTX_GI_STAGE 0      // 1: stage them (cp.async into per-thread shared-memory slots).  Bit-identical either way.  Measured on B200
@@ -303,7 +303,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         extern __shared__ float4 s_stage[];
         constexpr bool STAGE = RTX_GI_STAGE && !ITER0;
         if (STAGE) {
-            const int planes[GI_STAGED] = {SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_F, SP_ACC_FR, SP_GI_SC};
+            const int planes[GI_STAGED] = {SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_FR, SP_GI_SC};
 #pragma unroll
             for (int k = 0; k < GI_STAGED; k++) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_stage[k * RTX_GI_BLOCK + threadIdx.x]);
@@ -330,14 +330,16 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
         const float4 one3 = make_float4(1, 1, 1, 0);
         const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);
-        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(GI_STATE(1, SP_NORMAL));
-        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(GI_STATE(2, SP_OUTGOING));
-        f3 acc_f = xyz(ITER0 ? one3 : GI_STATE(3, SP_ACC_F)), acc_fr = xyz(ITER0 ? one3 : GI_STATE(4, SP_ACC_FR));
+        // acc_f rides in the .w of the normal / outgoing / acc_f_reconnection planes (four planes per path vertex instead of five)
+        const float4 pn = ITER0 ? one3 : GI_STATE(1, SP_NORMAL), po = ITER0 ? one3 : GI_STATE(2, SP_OUTGOING), pf = ITER0 ? one3 : GI_STATE(3, SP_ACC_FR);
+        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(pn);
+        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(po);
+        f3 acc_f = ITER0 ? mk3(1, 1, 1) : mk3(pn.w, po.w, pf.w), acc_fr = xyz(pf);
         // The GI reservoir of the path.  Per bounce only its scalars change (w_sum, acc_pdf, "a sample was accepted"): they live in their
         // own plane SP_GI_SC; xn / nn are written once by iteration 0; E3 and the winner's shadow end points are only ever REPLACED, so
         // later iterations neither load them (the end points: only where the path ends) nor store them unless this bounce replaced them.
         // (Before: ten planes read and ten written per path and bounce; now six and three to six + what changed.)
-        const float4 sc = ITER0 ? make_float4(0, 1.0f, 0, 0) : GI_STATE(5, SP_GI_SC);
+        const float4 sc = ITER0 ? make_float4(0, 1.0f, 0, 0) : GI_STATE(4, SP_GI_SC);
         f3 xn = mk3(0, 0, 0), nn = mk3(0, 0, 0), E3 = mk3(0, 0, 0);
         float w_sum = sc.x, acc_pdf = sc.y;
         f3 x1s = mk3(0, 0, 0), x2s = mk3(0, 0, 0);
@@ -452,10 +454,9 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         }
         if (ITER0 || emit) {                                        // the path vertex: read again only if another bounce follows
             st.at(SP_ORIGIN, pid) = f4u(origin, material.mID);
-            st.at(SP_NORMAL, pid) = f4(normal, 0.0f);
-            st.at(SP_OUTGOING, pid) = f4(outgoing, 0.0f);
-            st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
-            st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
+            st.at(SP_NORMAL, pid) = f4(normal, acc_f.x);
+            st.at(SP_OUTGOING, pid) = f4(outgoing, acc_f.y);
+            st.at(SP_ACC_FR, pid) = f4(acc_fr, acc_f.z);
         }
         st.at(SP_GI_SC, pid) = make_float4(w_sum, acc_pdf, gi_has, 0.0f);
         if (ITER0) {                                                // written once (Path_Sampler_v7.hlsl:104-106)
