@@ -20,7 +20,7 @@ void set_error(const std::string& s) { g_err = s; }
 using namespace rtx;
 
 struct ModelRec {
-    uint8_t* d_verts = nullptr; uint32_t* d_idx = nullptr;
+    uint8_t* d_verts = nullptr; uint32_t* d_idx = nullptr; float4* d_shade = nullptr;
     uint32_t n_verts = 0, n_tris = 0, mat_offset = 0;
     Bvh8 bvh;
 };
@@ -127,7 +127,7 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     rtx_comm_destroy(c);
-    for (auto& m : c->models) { if (m.d_verts) cudaFree(m.d_verts); if (m.d_idx) cudaFree(m.d_idx); free_bvh(&m.bvh); }
+    for (auto& m : c->models) { if (m.d_verts) cudaFree(m.d_verts); if (m.d_idx) cudaFree(m.d_idx); if (m.d_shade) cudaFree(m.d_shade); free_bvh(&m.bvh); }
     void* ptrs[] = {c->d_material_ids, c->d_materials, c->d_descs, c->d_props, c->d_inst_model, c->d_inst_recs, c->d_lights,
                     c->d_trace_o, c->d_trace_d, c->d_trace_ha, c->d_trace_hi, c->d_trace_out, c->d_stats, c->d_overflow, c->d_trace_rays,
                     c->d_trace_hits};
@@ -161,6 +161,21 @@ static rtx_status upload(T** dptr, const T* host, size_t n, cudaStream_t s, size
     return RTX_OK;
 }
 
+// closest-hit attribute records (shade.cuh ModelRef::shade): positions and normals of a triangle's three vertices in one 80-byte record
+__global__ void k_shade_records(const uint8_t* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t n_tris, float4* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    const float* a = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t] * 28);
+    const float* b = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t + 1] * 28);
+    const float* d = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t + 2] * 28);
+    float4* o = out + (size_t)t * 5;
+    o[0] = make_float4(a[0], a[1], a[2], a[3]);
+    o[1] = make_float4(b[0], b[1], b[2], a[4]);
+    o[2] = make_float4(d[0], d[1], d[2], a[5]);
+    o[3] = make_float4(b[3], b[4], b[5], 0.0f);
+    o[4] = make_float4(d[3], d[4], d[5], 0.0f);
+}
+
 extern "C" rtx_status rtx_upload_model(rtx_ctx* c, const rtx_vertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni,
                                        uint32_t material_id_offset, uint32_t* model_id_out) {
     if (!c || (!v && nv) || (!idx && ni)) return fail(RTX_ERR_ARG, "rtx_upload_model: null argument");
@@ -173,7 +188,10 @@ extern "C" rtx_status rtx_upload_model(rtx_ctx* c, const rtx_vertex* v, uint32_t
     if ((st = upload((rtx_vertex**)&m.d_verts, v, nv, c->stream)) != RTX_OK) return st;
     if ((st = upload(&m.d_idx, idx, ni, c->stream)) != RTX_OK) return st;
     RTX_CK(build_blas(m.d_verts, nv, m.d_idx, m.n_tris, &m.bvh, c->stream));
-    c->launches += 8;
+    RTX_CK(cudaMalloc((void**)&m.d_shade, (size_t)(m.n_tris ? m.n_tris : 1) * 80));
+    if (m.n_tris) k_shade_records<<<(m.n_tris + 255) / 256, 256, 0, c->stream>>>(m.d_verts, m.d_idx, m.n_tris, m.d_shade);
+    RTX_CK(cudaGetLastError());
+    c->launches += 9;
     c->models.push_back(m);
     // the per-model tables are rebuilt by the next rtx_set_instances; until then there is no valid TLAS (rendering or tracing in
     // between returns RTX_ERR_STATE instead of handing freed tables to the kernels)
@@ -217,7 +235,7 @@ static rtx_status ensure_tables(rtx_ctx* c) {
         for (int k = 0; k < 3; k++) { bb[i].lo[k] = br[i].lo[k] = m.bvh.lo[k]; bb[i].hi[k] = br[i].hi[k] = m.bvh.hi[k]; }
         br[i].pad_[0] = br[i].pad_[1] = 0.0f;
         bb[i].verts = m.d_verts; bb[i].n_verts = m.n_verts;
-        mr[i].verts = m.d_verts; mr[i].idx = m.d_idx; mr[i].mat_offset = m.mat_offset; mr[i].n_tris = m.n_tris;
+        mr[i].verts = m.d_verts; mr[i].idx = m.d_idx; mr[i].mat_offset = m.mat_offset; mr[i].n_tris = m.n_tris; mr[i].shade = m.d_shade;
     }
     rtx_status st;
     if ((st = upload(&c->d_blas, br.data(), n, c->stream)) != RTX_OK) return st;
