@@ -308,6 +308,16 @@ class Dist:
         return a.tolist(), b.tolist()
 
 
+def warm_build_ms(rtdx, D, sc):
+    """BLAS build times of a SECOND upload of the scene's models (a fresh context): the first build of a process also pays for the lazy
+    loading of the builder's kernels and cub's first-use set-up (10 K triangles and 50 M read alike then), which is not the build."""
+    ctx = rtdx.Context(64, 64, device=D.local, stream=D.stream.cuda_stream)
+    ids = [ctx.upload_model(m["vertices"], m["indices"], m["material_id_offset"]) for m in sc.models]
+    out = [ctx.blas_info(i)["build_ms"] for i in ids]
+    ctx.close()
+    return out
+
+
 def make_context(rtdx, D, cfg, sc):
     ctx = rtdx.Context(cfg["W"], cfg["H"], bounces=cfg["bounces"], flags=cfg["flags"], samples_per_pass=cfg["spp"], device=D.local,
                        stream=D.stream.cuda_stream)
@@ -425,6 +435,9 @@ def run_render(rtdx, D, cfg, args, steps, warmup, full):
     W, H, spp = cfg["W"], cfg["H"], cfg["spp"]
     ctx, up = make_context(rtdx, D, cfg, sc)
     blas = [ctx.blas_info(i) for i in up["model_ids"]]
+    if full:
+        for b, w in zip(blas, warm_build_ms(rtdx, D, sc)):
+            b["build_ms_warm"] = w
     stats = traversal_stats(rtdx, ctx, cfg, rank)
 
     def step_resident(k):
@@ -528,6 +541,8 @@ def run_trace(rtdx, D, cfg, args, steps, warmup):
     ctx = rtdx.Context(64, 64, device=D.local, stream=D.stream.cuda_stream)
     up = ctx.upload_scene(sc)
     blas = [ctx.blas_info(i) for i in up["model_ids"]]
+    for b, w in zip(blas, warm_build_ms(rtdx, D, sc)):
+        b["build_ms_warm"] = w
     cam = rtdx.camera_params(sc.eye, sc.center, sc.up, 1.0)
     prim = rtdx.scenes.camera_rays(cam, cfg["W"], cfg["H"])
     rays = torch.from_numpy(prim.view(np.float32).reshape(-1, 8)).cuda()
