@@ -305,6 +305,24 @@ def test_legacy_rr_estimator_bit_exact(rtdx, orc, scene_name):
     ctx.close()
 
 
+def test_engine_side_reduce_single_rank(rtdx):
+    """rtx_comm_init / rtx_reduce_accum / rtx_read_reduced_accum with a communicator of one rank (NCCL bound at run time): the reduced
+    buffer equals the context's own accumulation after every pass, rtx_read_output resolves it, and rendering continues to accumulate
+    (the next pass's accumulation waits for the reduce, not the other way round).  Two ranks: tests/test_gpu_host.py, bench.py --gpus N."""
+    sc = rtdx.scenes.cornell()
+    W, H = 64, 48
+    ctx, up = _upload(rtdx, sc, W, H, bounces=2)
+    ref, _ = _upload(rtdx, sc, W, H, bounces=2)
+    ctx.comm_init(ctx.comm_unique_id(), 0, 1)
+    for k in range(3):
+        ctx.render_pass(k, 1); ctx.reduce_accum()
+        ref.render_pass(k, 1); ref.synchronize()
+        total = ctx.read_reduced_accum()
+        assert np.array_equal(bits(total), bits(ref.read_accum())), k
+        assert np.array_equal(ctx.read_output(), ref.read_output())
+    ctx.close(); ref.close()
+
+
 def test_builder_quality_and_shape(rtdx):
     """The GPU builder (Morton -> PLOC with the SAH programme -> 8-wide collapse) beyond "the hits are right": node fan-out, leaf size,
     SAH cost and the per-ray work it leads to stay inside bounds a regression in any stage would break; a TLAS holds ONE instance per leaf
