@@ -540,6 +540,41 @@ def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
     ctx.close()
 
 
+def test_graph_replay_and_trace_order_do_not_change_the_image(rtdx, orc):
+    """RTX_OPT_PASS_GRAPH / RTX_OPT_QUEUE_LPT: the third and later passes of a static configuration replay a captured CUDA graph (the
+    sample index comes from a device word), and the traversal kernels claim rays longest-first through the queue's order array.  Six
+    accumulated samples are bit-identical with both on (default), graph off, order off — and equal to the oracle's six samples; the
+    kernel-launch count is the same whether a pass was launched directly or replayed."""
+    sc = rtdx.scenes.mesh_room(n=16)
+    W, H, bounces, n_samples = 384, 192, 3, 6
+    ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
+    osc = orc.OracleScene(sc, up["props"], up["lights"])
+    ref = None
+    for s in range(n_samples):
+        img, _ = osc.render(up["camera"], W, H, s, 1, bounces=bounces, flags=0)
+        ref = img if ref is None else ref + img               # gPermanentData += sample, in sample order (F20)
+    results = {}
+    for name, opts in (("default", {}), ("no graph", {rtdx.OPT_PASS_GRAPH: 0}), ("emission order", {rtdx.OPT_QUEUE_LPT: 0})):
+        ctx.set_option(rtdx.OPT_PASS_GRAPH, 1); ctx.set_option(rtdx.OPT_QUEUE_LPT, 1)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.reset_accum(); ctx.reset_counters()
+        per_pass = []
+        for s in range(n_samples):
+            before = ctx.counters()["kernel_launches"]
+            ctx.render_pass(s, 1)
+            per_pass.append(ctx.counters()["kernel_launches"] - before)
+        ctx.synchronize()
+        results[name] = (ctx.read_accum(), ctx.counters(), per_pass)
+        assert len(set(per_pass)) == 1 and per_pass[0] > 20, (name, per_pass)
+    base = results["default"]
+    assert (bits(base[0]) != bits(ref)).sum() == 0
+    for name, (img, cnt, per_pass) in results.items():
+        assert np.array_equal(bits(img), bits(base[0])), name
+        assert cnt["closest_rays"] == base[1]["closest_rays"] and cnt["shadow_rays"] == base[1]["shadow_rays"], name
+    ctx.close()
+
+
 def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
     (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""
