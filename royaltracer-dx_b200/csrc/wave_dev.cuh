@@ -54,33 +54,74 @@ __device__ __forceinline__ bool ray_is_heavy(const SceneData& S, f3 o, float tmi
     return !(tn > tf);            // NaN (a direction component of 0 inside the slab) counts as heavy
 }
 
-// Records `slot` in the queue's trace order: heavy rays from entry 0 upwards, the others from entry cap-1 downwards (one atomic per warp
-// and class).  mask = ballot(emit); must be reached by all 32 lanes.
+// Trace order of a queue (wavefront.h RayQueue): heavy rays are recorded from entry 0 upwards, the others from entry cap-1 downwards.
+// A warp claims its queue slots and its order entries with ONE round of atomics: lane k performs the k-th of {count, n_heavy, n_light}
+// of the first queue and, in push_ray_pair, of the second (six dependent round trips to the L2 per warp before; ncu showed 7 % of
+// k_gi_step's stall samples on them at 3 of 32 lanes).  Both must be reached by all 32 lanes.
+__device__ __forceinline__ void store_ray(const RayQueue& q, unsigned slot, f3 o, float tmin, f3 d, float tmax, uint32_t pid) {
+    q.o_tmin[slot] = f4(o, tmin);
+    q.d_tmax[slot] = f4(d, tmax);
+    q.pid[slot] = pid;
+}
+
+// order entries only, for rays whose slots are already fixed (k_generate: slot = index within the part)
 __device__ __forceinline__ void record_order(const RayQueue& q, unsigned mask, bool emit, bool heavy, unsigned slot) {
-    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    const unsigned mh = __ballot_sync(0xffffffffu, emit && heavy), ml = mask & ~mh;
-    unsigned bh = 0, bl = 0;
-    if (mh) { const int l = __ffs(mh) - 1; if ((int)lane == l) bh = atomicAdd(q.n_heavy, (unsigned)__popc(mh)); bh = __shfl_sync(0xffffffffu, bh, l); }
-    if (ml) { const int l = __ffs(ml) - 1; if ((int)lane == l) bl = atomicAdd(q.n_light, (unsigned)__popc(ml)); bl = __shfl_sync(0xffffffffu, bl, l); }
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const unsigned mh = __ballot_sync(full, emit && heavy), ml = mask & ~mh;
+    const unsigned v = lane == 0u ? __popc(mh) : (lane == 1u ? __popc(ml) : 0u);
+    unsigned r = 0;
+    if (v) r = atomicAdd(lane == 0u ? q.n_heavy : q.n_light, v);
+    const unsigned bh = __shfl_sync(full, r, 0), bl = __shfl_sync(full, r, 1);
     if (emit) q.order[heavy ? bh + __popc(mh & below) : q.cap - 1u - (bl + __popc(ml & below))] = slot;
 }
 
-// push_ray that also records the ray's slot in the queue's trace order (wavefront.h RayQueue).  Must be reached by all 32 lanes.
 __device__ __forceinline__ void push_ray2(const RayQueue& q, bool emit, bool heavy, f3 o, float tmin, f3 d, float tmax, uint32_t pid) {
-    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const unsigned mask = __ballot_sync(full, emit);
     if (mask == 0u) return;
-    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if ((int)lane == leader) base = atomicAdd(q.count, (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    const unsigned slot = base + __popc(mask & below);
+    const bool ord = q.order != nullptr;
+    const unsigned mh = __ballot_sync(full, emit && heavy), ml = mask & ~mh;
+    unsigned* p = lane == 0u ? q.count : (lane == 1u ? q.n_heavy : q.n_light);
+    const unsigned v = lane == 0u ? __popc(mask) : (!ord || lane > 2u ? 0u : (lane == 1u ? __popc(mh) : __popc(ml)));
+    unsigned r = 0;
+    if (v) r = atomicAdd(p, v);
+    const unsigned slot = __shfl_sync(full, r, 0) + __popc(mask & below);
+    const unsigned bh = __shfl_sync(full, r, 1), bl = __shfl_sync(full, r, 2);
     if (emit) {
-        q.o_tmin[slot] = f4(o, tmin);
-        q.d_tmax[slot] = f4(d, tmax);
-        q.pid[slot] = pid;
+        store_ray(q, slot, o, tmin, d, tmax, pid);
+        if (ord) q.order[heavy ? bh + __popc(mh & below) : q.cap - 1u - (bl + __popc(ml & below))] = slot;
     }
-    if (q.order) record_order(q, mask, emit, heavy, slot);
+}
+
+__device__ __forceinline__ void push_ray_pair(const RayQueue& qa, bool ea, bool ha, f3 oa, float tmina, f3 da, float tmaxa,
+                                              const RayQueue& qb, bool eb, bool hb, f3 ob, float tminb, f3 db, float tmaxb, uint32_t pid) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const unsigned ma = __ballot_sync(full, ea), mb = __ballot_sync(full, eb);
+    if ((ma | mb) == 0u) return;
+    const bool orda = qa.order != nullptr, ordb = qb.order != nullptr;
+    const unsigned mha = __ballot_sync(full, ea && ha), mla = ma & ~mha, mhb = __ballot_sync(full, eb && hb), mlb = mb & ~mhb;
+    unsigned* p = qa.count; unsigned v = 0;
+    switch (lane) {
+        case 0: v = __popc(ma); break;
+        case 1: p = qa.n_heavy; v = orda ? __popc(mha) : 0u; break;
+        case 2: p = qa.n_light; v = orda ? __popc(mla) : 0u; break;
+        case 3: p = qb.count; v = __popc(mb); break;
+        case 4: p = qb.n_heavy; v = ordb ? __popc(mhb) : 0u; break;
+        case 5: p = qb.n_light; v = ordb ? __popc(mlb) : 0u; break;
+        default: break;
+    }
+    unsigned r = 0;
+    if (v) r = atomicAdd(p, v);
+    const unsigned sa = __shfl_sync(full, r, 0) + __popc(ma & below), bha = __shfl_sync(full, r, 1), bla = __shfl_sync(full, r, 2);
+    const unsigned sb = __shfl_sync(full, r, 3) + __popc(mb & below), bhb = __shfl_sync(full, r, 4), blb = __shfl_sync(full, r, 5);
+    if (ea) {
+        store_ray(qa, sa, oa, tmina, da, tmaxa, pid);
+        if (orda) qa.order[ha ? bha + __popc(mha & below) : qa.cap - 1u - (bla + __popc(mla & below))] = sa;
+    }
+    if (eb) {
+        store_ray(qb, sb, ob, tminb, db, tmaxb, pid);
+        if (ordb) qb.order[hb ? bhb + __popc(mhb & below) : qb.cap - 1u - (blb + __popc(mlb & below))] = sb;
+    }
 }
 
 }  // namespace rtx

@@ -251,8 +251,8 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
         // the path state of SamplePathSimple's start (origin = x1, normal, outgoing = normalize(o), acc_f = 1, empty GI reservoir) is not
         // stored: k_gi_step<ITER0> derives it from SP_X1 / SP_N1 / SP_O and constants
     }
-    push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.0f, sd, stmax), so, 0.0f, sd, stmax, pid);
-    push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
+    push_ray_pair(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.0f, sd, stmax), so, 0.0f, sd, stmax,
+                  qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
 }
 
 // SampleLightNEE_GI with useVisibility=false, Sampler_v7.hlsl:508-647 (call site Path_Sampler_v7.hlsl:133-151)
@@ -467,8 +467,8 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         if (ITER0 || sh_set) { st.at(SP_SH1, pid) = f4(x1s, 0.0f); st.at(SP_SH2, pid) = f4(x2s, 0.0f); }
         st.seed[pid] = seed;
     }
-    push_ray2(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax, pid);
-    push_ray2(qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
+    push_ray_pair(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax,
+                  qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
 }
 
 // ---- stage: estimator E0 (Pass_init_di_v7.hlsl:166-181 + Pass_spat_di_v7.hlsl:334-372 with no accepted neighbours)
