@@ -196,6 +196,7 @@ inline bool isinf(float x) { return ::fabsf(x) == INFINITY; }
 inline bool isfinite(float x) { return !isnan(x) && !isinf(x); }
 inline float sin(float x) { float s, c; orc::d_sincos(x, &s, &c); return s; }
 inline float cos(float x) { float s, c; orc::d_sincos(x, &s, &c); return c; }
+inline float radians(float d) { return d * 0.017453292f; }
 inline float pow(float x, float y) {
     if (y == 5.0f) return x * x * x * x * x;
     if (y == 1.0f) return x;
@@ -241,6 +242,7 @@ inline float dot(const float3& a, const float3& b) { return (a.x * b.x + a.y * b
 inline float dot(const float4& a, const float4& b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + a.w * b.w; }
 inline float3 cross(const float3& a, const float3& b) { return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 template <int N> inline float length(const vec<float, N>& a) { return ::sqrtf(dot(a, a)); }
+inline float length(float x) { return ::fabsf(x); }            // HLSL length() of a scalar (include/Hit.hlsl:310)
 template <int N> inline float distance(const vec<float, N>& a, const vec<float, N>& b) { return length(a - b); }
 template <int N> inline vec<float, N> normalize(const vec<float, N>& a) { return a * rsqrt(dot(a, a)); }
 inline float3 reflect(const float3& i, const float3& n) { return i - (2.0f * dot(n, i)) * n; }
@@ -261,6 +263,13 @@ typedef float4x4 matrix;
 inline float4 mul(const float4x4& M, const float4& v) {
     const orc::f4 r = orc::mul44(M.m, v.x, v.y, v.z, v.w);
     return float4(r.x, r.y, r.z, r.w);
+}
+
+// row-vector form (a `row_major` parameter: element (r, c) of the same 64 bytes is m[4 r + c])
+inline float4 mul(const float4& v, const float4x4& M) {
+    float4 r;
+    for (int c = 0; c < 4; c++) r[c] = ((v.x * M.m[c] + v.y * M.m[4 + c]) + v.z * M.m[8 + c]) + v.w * M.m[12 + c];
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------ resources

@@ -16,7 +16,7 @@ lives in plain-function HLSL (Pathtracer/shaders/*_v7.hlsl, which #include Patht
 tests/test_ref_pins.py then drives the hand-written oracle (oracle/rtx_oracle.cpp) and this library with the same inputs.
 /root/reference does not exist on the GPU box: the library is built here and travels with the repository snapshot.
 
-usage: python oracle/ref/make_ref.py [--force] [--bounces N]
+usage: python oracle/ref/make_ref.py [--force] [--bounces N] [--legacy]
 """
 import os
 import re
@@ -43,6 +43,17 @@ UNITS = {
     "shadow": os.path.join(INCLUDE, "ShadowRay.hlsl"),          # ShadowClosestHit / ShadowMiss
 }
 
+# the reference's first estimator (RTX_FLAG_LEGACY_RR): include/RayGen.hlsl + include/Hit.hlsl + include/Miss.hlsl
+# (-> Common.hlsl, BRDF.hlsl, GGX.hlsl, Lambertian.hlsl), with the same shadow shaders; compiled into its own library because its
+# headers define the same names differently (HitInfo, Material accessors, SampleBRDF ...)
+LEGACY_UNITS = {
+    "leg_rg": os.path.join(INCLUDE, "RayGen.hlsl"),             # RayGen: path loop, Russian roulette, accumulation
+    "leg_hit": os.path.join(INCLUDE, "Hit.hlsl"),               # ClosestHit: RIS-10 NEE + shadow ray + BSDF sample + MIS on emitter hits
+    "leg_miss": os.path.join(INCLUDE, "Miss.hlsl"),             # Miss
+    "shadow": os.path.join(INCLUDE, "ShadowRay.hlsl"),
+}
+LEGACY_LIB = os.path.join(OUT, "libref_legacy.so")
+
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
 
 # (pattern, replacement, what it is)
@@ -54,13 +65,14 @@ FILTER = [
     (re.compile(r":\s*SV_RayPayload"), "", "semantic"),
     (re.compile(r"\[shader\(\"[^\"]*\"\)\]"), "", "shader stage attribute"),
     (re.compile(r"\[(?:loop|unroll|branch|flatten)\]"), "", "loop / branch hints"),
+    (re.compile(r"\brow_major\s+"), "", "matrix packing qualifier of a parameter"),
     (re.compile(r"cbuffer\s+\w+\s*\{([^{}]*)\}"), r"\1", "cbuffer members are globals"),
     (re.compile(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+(?=[A-Za-z_])"), r"\1& ", "inout / out parameters are references"),
     (re.compile(r"\bin\s+([A-Z][A-Za-z_]\w*)\s+(?=[A-Za-z_])"), r"\1 ", "in parameters are values"),
     # HLSL flattens nested initialiser lists ("Row 2: { float3(...), uint16_t(0) }" initialises the two members L2, M)
     (re.compile(r"\{\s*(float3\([^)]*\))\s*,\s*(uint16_t\(0\))\s*\}"), r"\1, \2", "flattened initialiser list"),
     # C++ has no swizzle members: .xyz / .xy become calls; the one swizzled compound assignment becomes a setter
-    (re.compile(r"([A-Za-z_][\w\[\]\(\)]*)\.xyz\s*\+=\s*([^;]+);"), r"\1.set_xyz(\1.xyz + (\2));", "swizzled compound assignment"),
+    (re.compile(r"([A-Za-z_][\w\.\[\]\(\)]*)\.xyz\s*([-+*/])=\s*([^;]+);"), r"\1.set_xyz(\1.xyz \2 (\3));", "swizzled compound assignment"),
     (re.compile(r"\.xyz\b"), ".xyz()", "swizzle"),
     (re.compile(r"\.xy\b"), ".xy()", "swizzle"),
     # unsuffixed literals are float in HLSL, double in C++
@@ -93,6 +105,38 @@ def filtered(path, bounces=None):
     return text
 
 
+def filtered_legacy(path, bounces=None):
+    text = filtered(path)
+    if bounces is not None:      # RayGen.hlsl:63 `uint bounces = 10000000;` (Russian roulette ends the paths); the engine's legacy mode has a cap
+        text = re.sub(r"(uint\s+bounces\s*=\s*)\d+", r"\g<1>%d" % bounces, text)
+    return text
+
+
+def build_legacy(force=False, bounces=None, lib=None, verbose=False):
+    lib = lib or (LEGACY_LIB if bounces is None else os.path.join(OUT, "libref_legacy_b%d.so" % bounces))
+    if not os.path.isdir(INCLUDE):
+        if os.path.exists(lib):
+            return lib
+        raise RuntimeError("reference sources not found under %s and no prebuilt %s" % (REF, lib))
+    srcs = [os.path.join(HERE, f) for f in ("ref_legacy_harness.cpp", "hlsl_shim.h", "make_ref.py")] + [os.path.join(ORACLE, "det_math.h")]
+    refs = [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f.endswith(".hlsl")]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(s) <= os.path.getmtime(lib) for s in srcs + refs):
+        return lib
+    gen = os.path.join(OUT, "gen_legacy" + ("" if bounces is None else "_b%d" % bounces))
+    os.makedirs(gen, exist_ok=True)
+    for name, path in LEGACY_UNITS.items():
+        with open(os.path.join(gen, "%s.inc" % name), "w") as f:
+            f.write("// GENERATED by oracle/ref/make_ref.py from %s — reference text, do not commit\n" % os.path.relpath(path, REF))
+            f.write(filtered_legacy(path, bounces))
+            f.write("\n")
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wno-narrowing", "-w",
+           "-I", gen, "-o", lib, os.path.join(HERE, "ref_legacy_harness.cpp")]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return lib
+
+
 def build(force=False, bounces=None, lib=LIB, verbose=False):
     if not os.path.isdir(SHADERS):
         if os.path.exists(lib):
@@ -121,5 +165,8 @@ if __name__ == "__main__":
     b = None
     if "--bounces" in sys.argv:
         b = int(sys.argv[sys.argv.index("--bounces") + 1])
+    if "--legacy" in sys.argv:
+        print(build_legacy(force="--force" in sys.argv, bounces=b, verbose=True))
+        sys.exit(0)
     lib = LIB if b is None else os.path.join(OUT, "libref_b%d.so" % b)
     print(build(force="--force" in sys.argv, bounces=b, lib=lib, verbose=True))

@@ -47,6 +47,34 @@ def lib(bounces=None):
     return _libs[bounces]
 
 
+def legacy_available(bounces=None):
+    path = make_ref.LEGACY_LIB if bounces is None else os.path.join(make_ref.OUT, "libref_legacy_b%d.so" % bounces)
+    return os.path.isdir(make_ref.INCLUDE) or os.path.exists(path)
+
+
+def legacy_lib(bounces=None):
+    """The reference's FIRST estimator (include/RayGen.hlsl + Hit.hlsl + Miss.hlsl + ShadowRay.hlsl) compiled for the CPU; `bounces`
+    replaces RayGen.hlsl:63's `uint bounces = 10000000` (the engine's and the oracle's legacy mode cap the path length)."""
+    key = ("legacy", bounces)
+    if key not in _libs:
+        L = C.CDLL(make_ref.build_legacy(bounces=bounces))
+        vp, u32 = C.c_void_p, C.c_uint32
+        L.ref_set_tracer.argtypes = [vp, vp, C.c_int]
+        L.ref_set_scene.argtypes = [u32, vp, vp, vp, vp, u32, vp, vp, vp, u32, vp, u32, vp, u32]
+        L.ref_set_camera.argtypes = [vp]
+        L.ref_set_time.argtypes = [C.c_float]
+        L.ref_alloc_frame.argtypes = [u32, u32]
+        L.ref_raygen.argtypes = [C.c_int, u32, u32]
+        L.ref_dispatch.argtypes = [C.c_int]
+        L.ref_ray_counts.argtypes = [vp, vp, C.c_int]
+        L.ref_read_permanent.argtypes = [vp]
+        L.ref_write_permanent.argtypes = [vp]
+        L.ref_read_output.argtypes = [vp]
+        L.ref_config.argtypes = [vp]
+        _libs[key] = L
+    return _libs[key]
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
@@ -55,8 +83,8 @@ class RefScene:
     """Binds a scenes.SceneDesc + the host-produced buffers (instance props, light list) to the reference shaders' resources and
     routes TraceRay to the oracle's ray caster (orc.OracleScene): the reference has no source for traversal / intersection."""
 
-    def __init__(self, scene, props, lights, oracle_scene, trace_mode=1, bounces=None):
-        self.L = L = lib(bounces)
+    def __init__(self, scene, props, lights, oracle_scene, trace_mode=1, bounces=None, legacy=False):
+        self.L = L = legacy_lib(bounces) if legacy else lib(bounces)
         self.osc = oracle_scene
         nm = len(scene.models)
         self._keep = [np.ascontiguousarray(m["vertices"]) for m in scene.models] + [np.ascontiguousarray(m["indices"]) for m in scene.models]
@@ -103,6 +131,11 @@ class RefScene:
         """Estimator E0 per pixel from the *_current buffers of pass 1 (float4: C.rgb, 1 sampled / 3 emitter)."""
         out = np.zeros((self.h, self.w, 4), dtype=np.float32)
         self.L.ref_e0(_p(out))
+        return out
+
+    def output(self):
+        out = np.zeros((self.h, self.w, 4), dtype=np.float32)
+        self.L.ref_read_output(_p(out))
         return out
 
     def permanent(self):

@@ -233,3 +233,51 @@ def test_restir_frames_moving_camera_equal_the_reference(rtdx, orc):
     cams = [None, rtdx.camera_params((sc.eye[0] + 0.05, sc.eye[1], sc.eye[2]), sc.center, sc.up, W / H),
             rtdx.camera_params((sc.eye[0] + 0.10, sc.eye[1] + 0.02, sc.eye[2]), sc.center, sc.up, W / H), None]
     _frames(rtdx, orc, sc, W, H, [(c, None) for c in cams])
+
+
+# ---- the reference's first estimator: include/RayGen.hlsl + include/Hit.hlsl + include/Miss.hlsl -----------------
+@pytest.mark.parametrize("name", sorted(SCENES))
+@pytest.mark.parametrize("bounces", [2, 12])
+def test_legacy_estimator_equals_the_reference_text(rtdx, orc, name, bounces):
+    """RayGen (include/RayGen.hlsl:48-187: jittered camera ray, path loop, Russian roulette after depth 3, accumulation) and ClosestHit
+    (include/Hit.hlsl:59-357: face-forwarded normals, RIS over 10 light candidates, the nested shadow TraceRay, BSDF sample, MIS on
+    emitter hits) run from the reference's own text, one DispatchRays per sample: gPermanentData and the closest / shadow ray counts of
+    the oracle's `legacy` estimator (what RTX_FLAG_LEGACY_RR is tested against) are bit-identical on every pixel, for one sample and
+    accumulated over three.  The only edit to the text is RayGen.hlsl:63's `uint bounces = 10000000` -> the cap under test (D13);
+    the legacy text's older Material / InstanceProperties / LightTriangle layouts are filled field by field (ref_legacy_harness.cpp)."""
+    if not ref.legacy_available(bounces):
+        pytest.skip("libref_legacy_b%d.so not built" % bounces)
+    W, H = 40, 24
+    sc = SCENES[name](rtdx)
+    props, descs, lights, cam = host_inputs(rtdx, sc, W, H)
+    osc = orc.OracleScene(sc, props, lights)
+    rs = ref.RefScene(sc, props, lights, osc, bounces=bounces, legacy=True)
+    cfg = np.zeros(4, dtype=np.uint32)
+    rs.L.ref_config(_p(cfg))
+    assert cfg[0] == 10                                                   # RIS_M (include/Common.hlsl:8)
+    flags = orc.FLAG_LEGACY_RR | orc.FLAG_JITTER                          # RayGen.hlsl:86-87 always jitters
+    rs.frame(W, H)
+    rs.ray_counts()                                                       # (the library is shared between tests: start the counters at zero)
+    zeros = np.zeros((H, W, 4), dtype=np.float32)
+    for sample in (0, 5):
+        rs.L.ref_write_permanent(_p(zeros))
+        rs.set_camera(cam, sample)
+        rs.dispatch(1)
+        a, rc = rs.permanent(), rs.ray_counts()
+        b, ctr = osc.render(cam, W, H, sample, 1, bounces=bounces, flags=flags)
+        assert rc == (ctr["closest_rays"], ctr["shadow_rays"]), (sample, rc, ctr)
+        assert np.array_equal(bits(a + 0), bits(b + 0)), (sample, int((bits(a + 0) != bits(b + 0)).any(axis=2).sum()))
+        assert np.isfinite(a).all() and a[..., :3].sum() > 0 and (a[..., 3] == 1).all()
+    # three samples accumulated by the reference's own temporal accumulation (RayGen.hlsl:140-156), then its averaged output (:176-183)
+    rs.L.ref_write_permanent(_p(zeros))
+    for sample in range(3):
+        rs.set_camera(cam, sample)
+        rs.dispatch(1)
+    a = rs.permanent()
+    b, _ = osc.render(cam, W, H, 0, 3, bounces=bounces, flags=flags)
+    assert np.array_equal(bits(a + 0), bits(b + 0))
+    # The legacy RayGen displays sum / max(count BEFORE this frame, 1) (RayGen.hlsl:142,176-177: frameCount is read before the
+    # accumulation): its third frame shows the three-sample sum over 2.  The engine resolves every accumulation buffer with the current
+    # count (F20, Common_v7 / Pass_spat_di_v7.hlsl:425-444); only gPermanentData is the legacy row's contract.  Asserted as found:
+    out = rs.output()
+    assert np.array_equal(bits(out[..., :3] + 0), bits((b[..., :3] / np.float32(2.0)) + 0))
