@@ -649,6 +649,11 @@ void wave_free(WaveBuffers* B) {
         if (B->ev_join[i]) cudaEventDestroy(B->ev_join[i]);
     }
     if (B->ev_fork) cudaEventDestroy(B->ev_fork);
+    for (int i = 0; i < WAVE_MAX_PARTS; i++) {
+        if (B->aux_sh[i]) cudaStreamDestroy(B->aux_sh[i]);
+        if (B->ev_sh_fork[i]) cudaEventDestroy(B->ev_sh_fork[i]);
+        if (B->ev_sh_join[i]) cudaEventDestroy(B->ev_sh_join[i]);
+    }
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
     if (B->graph_exec) cudaGraphExecDestroy(B->graph_exec);
@@ -724,11 +729,14 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         CKE(mark(SK_CLOSEST));
         return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, parts, q.order, q.n_heavy, q.cap);
     };
-    auto shadow = [&](Part& p, const RayQueue& q, float* vis) -> cudaError_t {
+    const bool side_shadow = B.shadow_overlap && !T->stage_timing && !T->stats;
+    auto shadow = [&](Part& p, const RayQueue& q, float* vis, bool side) -> cudaError_t {
         CKE(mark(SK_ANY));
-        // the occlusion result goes straight to the per-path visibility array (the separate scatter kernel of round 1 is gone)
-        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, true, nullptr, p.stream, parts, q.order, q.n_heavy, q.cap,
-                            q.pid, vis);
+        // the occlusion result goes straight to the per-path visibility array (the separate scatter kernel of round 1 is gone);
+        // a launch on the side stream has its own cursor words (it runs beside the part's closest-hit launches)
+        const int h = (int)(&p - P);
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, side ? p.cursor + 2 : p.cursor, p.hit_a, p.hit_inst, true, nullptr,
+                            side ? B.aux_sh[h] : p.stream, parts, q.order, q.n_heavy, q.cap, q.pid, vis);
     };
     // stage s of one part; the parts are issued round-robin stage by stage so that every stream always has work queued
     const int n_stages = 7 + 2 * ((int)S.bounces + 1) + 2;
@@ -752,7 +760,14 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
             CKE(mark(SK_DI_FINISH));
             k_di_finish<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, q1, p.hit_a, p.hit_inst, p.sdi, qa, B.ray_counters);
         } else if (s == 5) {
-            CKE(shadow(p, p.sdi, B.vis_di));        // DI visibility (connect); hit_inst is reused by the next closest trace
+            // DI visibility (connect): writes vis_di only, read by k_finalize
+            const int h = (int)(&p - P);
+            if (side_shadow) {
+                CKE(cudaEventRecord(B.ev_sh_fork[h], p.stream));
+                CKE(cudaStreamWaitEvent(B.aux_sh[h], B.ev_sh_fork[h], 0));
+            }
+            CKE(shadow(p, p.sdi, B.vis_di, side_shadow));
+            if (side_shadow) CKE(cudaEventRecord(B.ev_sh_join[h], B.aux_sh[h]));
         } else if (s == 6) {
             CKE(closest(p, qa));
             p.qin = qa; p.cur = 0;
@@ -778,8 +793,9 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
                 p.qin = p.qout; p.cur ^= 1;
             }
         } else if (s == last) {
-            CKE(shadow(p, p.sgi, B.vis_gi));
+            CKE(shadow(p, p.sgi, B.vis_gi, false));
         } else {
+            if (side_shadow) CKE(cudaStreamWaitEvent(p.stream, B.ev_sh_join[(int)(&p - P)], 0));
             CKE(mark(SK_FINALIZE));
             k_finalize<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.p0, p.np, S, B.vis_di, B.vis_gi, p.counts + 2, B.ray_counters);
         }
@@ -806,7 +822,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
 }
 
 // What a captured pass depends on besides the sample index: every kernel argument is in here (device pointers, counts, flags, bounds).
-struct GraphKey { SceneData S; SceneAS AS; uint32_t spp; int parts; int variant; cudaStream_t stream; };
+struct GraphKey { SceneData S; SceneAS AS; uint32_t spp; int parts; int variant; int side_shadow; cudaStream_t stream; };
 static_assert(sizeof(GraphKey) <= sizeof(WaveBuffers().graph_key), "WaveBuffers::graph_key too small");
 
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
@@ -819,6 +835,11 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         if (!B.ev_join[h - 1]) CKE(cudaEventCreateWithFlags(&B.ev_join[h - 1], cudaEventDisableTiming));
     }
     if (parts > 1 && !B.ev_fork) CKE(cudaEventCreateWithFlags(&B.ev_fork, cudaEventDisableTiming));
+    for (int h = 0; h < parts && B.shadow_overlap; h++) {
+        if (!B.aux_sh[h]) CKE(cudaStreamCreateWithFlags(&B.aux_sh[h], cudaStreamNonBlocking));
+        if (!B.ev_sh_fork[h]) CKE(cudaEventCreateWithFlags(&B.ev_sh_fork[h], cudaEventDisableTiming));
+        if (!B.ev_sh_join[h]) CKE(cudaEventCreateWithFlags(&B.ev_sh_join[h], cudaEventDisableTiming));
+    }
     static bool smem_opt_in = false;       // 72 KB of dynamic shared memory per CTA: above the 48 KB a kernel gets without asking
     if (RTX_GI_STAGE && !smem_opt_in) {
         CKE(cudaFuncSetAttribute(k_gi_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GI_STAGED * RTX_GI_BLOCK * sizeof(float4))));
@@ -836,7 +857,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     GraphKey key;
     memset(&key, 0, sizeof key);
     memcpy(&key.S, &S, sizeof S); memcpy(&key.AS, &AS, sizeof AS);
-    key.spp = spp; key.parts = parts; key.stream = stream;
+    key.spp = spp; key.parts = parts; key.stream = stream; key.side_shadow = B.shadow_overlap ? 1 : 0;
 #ifdef RTX_FAST_MATH
     key.variant = 1;
 #endif

@@ -49,6 +49,10 @@ struct WaveBuffers {
     uint32_t n_paths = 0;
     int parts = 2;                     // path ranges of a pass that run concurrently on separate streams (wave_render_pass)
     cudaStream_t aux[WAVE_MAX_PARTS - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[WAVE_MAX_PARTS - 1] = {};
+    // the DI visibility rays of a part are traced on a side stream, beside the part's indirect bounces (they are only read by k_finalize):
+    // their persistent CTAs take the SM slots the closest-hit launches leave idle while their last long rays drain
+    cudaStream_t aux_sh[WAVE_MAX_PARTS] = {}; cudaEvent_t ev_sh_fork[WAVE_MAX_PARTS] = {}, ev_sh_join[WAVE_MAX_PARTS] = {};
+    bool shadow_overlap = true;
     float4* state = nullptr;           // NSTATE * n_paths
     uint2* seeds = nullptr;            // n_paths: RNG state (StateView::seed)
     RayQueue q[2];                     // closest-hit ray queues (ping-pong)

@@ -541,7 +541,7 @@ def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
 
 
 def test_graph_replay_and_trace_order_do_not_change_the_image(rtdx, orc):
-    """RTX_OPT_PASS_GRAPH / RTX_OPT_QUEUE_LPT: the third and later passes of a static configuration replay a captured CUDA graph (the
+    """RTX_OPT_PASS_GRAPH / RTX_OPT_QUEUE_LPT / RTX_OPT_SHADOW_OVERLAP (DI visibility rays on a side stream): the third and later passes of a static configuration replay a captured CUDA graph (the
     sample index comes from a device word), and the traversal kernels claim rays longest-first through the queue's order array.  Six
     accumulated samples are bit-identical with both on (default), graph off, order off — and equal to the oracle's six samples; the
     kernel-launch count is the same whether a pass was launched directly or replayed."""
@@ -554,8 +554,9 @@ def test_graph_replay_and_trace_order_do_not_change_the_image(rtdx, orc):
         img, _ = osc.render(up["camera"], W, H, s, 1, bounces=bounces, flags=0)
         ref = img if ref is None else ref + img               # gPermanentData += sample, in sample order (F20)
     results = {}
-    for name, opts in (("default", {}), ("no graph", {rtdx.OPT_PASS_GRAPH: 0}), ("emission order", {rtdx.OPT_QUEUE_LPT: 0})):
-        ctx.set_option(rtdx.OPT_PASS_GRAPH, 1); ctx.set_option(rtdx.OPT_QUEUE_LPT, 1)
+    for name, opts in (("default", {}), ("no graph", {rtdx.OPT_PASS_GRAPH: 0}), ("emission order", {rtdx.OPT_QUEUE_LPT: 0}),
+                       ("shadow rays in sequence", {rtdx.OPT_SHADOW_OVERLAP: 0}), ("in sequence, no graph", {rtdx.OPT_SHADOW_OVERLAP: 0, rtdx.OPT_PASS_GRAPH: 0})):
+        ctx.set_option(rtdx.OPT_PASS_GRAPH, 1); ctx.set_option(rtdx.OPT_QUEUE_LPT, 1); ctx.set_option(rtdx.OPT_SHADOW_OVERLAP, 1)
         for k, v in opts.items():
             ctx.set_option(k, v)
         ctx.reset_accum(); ctx.reset_counters()
