@@ -39,7 +39,7 @@ namespace fast {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
-#define GI_STAGED 5         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 5 x 16 B x RTX_GI_BLOCK per CTA
+#define GI_STAGED 4         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 4 x 16 B x RTX_GI_BLOCK per CTA
                             // (12 planes = 72 KB per CTA when the measurement below was made)
 #ifndef RTX_GI_STAGE
 #define RTX_GI_STAGE 0      // 1: stage them (cp.async into per-thread shared-memory slots).  Bit-identical either way.  Measured on B200
@@ -303,7 +303,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         extern __shared__ float4 s_stage[];
         constexpr bool STAGE = RTX_GI_STAGE && !ITER0;
         if (STAGE) {
-            const int planes[GI_STAGED] = {SP_ORIGIN, SP_NORMAL, SP_OUTGOING, SP_ACC_FR, SP_GI_SC};
+            const int planes[GI_STAGED] = {SP_ORIGIN, SP_ACC_F, SP_ACC_FR, SP_GI_SC};
 #pragma unroll
             for (int k = 0; k < GI_STAGED; k++) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_stage[k * RTX_GI_BLOCK + threadIdx.x]);
@@ -314,7 +314,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         const f3 sample = xyz(qin.d_tmax[j]);
         const uint32_t inst = hit_inst[j];
         float4 ha = make_float4(0, 0, 0, 0);
-        HitInfo sp; MatOpt hm; f3 ke_full = mk3(0, 0, 0);
+        HitInfo sp; MatOpt hm = MatOpt(); f3 ke_full = mk3(0, 0, 0);
         if (inst != 0xFFFFFFFFu) {                                  // hit attributes: independent of the path state (hitPosition is set below)
             ha = hit_a[j];
             ClosestHit(S, mk3(0, 0, 0), sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
@@ -329,17 +329,22 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         // (SP_X1 / SP_N1 / SP_O), acc_f = acc_f_reconnection = 1, an empty GI reservoir, acc_pdf = 1 — k_di_finish does not write those
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
         const float4 one3 = make_float4(1, 1, 1, 0);
-        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);
-        // acc_f rides in the .w of the normal / outgoing / acc_f_reconnection planes (four planes per path vertex instead of five)
-        const float4 pn = ITER0 ? one3 : GI_STATE(1, SP_NORMAL), po = ITER0 ? one3 : GI_STATE(2, SP_OUTGOING), pf = ITER0 ? one3 : GI_STATE(3, SP_ACC_FR);
-        f3 origin = xyz(d0), normal = ITER0 ? xyz(a1) : xyz(pn);
-        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : xyz(po);
-        f3 acc_f = ITER0 ? mk3(1, 1, 1) : mk3(pn.w, po.w, pf.w), acc_fr = xyz(pf);
+        // Between bounces a path carries its origin, acc_f, acc_f_reconnection and the reservoir scalars: FOUR planes.  The BSDF value and
+        // pdf of the ray in flight (Sampler_v7.hlsl:436-456: evaluated by the reference when the ray comes back) are evaluated by the
+        // iteration that SAMPLED the direction, where the vertex's material, normal, outgoing direction and lobe context are live — same
+        // expressions on the same values, so bit-identical — and acc_f / acc_pdf / acc_f_reconnection are stored already multiplied
+        // (nothing else touches them in between; a ray that misses ends the path).  Before: five planes, and every bounce re-loaded the
+        // previous vertex's material and rebuilt its strategy probabilities and lobe context just for that one evaluation.
+        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);         // origin; ITER0: bits(material id), else: pdf of the ray in flight
+        const float4 pa = ITER0 ? one3 : GI_STATE(1, SP_ACC_F), pf = ITER0 ? one3 : GI_STATE(2, SP_ACC_FR);
+        f3 origin = xyz(d0), normal = xyz(a1);
+        f3 outgoing = ITER0 ? normalize3(xyz(a2)) : mk3(0, 0, 0);
+        f3 acc_f = xyz(pa), acc_fr = xyz(pf);
         // The GI reservoir of the path.  Per bounce only its scalars change (w_sum, acc_pdf, "a sample was accepted"): they live in their
         // own plane SP_GI_SC; xn / nn are written once by iteration 0; E3 and the winner's shadow end points are only ever REPLACED, so
         // later iterations neither load them (the end points: only where the path ends) nor store them unless this bounce replaced them.
         // (Before: ten planes read and ten written per path and bounce; now six and three to six + what changed.)
-        const float4 sc = ITER0 ? make_float4(0, 1.0f, 0, 0) : GI_STATE(4, SP_GI_SC);
+        const float4 sc = ITER0 ? make_float4(0, 1.0f, 0, 0) : GI_STATE(3, SP_GI_SC);
         f3 xn = mk3(0, 0, 0), nn = mk3(0, 0, 0), E3 = mk3(0, 0, 0);
         float w_sum = sc.x, acc_pdf = sc.y;
         f3 x1s = mk3(0, 0, 0), x2s = mk3(0, 0, 0);
@@ -347,9 +352,12 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
 #undef GI_STATE
         float gi_has = sc.z;                                        // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
         uint2 seed = st.seed[pid];
-        MatOpt material = load_matopt(S, __float_as_uint(d0.w), nullptr);
+        MatOpt material;                                            // the vertex the path stands on: ITER0 the primary hit, then the hit being consumed
+        if (ITER0) material = load_matopt(S, __float_as_uint(d0.w), nullptr);
+        else material = hm;
         const float fnee = (float)S.nee_samples;
         bool cont = false;
+        float next_pdf = 0.0f;
         if (inst != 0xFFFFFFFFu) {                                  // miss: path ends (deviation D1)
             sp.hitPosition = origin + ha.x * sample;                // Hit_v7.hlsl:15 (the one line of ClosestHit that needs the path state)
             if (ITER0) {
@@ -367,23 +375,9 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                     xn = origin; nn = normalize3(normal);           // :104-106
                     cont = true;
                 }
-            } else {                                                // Sampler_v7.hlsl:436-504
-                float p_d, p_s;
-                const f3 on = normalize3(outgoing);
-                CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
-                // F sees V = normalize3(on), the pdf sees V = normalize3(outgoing) = on (Sampler_v7.hlsl:443-456)
-                const bool lo = (S.cfg_flags & RTX_FLAG_LAMBERT_ONLY) != 0u;
-                const f3 N = lo ? normal : normalize3(normal);
-                const LobeCtx lobeF = make_lobe_ctx_nv(S, material, normal, N, lo ? on : normalize3(on), p_d, p_s);
-                const LobeCtx lobeP = make_lobe_ctx_nv(S, material, normal, N, on, p_d, p_s);
-                f3 brdf, unusedF; float pdf_bsdf, unusedP;
-                lobe_FP<true, false>(lobeF, -sample, false, 1.0f, 1.0f, brdf, unusedP);
-                lobe_FP<false, true>(lobeP, -sample, false, 1.0f, 1.0f, unusedF, pdf_bsdf);
-                const float NdotL = dot3(normal, sample);
+            } else {                                                // Sampler_v7.hlsl:436-504 (brdf, pdf_bsdf, NdotL and the three products: see below)
+                const float pdf_bsdf = d0.w;
                 const bool emitter = (hm.Ke.x != 0.0f || hm.Ke.y != 0.0f || hm.Ke.z != 0.0f);
-                acc_pdf *= pdf_bsdf;
-                acc_f = acc_f * (brdf * NdotL);
-                const f3 throughput = brdf * NdotL;
                 f3 contribution = mk3(0, 0, 0), emission = mk3(0, 0, 0);
                 float pdf_light = 1.0f;
                 if (emitter) {
@@ -396,8 +390,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                     emission = hm.Ke;
                     contribution = (hm.Ke * acc_f) / acc_pdf;
                 }
-                acc_fr = acc_fr * throughput;                       // Path_Sampler_v7.hlsl:232
-                if (length3(contribution) > 0.0f) {                 // :235-261
+                if (length3(contribution) > 0.0f) {                 // Path_Sampler_v7.hlsl:235-261
                     float mi = pdf_bsdf / (fnee * pdf_light + pdf_bsdf);
                     f3 E_reconnection = (acc_fr * mi) * emission;
                     f3 E_path = mi * contribution;
@@ -416,12 +409,10 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             uint32_t strategy = SelectWithPs(ps_sel, material, seed);
             LobeCtx lobe;
             const f3 Nn = normalize3(normal);
-            if (S.nee_samples > 0u) {
-                const f3 on = normalize3(outgoing);
-                float p_d, p_s;
-                CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
-                lobe = make_lobe_ctx_nv(S, material, normal, Nn, normalize3(on), p_d, p_s);
-            }
+            const f3 on = normalize3(outgoing);
+            float p_d, p_s;
+            CalculateStrategyProbabilities(S, material, on, normal, p_d, p_s);
+            lobe = make_lobe_ctx_nv(S, material, normal, Nn, normalize3(on), p_d, p_s);
             for (uint32_t k = 0; k < S.nee_samples; k++) {
                 float pdf_light = 1.0f, pdf_bsdf = 1.0f;
                 f3 throughput_NEE = mk3(1, 1, 1), emission_NEE = mk3(0, 0, 0), x2;
@@ -442,6 +433,19 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             strategy = SelectWithPs(ps_sel, material, seed);
             const f3 s2 = SampleBRDF(strategy, material, outgoing, normal, seed);
             emit = true; ro = origin; rd = s2;
+            // What the reference evaluates when this ray comes back (Sampler_v7.hlsl:436-456, Path_Sampler_v7.hlsl:232): F sees
+            // V = normalize3(on) — the NEE context above (with RTX_FLAG_LAMBERT_ONLY a context ignores N and V) — the pdf sees V = on.
+            {
+                const LobeCtx lobeP = make_lobe_ctx_nv(S, material, normal, Nn, on, p_d, p_s);
+                f3 brdf, unusedF; float unusedP;
+                lobe_FP<true, false>(lobe, -s2, false, 1.0f, 1.0f, brdf, unusedP);
+                lobe_FP<false, true>(lobeP, -s2, false, 1.0f, 1.0f, unusedF, next_pdf);
+                const float NdotL = dot3(normal, s2);
+                const f3 throughput = brdf * NdotL;
+                acc_pdf *= next_pdf;
+                acc_f = acc_f * throughput;
+                acc_fr = acc_fr * throughput;
+            }
         } else {
             // the path's sampling is over: one shadow ray for the reservoir winner (Path_Sampler_v7.hlsl:271-283)
             if (!ITER0) { x1s = xyz(st.at(SP_SH1, pid)); x2s = xyz(st.at(SP_SH2, pid)); }     // the winner's end points, set by an earlier bounce
@@ -452,11 +456,10 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
                 stmax = fmaxf(RTX_S_BIAS, len - (RTX_S_BIAS * 5.0f));
             }
         }
-        if (ITER0 || emit) {                                        // the path vertex: read again only if another bounce follows
-            st.at(SP_ORIGIN, pid) = f4u(origin, material.mID);
-            st.at(SP_NORMAL, pid) = f4(normal, acc_f.x);
-            st.at(SP_OUTGOING, pid) = f4(outgoing, acc_f.y);
-            st.at(SP_ACC_FR, pid) = f4(acc_fr, acc_f.z);
+        if (emit) {                                                 // the path vertex: read again only if another bounce follows
+            st.at(SP_ORIGIN, pid) = f4(origin, next_pdf);
+            st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
+            st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
         }
         st.at(SP_GI_SC, pid) = make_float4(w_sum, acc_pdf, gi_has, 0.0f);
         if (ITER0) {                                                // written once (Path_Sampler_v7.hlsl:104-106)

@@ -18,11 +18,9 @@ enum StatePlane {
     SP_GI_XN,       // reservoir_GI.xn, - (k_finalize: w_sum after the visibility test)
     SP_GI_NN,       // reservoir_GI.nn, -
     SP_GI_E3,       // reservoir_GI.E3 (binary16 values), -
-    SP_ORIGIN,      // path origin, bits(current material id)
-    SP_NORMAL,      // path normal, acc_f.x
-    SP_OUTGOING,    // path outgoing, acc_f.y
-    SP_ACC_F,       // (E0: unused since round 2, acc_f rides in the .w of SP_NORMAL / SP_OUTGOING / SP_ACC_FR; legacy estimator: colour)
-    SP_ACC_FR,      // acc_f_reconnection, acc_f.z
+    SP_ORIGIN,      // path origin, pdf of the BSDF ray in flight
+    SP_ACC_F,       // acc_f incl. the ray in flight, -  (legacy estimator: colour, pdf)
+    SP_ACC_FR,      // acc_f_reconnection incl. the ray in flight, -
     SP_SH1,         // x1_shadow, flag (1 = a reservoir winner exists)
     SP_SH2,         // x2_shadow, -
     SP_RESULT,      // per-sample radiance C, flag (1 = sampling path: finalize computes C)
