@@ -385,7 +385,8 @@ __device__ __forceinline__ void ClosestHit(const SceneData& S, f3 ro, f3 rd, flo
     f3 pos[3], nrm[3];
     {
         const float4* r = M.shade + (size_t)prim * 5;
-        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4);
+        // one record per hit out of 84 MB (C2): evict-first, like the path state (wave_dev.cuh StateView::ld)
+        const float4 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3), r4 = __ldcs(r + 4);
         pos[0] = mk3(r0.x, r0.y, r0.z); pos[1] = mk3(r1.x, r1.y, r1.z); pos[2] = mk3(r2.x, r2.y, r2.z);
         nrm[0] = mk3(r0.w, r1.w, r2.w); nrm[1] = mk3(r3.x, r3.y, r3.z); nrm[2] = mk3(r4.x, r4.y, r4.z);
     }

@@ -15,7 +15,21 @@ struct StateView {
 #else
     __device__ __forceinline__ float4& at(int plane, uint32_t pid) const { return base[(size_t)plane * n + pid]; }
 #endif
+    // The path state is STREAMED: each stage reads a plane once and the next reader is a launch later, ~0.5 GB per k_gi_step launch.
+    // ld / stt use the evict-first cache policy (ld.global.cs / st.global.cs) so that this traffic does not push the BVH, which every
+    // traversal launch re-reads at random, out of the L2: closest-hit launches -2.7 %, C2 pass -1.3 % (profiles/r02_l2_policy_ab.txt).
+    // -DRTX_STREAM_HINTS=0 restores plain accesses.
+#ifndef RTX_STREAM_HINTS
+#define RTX_STREAM_HINTS 1
+#endif
+    __device__ __forceinline__ float4 ld(int plane, uint32_t pid) const { return RTX_STREAM_HINTS ? __ldcs(&at(plane, pid)) : at(plane, pid); }
+    __device__ __forceinline__ void stt(int plane, uint32_t pid, float4 v) const { if (RTX_STREAM_HINTS) __stcs(&at(plane, pid), v); else at(plane, pid) = v; }
+    __device__ __forceinline__ uint2 ld_seed(uint32_t pid) const { return RTX_STREAM_HINTS ? __ldcs(&seed[pid]) : seed[pid]; }
+    __device__ __forceinline__ void st_seed(uint32_t pid, uint2 v) const { if (RTX_STREAM_HINTS) __stcs(&seed[pid], v); else seed[pid] = v; }
 };
+
+// queue entries and hit records a shading stage consumes (read once)
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return RTX_STREAM_HINTS ? __ldcs(p) : *p; }
 
 __device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 __device__ __forceinline__ float4 f4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }

@@ -81,7 +81,7 @@ k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, con
         q0.d_tmax[k] = f4(dir, 10000.0f);
         q0.pid[k] = p;
         st.seed[p] = seed;
-        st.at(SP_O, p) = f4(-dir, 0.0f);
+        st.at(SP_O, p) = f4(-dir, 0.0f);            // (plain stores: k_shade_primary reads them one launch later)
         st.at(SP_RESULT, p) = make_float4(0, 0, 0, 0);
         vis_di[p] = 1.0f; vis_gi[p] = 1.0f;
     }
@@ -126,21 +126,21 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
     if (j == 0) atomicAdd(&ray_counters[0], (unsigned long long)n);
     bool emit = false; f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0); uint32_t pid = 0;
     if (j < n) {
-        pid = qin.pid[j];
-        const uint32_t inst = hit_inst[j];
+        pid = ld_stream(qin.pid + j);
+        const uint32_t inst = ld_stream(hit_inst + j);
         if (inst != 0xFFFFFFFFu) {                                  // miss: radiance 0 (DESIGN.md deviation D1)
-            const float4 ha = hit_a[j];
-            const f3 o = xyz(qin.o_tmin[j]), d = xyz(qin.d_tmax[j]);
+            const float4 ha = ld_stream(hit_a + j);
+            const f3 o = xyz(ld_stream(qin.o_tmin + j)), d = xyz(ld_stream(qin.d_tmax + j));
             HitInfo payload;
             ClosestHit(S, o, d, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, payload);
             f3 ke_full;
             const MatOpt mat = load_matopt(S, payload.materialID, &ke_full);
             if (length3(ke_full) > 0.0f) {                          // :103-106 ; L1 = half3(Ke) (deviation D5: accumulated)
-                st.at(SP_RESULT, pid) = f4(mat.Ke, 3.0f);          // .w: 0 miss, 3 emitter, 1 sampled (2 once finalized)
-                st.at(SP_X1, pid) = f4u(mk3(0, 0, 0), payload.materialID);
-                st.at(SP_DI_L2, pid) = f4u(mk3(0, 0, 0), inst);
+                st.stt(SP_RESULT, pid, f4(mat.Ke, 3.0f));          // .w: 0 miss, 3 emitter, 1 sampled (2 once finalized)
+                st.stt(SP_X1, pid, f4u(mk3(0, 0, 0), payload.materialID));
+                st.stt(SP_DI_L2, pid, f4u(mk3(0, 0, 0), inst));
             } else {
-                uint2 seed = st.seed[pid];
+                uint2 seed = st.ld_seed(pid);
                 const f3 outgoing = -d;
                 const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, payload.hitNormal, seed);
                 f3 rx = mk3(0, 0, 0), rn = mk3(0, 0, 0), rL = mk3(0, 0, 0); float w_sum = 0.0f;
@@ -158,14 +158,14 @@ k_shade_primary(StateView st, SceneData S, RayQueue qin, const float4* __restric
                 }
                 const f3 sample = SampleBRDF(strategy, mat, outgoing, payload.hitNormal, seed);   // Sampler_v7.hlsl:218-220
                 emit = true; ro = payload.hitPosition; rd = sample;
-                st.at(SP_X1, pid) = f4u(payload.hitPosition, payload.materialID);
-                st.at(SP_N1, pid) = f4(payload.hitNormal, 0.0f);
-                st.at(SP_O, pid) = f4(outgoing, 0.0f);
-                st.seed[pid] = seed;
-                st.at(SP_DI_X2, pid) = f4(rx, w_sum);
-                st.at(SP_DI_N2, pid) = f4(rn, 0.0f);
-                st.at(SP_DI_L2, pid) = f4u(rL, inst);              // .w: primary-hit instance (SampleData::objID)
-                st.at(SP_RESULT, pid) = make_float4(0, 0, 0, 1.0f);
+                st.stt(SP_X1, pid, f4u(payload.hitPosition, payload.materialID));
+                st.stt(SP_N1, pid, f4(payload.hitNormal, 0.0f));
+                st.stt(SP_O, pid, f4(outgoing, 0.0f));
+                st.st_seed(pid, seed);
+                st.stt(SP_DI_X2, pid, f4(rx, w_sum));
+                st.stt(SP_DI_N2, pid, f4(rn, 0.0f));
+                st.stt(SP_DI_L2, pid, f4u(rL, inst));              // .w: primary-hit instance (SampleData::objID)
+                st.stt(SP_RESULT, pid, make_float4(0, 0, 0, 1.0f));
             }
         }
     }
@@ -183,19 +183,19 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
     bool emit = false, emit_sh = false; uint32_t pid = 0;
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
-        pid = qin.pid[j];
-        const float4 a0 = st.at(SP_X1, pid), a1 = st.at(SP_N1, pid), a2 = st.at(SP_O, pid);
+        pid = ld_stream(qin.pid + j);
+        const float4 a0 = st.ld(SP_X1, pid), a1 = st.ld(SP_N1, pid), a2 = st.ld(SP_O, pid);
         const f3 x1 = xyz(a0), hitNormal = xyz(a1), o = xyz(a2);
         const uint32_t mID = __float_as_uint(a0.w);
-        uint2 seed = st.seed[pid];
+        uint2 seed = st.ld_seed(pid);
         const MatOpt mat = load_matopt(S, mID, nullptr);
-        float4 b0 = st.at(SP_DI_X2, pid);
-        const float4 b2 = st.at(SP_DI_L2, pid);
-        f3 rx = xyz(b0), rn = xyz(st.at(SP_DI_N2, pid)), rL = xyz(b2); float w_sum = b0.w;
-        const f3 sample = xyz(qin.d_tmax[j]);
-        const uint32_t inst = hit_inst[j];
+        float4 b0 = st.ld(SP_DI_X2, pid);
+        const float4 b2 = st.ld(SP_DI_L2, pid);
+        f3 rx = xyz(b0), rn = xyz(st.ld(SP_DI_N2, pid)), rL = xyz(b2); float w_sum = b0.w;
+        const f3 sample = xyz(ld_stream(qin.d_tmax + j));
+        const uint32_t inst = ld_stream(hit_inst + j);
         if (inst != 0xFFFFFFFFu) {                                  // miss => materials[MISS] reads 0 => p_hat = 0
-            const float4 ha = hit_a[j];
+            const float4 ha = ld_stream(hit_a + j);
             HitInfo sp;
             ClosestHit(S, x1, sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
             float4 kd, ks, ke, pr;
@@ -238,16 +238,16 @@ k_di_finish(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ 
             sd = normalize3(d21);
             stmax = fmaxf(dist - 10.0f * RTX_S_BIAS, 2.0f * RTX_S_BIAS);
         }
-        st.at(SP_DI_X2, pid) = f4(rx, w_sum);
-        st.at(SP_DI_N2, pid) = f4(rn, f_g);
-        st.at(SP_DI_L2, pid) = f4(rL, b2.w);
-        st.at(SP_DI_R, pid) = f4(rdi, 0.0f);
+        st.stt(SP_DI_X2, pid, f4(rx, w_sum));
+        st.stt(SP_DI_N2, pid, f4(rn, f_g));
+        st.stt(SP_DI_L2, pid, f4(rL, b2.w));
+        st.stt(SP_DI_R, pid, f4(rdi, 0.0f));
         // SamplePathSimple step 1: Path_Sampler_v7.hlsl:24-52
         const f3 outgoing = normalize3(o);
         const uint32_t strategy = SelectSamplingStrategy(S, mat, outgoing, hitNormal, seed);
         const f3 s2 = SampleBRDF(strategy, mat, outgoing, hitNormal, seed);
         emit = true; ro = x1; rd = s2;
-        st.seed[pid] = seed;            // (SP_N1 / SP_O keep what k_shade_primary wrote)
+        st.st_seed(pid, seed);            // (SP_N1 / SP_O keep what k_shade_primary wrote)
         // the path state of SamplePathSimple's start (origin = x1, normal, outgoing = normalize(o), acc_f = 1, empty GI reservoir) is not
         // stored: k_gi_step<ITER0> derives it from SP_X1 / SP_N1 / SP_O and constants
     }
@@ -294,7 +294,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
     bool emit = false, emit_sh = false; uint32_t pid = 0;
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
-        pid = qin.pid[j];
+        pid = ld_stream(qin.pid + j);
         // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the six 16-byte planes a bounce reads are requested with
         // cp.async straight into this thread's shared-memory slots — no registers are held while they are in flight (at 80 registers the
         // compiler could keep two or three of the float4 loads outstanding and serialised the rest next to their uses) — and they
@@ -311,20 +311,20 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const f3 sample = xyz(qin.d_tmax[j]);
-        const uint32_t inst = hit_inst[j];
+        const f3 sample = xyz(ld_stream(qin.d_tmax + j));
+        const uint32_t inst = ld_stream(hit_inst + j);
         float4 ha = make_float4(0, 0, 0, 0);
         HitInfo sp; MatOpt hm = MatOpt(); f3 ke_full = mk3(0, 0, 0);
         if (inst != 0xFFFFFFFFu) {                                  // hit attributes: independent of the path state (hitPosition is set below)
-            ha = hit_a[j];
+            ha = ld_stream(hit_a + j);
             ClosestHit(S, mk3(0, 0, 0), sample, ha.x, ha.y, ha.z, __float_as_uint(ha.w), inst, sp);
             hm = load_matopt(S, sp.materialID, &ke_full);
         }
         if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
-#define GI_STATE(K, PLANE) (!STAGE ? st.at(PLANE, pid) : s_stage[(K) * RTX_GI_BLOCK + threadIdx.x])
+#define GI_STATE(K, PLANE) (!STAGE ? st.ld(PLANE, pid) : s_stage[(K) * RTX_GI_BLOCK + threadIdx.x])
         const float4 zero4 = make_float4(0, 0, 0, 0);
         // SP_N1 / SP_O (the primary hit's normal and outgoing direction) are only read by iteration 0
-        const float4 a1 = ITER0 ? st.at(SP_N1, pid) : zero4, a2 = ITER0 ? st.at(SP_O, pid) : zero4;
+        const float4 a1 = ITER0 ? st.ld(SP_N1, pid) : zero4, a2 = ITER0 ? st.ld(SP_O, pid) : zero4;
         // iteration 0 starts from the state SamplePathSimple begins with (Path_Sampler_v7.hlsl:9-23): the path vertex is the primary hit
         // (SP_X1 / SP_N1 / SP_O), acc_f = acc_f_reconnection = 1, an empty GI reservoir, acc_pdf = 1 — k_di_finish does not write those
         // ten planes and this kernel does not read them (330 MB less written and 300 MB less read per 1080p pass)
@@ -335,7 +335,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         // expressions on the same values, so bit-identical — and acc_f / acc_pdf / acc_f_reconnection are stored already multiplied
         // (nothing else touches them in between; a ray that misses ends the path).  Before: five planes, and every bounce re-loaded the
         // previous vertex's material and rebuilt its strategy probabilities and lobe context just for that one evaluation.
-        const float4 d0 = ITER0 ? st.at(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);         // origin; ITER0: bits(material id), else: pdf of the ray in flight
+        const float4 d0 = ITER0 ? st.ld(SP_X1, pid) : GI_STATE(0, SP_ORIGIN);         // origin; ITER0: bits(material id), else: pdf of the ray in flight
         const float4 pa = ITER0 ? one3 : GI_STATE(1, SP_ACC_F), pf = ITER0 ? one3 : GI_STATE(2, SP_ACC_FR);
         f3 origin = xyz(d0), normal = xyz(a1);
         f3 outgoing = ITER0 ? normalize3(xyz(a2)) : mk3(0, 0, 0);
@@ -351,7 +351,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
         bool e3_set = false, sh_set = false;
 #undef GI_STATE
         float gi_has = sc.z;                                        // 1 once UpdateReservoir_GI has accepted a sample (ReSTIR: reservoir.xn/nn)
-        uint2 seed = st.seed[pid];
+        uint2 seed = st.ld_seed(pid);
         MatOpt material;                                            // the vertex the path stands on: ITER0 the primary hit, then the hit being consumed
         if (ITER0) material = load_matopt(S, __float_as_uint(d0.w), nullptr);
         else material = hm;
@@ -448,7 +448,7 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             }
         } else {
             // the path's sampling is over: one shadow ray for the reservoir winner (Path_Sampler_v7.hlsl:271-283)
-            if (!ITER0) { x1s = xyz(st.at(SP_SH1, pid)); x2s = xyz(st.at(SP_SH2, pid)); }     // the winner's end points, set by an earlier bounce
+            if (!ITER0) { x1s = xyz(st.ld(SP_SH1, pid)); x2s = xyz(st.ld(SP_SH2, pid)); }     // the winner's end points, set by an earlier bounce
             const f3 ds = x2s - x1s;
             const float len = length3(ds);
             if (S.nee_samples > 0u && len > RTX_EPS) {
@@ -457,18 +457,18 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
             }
         }
         if (emit) {                                                 // the path vertex: read again only if another bounce follows
-            st.at(SP_ORIGIN, pid) = f4(origin, next_pdf);
-            st.at(SP_ACC_F, pid) = f4(acc_f, 0.0f);
-            st.at(SP_ACC_FR, pid) = f4(acc_fr, 0.0f);
+            st.stt(SP_ORIGIN, pid, f4(origin, next_pdf));
+            st.stt(SP_ACC_F, pid, f4(acc_f, 0.0f));
+            st.stt(SP_ACC_FR, pid, f4(acc_fr, 0.0f));
         }
-        st.at(SP_GI_SC, pid) = make_float4(w_sum, acc_pdf, gi_has, 0.0f);
+        st.stt(SP_GI_SC, pid, make_float4(w_sum, acc_pdf, gi_has, 0.0f));
         if (ITER0) {                                                // written once (Path_Sampler_v7.hlsl:104-106)
-            st.at(SP_GI_XN, pid) = f4(xn, 0.0f);
-            st.at(SP_GI_NN, pid) = f4(nn, 0.0f);
+            st.stt(SP_GI_XN, pid, f4(xn, 0.0f));
+            st.stt(SP_GI_NN, pid, f4(nn, 0.0f));
         }
-        if (ITER0 || e3_set) st.at(SP_GI_E3, pid) = f4(E3, 0.0f);
-        if (ITER0 || sh_set) { st.at(SP_SH1, pid) = f4(x1s, 0.0f); st.at(SP_SH2, pid) = f4(x2s, 0.0f); }
-        st.seed[pid] = seed;
+        if (ITER0 || e3_set) st.stt(SP_GI_E3, pid, f4(E3, 0.0f));
+        if (ITER0 || sh_set) { st.stt(SP_SH1, pid, f4(x1s, 0.0f)); st.stt(SP_SH2, pid, f4(x2s, 0.0f)); }
+        st.st_seed(pid, seed);
     }
     push_ray_pair(q_shadow, emit_sh, emit_sh && ray_is_heavy(S, so, 0.5f * RTX_S_BIAS, sd, stmax), so, 0.5f * RTX_S_BIAS, sd, stmax,
                   qout, emit, emit && ray_is_heavy(S, ro, RTX_S_BIAS, rd, 10000.0f), ro, RTX_S_BIAS, rd, 10000.0f, pid);
@@ -482,26 +482,26 @@ k_finalize(StateView st, uint32_t p0, uint32_t np, SceneData S, const float* __r
     if (k == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
     if (k >= np) return;
     const uint32_t p = p0 + k;
-    const float4 res = st.at(SP_RESULT, p);
+    const float4 res = st.ld(SP_RESULT, p);
     if (res.w != 1.0f) return;
-    const float4 a0 = st.at(SP_X1, p);
-    const f3 x1 = xyz(a0), hitNormal = xyz(st.at(SP_N1, p)), o = xyz(st.at(SP_O, p));
+    const float4 a0 = st.ld(SP_X1, p);
+    const f3 x1 = xyz(a0), hitNormal = xyz(st.ld(SP_N1, p)), o = xyz(st.ld(SP_O, p));
     const MatOpt mat = load_matopt(S, __float_as_uint(a0.w), nullptr);
     const f3 n1 = normalize3(hitNormal);
-    const f3 rdi = xyz(st.at(SP_DI_R, p));
-    const float f_g = st.at(SP_DI_N2, p).w, w_sum = st.at(SP_DI_X2, p).w;
+    const f3 rdi = xyz(st.ld(SP_DI_R, p));
+    const float f_g = st.ld(SP_DI_N2, p).w, w_sum = st.ld(SP_DI_X2, p).w;
     const float p_hat = f_g * vis_di[p];
     const float W = (p_hat > RTX_EPS) ? w_sum / p_hat : 0.0f;
     const f3 Cdi = rdi * W;
-    const float4 c0 = st.at(SP_GI_XN, p);
-    const float w_sum_gi = st.at(SP_GI_SC, p).x * vis_gi[p];
-    const f3 f_gi = ReconnectGI(S, x1, n1, xyz(c0), xyz(st.at(SP_GI_E3, p)), o, mat);
+    const float4 c0 = st.ld(SP_GI_XN, p);
+    const float w_sum_gi = st.ld(SP_GI_SC, p).x * vis_gi[p];
+    const f3 f_gi = ReconnectGI(S, x1, n1, xyz(c0), xyz(st.ld(SP_GI_E3, p)), o, mat);
     const float p_hat_gi = length3(f_gi);
     const float W_GI = (p_hat_gi > RTX_EPS) ? w_sum_gi / p_hat_gi : 0.0f;
     const f3 C = Cdi + f_gi * W_GI;
-    st.at(SP_RESULT, p) = f4(C, 2.0f);
-    st.at(SP_GI_XN, p) = make_float4(c0.x, c0.y, c0.z, w_sum_gi);
-    st.at(SP_DI_R, p) = f4(rdi, W);
+    st.at(SP_RESULT, p) = f4(C, 2.0f);                 // (plain: k_accumulate reads it next)
+    st.stt(SP_GI_XN, p, make_float4(c0.x, c0.y, c0.z, w_sum_gi));
+    st.stt(SP_DI_R, p, f4(rdi, W));
     st.at(SP_GI_E3, p).w = W_GI;
     st.at(SP_SH1, p).w = p_hat;
 }

@@ -1,6 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/tlas_nodes.txt; : > $O
-RTX_B200_LIB=build/variants/tlasstat.so python tools/stage_times.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 2 --tag "C3 (tri column = TLAS node visits)" >> $O 2>&1
-RTX_B200_LIB=build/variants/tlasstat.so python tools/stage_times.py --passes 2 --tag "C2 (tri column = TLAS node visits)" >> $O 2>&1
-cat $O
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/gpu_tests.log
+O=gpurun_out/sweep_hints.txt; : > $O
+for v in default nohints recstream; do
+L=build/variants/$v.so; [ $v = default ] && L=royaltracer-dx_b200/librtx_b200.so
+RTX_B200_LIB=$L python tools/stage_times.py --opt PASS_PARTS=1 --tag "C2 $v" >> $O 2>&1
+RTX_B200_LIB=$L python tools/pass_time.py --passes 30 --tag "C2 $v" >> $O 2>&1
+RTX_B200_LIB=$L python tools/stage_times.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 4 --tag "C3 $v" >> $O 2>&1
+done
+cat gpurun_out/gpu_tests.log; cat $O
