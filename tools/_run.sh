@@ -1,11 +1,8 @@
 #!/bin/bash
+# scratch runner for gpurun calls: edit, run as `gpurun -- 'bash tools/_run.sh'`; outputs under gpurun_out/
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/gpu_tests.log
-O=gpurun_out/sweep_hints.txt; : > $O
-for v in default nohints recstream; do
-L=build/variants/$v.so; [ $v = default ] && L=royaltracer-dx_b200/librtx_b200.so
-RTX_B200_LIB=$L python tools/stage_times.py --opt PASS_PARTS=1 --tag "C2 $v" >> $O 2>&1
-RTX_B200_LIB=$L python tools/pass_time.py --passes 30 --tag "C2 $v" >> $O 2>&1
-RTX_B200_LIB=$L python tools/stage_times.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 4 --tag "C3 $v" >> $O 2>&1
-done
-cat gpurun_out/gpu_tests.log; cat $O
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/gpu_tests.log
+cat gpurun_out/gpu_tests.log
+( time python bench.py > gpurun_out/bench_default_timed.json ) 2> gpurun_out/bench_default_time.txt
+tail -3 gpurun_out/bench_default_time.txt
+bash tools/final_capture_r02.sh s3
