@@ -39,12 +39,13 @@ namespace fast {
 #ifndef RTX_GI_MINB
 #define RTX_GI_MINB 2       // resident CTAs per SM the register budget of k_gi_step is set for
 #endif
-#define GI_STAGED 4         // path-state planes k_gi_step (iterations >= 1) can stage through shared memory: 4 x 16 B x RTX_GI_BLOCK per CTA
-                            // (12 planes = 72 KB per CTA when the measurement below was made)
+#define GI_STAGED 4         // path-state planes k_gi_step (iterations >= 1) stages through shared memory: 4 x 16 B x RTX_GI_BLOCK = 24 KB per CTA
 #ifndef RTX_GI_STAGE
-#define RTX_GI_STAGE 0      // 1: stage them (cp.async into per-thread shared-memory slots).  Bit-identical either way.  Measured on B200
-#endif                      // (profiles/r02_gi_step_staging.txt): k_gi_step 3.81 -> 4.11 ms per C2 pass (the 144 KB of shared memory per SM are
-                            // taken from the L1 that holds vertices, materials and lights), 2.81 -> 2.73 ms on C3: off by default
+#define RTX_GI_STAGE 1      // 1: stage them (cp.async into per-thread shared-memory slots); 0: plain loads.  Bit-identical either way.
+#endif                      // Measured on B200 (profiles/r02_gi_step_staging.txt): with the twelve planes a bounce read at the start of round 2
+                            // (72 KB per CTA, 144 KB per SM taken from the L1 that holds materials and lights) k_gi_step 3.81 -> 4.11 ms per C2
+                            // pass; with today's four planes (48 KB per SM) the stage alone is unchanged and the C2 pass with its concurrent
+                            // path ranges gains 1.2 % (7.41 -> 7.33 ms), fast-math 6.01 -> 5.94; C3 13.11 -> 13.17
 
 // camera ray, shaders/Pass_init_di_v7.hlsl:59,80-95
 __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t W, uint32_t H, uint32_t x, uint32_t y, float jx, float jy,
@@ -295,10 +296,10 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 0), so = mk3(0, 0, 0), sd = mk3(0, 0, 0); float stmax = 0.0f;
     if (j < n) {
         pid = ld_stream(qin.pid + j);
-        // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the six 16-byte planes a bounce reads are requested with
+        // ---- path state staged through shared memory (iterations >= 1, build option RTX_GI_STAGE): the four 16-byte planes a bounce reads are requested with
         // cp.async straight into this thread's shared-memory slots — no registers are held while they are in flight (at 80 registers the
         // compiler could keep two or three of the float4 loads outstanding and serialised the rest next to their uses) — and they
-        // land while the hit's attributes (instance -> model -> indices -> vertices -> material) are fetched, a chain of four dependent
+        // land while the hit's attributes (instance -> model -> attribute record -> material) are fetched, a chain of dependent
         // loads that does not need the state.  Each thread reads back only its own slots, so no CTA barrier is needed.
         extern __shared__ float4 s_stage[];
         constexpr bool STAGE = RTX_GI_STAGE && !ITER0;
