@@ -135,7 +135,7 @@ __global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict
 #define PLOC_RADIUS 16
 #define C_NODE 1.0f
 #ifndef C_PRIM
-#define C_PRIM 0.3f
+#define C_PRIM 0.9f      // relative cost of a primitive test (swept 0.15 .. 2.5 on C2 / C3 / C5: profiles/r02_sah_prim_cost_sweep.txt)
 #endif
 
 struct Hier {
