@@ -132,7 +132,9 @@ __global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict
 // table of the surface-area-heuristic dynamic programme that later picks the optimal 8-wide collapse:
 //   C(m,1) = min(C_leaf(m), C_inner(m)),  C(m,i) = min(C_dist(m,i), C(m,i-1)),
 //   C_inner(m) = A_m * c_node + C_dist(m,8),  C_dist(m,j) = min_k C(left,k) + C(right,j-k),  C_leaf(m) = A_m * P_m * c_prim (P_m <= 3)
+#ifndef PLOC_RADIUS
 #define PLOC_RADIUS 16
+#endif
 #define C_NODE 1.0f
 #ifndef C_PRIM
 #define C_PRIM 0.9f      // relative cost of a primitive test (swept 0.15 .. 2.5 on C2 / C3 / C5: profiles/r02_sah_prim_cost_sweep.txt)
