@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/sweep_spminb.txt; : > $O
-for v in default spminb6 spminb5 spminb4; do
-L=build/variants/$v.so; [ $v = default ] && L=royaltracer-dx_b200/librtx_b200.so
-RTX_B200_LIB=$L python tools/stage_times.py --opt PASS_PARTS=1 --tag "C2 $v" >> $O 2>&1
-RTX_B200_LIB=$L python tools/pass_time.py --passes 30 --tag "C2 $v" >> $O 2>&1
-RTX_B200_LIB=$L python tools/stage_times.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 4 --tag "C3 $v" >> $O 2>&1
-done
-cat $O
+S=gpurun_out/sanitizer2.txt; : > $S
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "memcheck smoke rc=$?" >> $S
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "racecheck smoke rc=$?" >> $S
+timeout 900 compute-sanitizer --tool initcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "initcheck smoke rc=$?" >> $S
+timeout 1200 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "concurrent_pass_parts or graph_replay or engine_side_reduce or instance_list_changes" >> $S 2>&1; echo "memcheck tests rc=$?" >> $S
+grep -E "SUMMARY|rc=|passed|failed|Error" $S
