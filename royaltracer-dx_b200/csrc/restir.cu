@@ -198,8 +198,9 @@ k_temporal_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, u
             }
         }
     }
-    push_ray(q, e0, r0.o, 0.0f, r0.d, r0.tmax, pix * 16u + 0u);
-    push_ray(q, e1, r1.o, 0.0f, r1.d, r1.tmax, pix * 16u + 1u);
+    // the queue's trace order is recorded like in the E0 stages (wave_dev.cuh push_ray2)
+    push_ray2(q, e0, e0 && ray_is_heavy(S, r0.o, 0.0f, r0.d, r0.tmax), r0.o, 0.0f, r0.d, r0.tmax, pix * 16u + 0u);
+    push_ray2(q, e1, e1 && ray_is_heavy(S, r1.o, 0.0f, r1.d, r1.tmax), r1.o, 0.0f, r1.d, r1.tmax, pix * 16u + 1u);
 }
 
 __global__ void __launch_bounds__(RS_BLOCK, RTX_RS_MINB)
@@ -316,7 +317,7 @@ k_spatial_a(RsView R, SceneData S, const rtx_camera_params* __restrict__ cam, ui
                 r = make_vis_ray(sc.x1, sc.n1, gn.x);
             }
         }
-        push_ray(q, e, r.o, 0.0f, r.d, r.tmax, pix * 16u + slot);
+        push_ray2(q, e, e && ray_is_heavy(S, r.o, 0.0f, r.d, r.tmax), r.o, 0.0f, r.d, r.tmax, pix * 16u + slot);
     }
 }
 
@@ -428,7 +429,7 @@ k_spatial_b(RsView R, SceneData S, RayQueue q) {
             R.tmp[(size_t)R.n + pix] = f4(f_fin * gc.W, 2.0f);
         }
     }
-    push_ray(q, e, vr.o, 0.0f, vr.d, vr.tmax, pix * 16u + 9u);
+    push_ray2(q, e, e && ray_is_heavy(S, vr.o, 0.0f, vr.d, vr.tmax), vr.o, 0.0f, vr.d, vr.tmax, pix * 16u + 9u);
 }
 
 // W of the DI reservoir, final colour, accumulation F20 (Pass_spat_di_v7.hlsl:343-365,383-404)
@@ -452,15 +453,10 @@ k_spatial_c(RsView R, float4* __restrict__ accum) {
     }
 }
 
-// occlusion bits of a traced shadow queue: pid = pixel * 16 + slot
-__global__ void __launch_bounds__(RS_BLOCK)
-k_scatter_mask(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ pid, const uint32_t* __restrict__ hit_inst,
-               uint32_t* __restrict__ vmask, unsigned long long* ray_counters) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = *n_ptr;
-    if (j == 0) atomicAdd(&ray_counters[1], (unsigned long long)n);
-    if (j >= n) return;
-    if (hit_inst[j] != 0xFFFFFFFFu) atomicOr(&vmask[pid[j] >> 4], 1u << (pid[j] & 15u));
+// The occlusion bits of a traced shadow queue (pid = pixel * 16 + slot) are set by the any-hit launch itself (trace.cu: vmask); this
+// adds the queue's size to the shadow-ray counter
+__global__ void k_count_shadow_rays(const uint32_t* __restrict__ n_ptr, unsigned long long* ray_counters) {
+    atomicAdd(&ray_counters[1], (unsigned long long)*n_ptr);
 }
 
 __global__ void __launch_bounds__(RS_BLOCK)
@@ -495,8 +491,9 @@ cudaError_t restir_alloc(RestirBuffers* R, uint32_t width, uint32_t height) {
     CKE(cudaMalloc((void**)&R->q.o_tmin, cap * 16));
     CKE(cudaMalloc((void**)&R->q.d_tmax, cap * 16));
     CKE(cudaMalloc((void**)&R->q.pid, cap * 4));
-    CKE(cudaMalloc((void**)&R->q_hit, cap * 4));
-    CKE(cudaMalloc((void**)&R->q_count, 4 * 4));
+    CKE(cudaMalloc((void**)&R->q.order, cap * 4));
+    R->q.cap = (uint32_t)cap;
+    CKE(cudaMalloc((void**)&R->q_count, 12 * 4));          // queue i: count [i], heavy rays [4 + i], the others [8 + i]
     R->q.count = R->q_count;
     return cudaSuccess;
 }
@@ -507,7 +504,7 @@ void restir_free(RestirBuffers* R) {
         if (R->gi[i]) cudaFree(R->gi[i]);
         if (R->sd[i]) cudaFree(R->sd[i]);
     }
-    void* ptrs[] = {R->cand, R->tmp, R->vmask, R->q.o_tmin, R->q.d_tmax, R->q.pid, R->q_hit, R->q_count};
+    void* ptrs[] = {R->cand, R->tmp, R->vmask, R->q.o_tmin, R->q.d_tmax, R->q.pid, R->q.order, R->q_count};
     for (void* p : ptrs) if (p) cudaFree(p);
     *R = RestirBuffers();
 }
@@ -541,30 +538,35 @@ cudaError_t restir_reuse_passes(RestirBuffers& R, WaveBuffers& B, const SceneDat
                                 cudaStream_t stream, uint64_t* launches) {
     const RsView V = view_of(R);
     const unsigned grid = (R.n + RS_BLOCK - 1) / RS_BLOCK;
-    const unsigned qgrid = (unsigned)(((size_t)R.n * RS_MAX_RAYS_PER_PIXEL + RS_BLOCK - 1) / RS_BLOCK);
     uint64_t L = 0;
-    auto trace_queue = [&](uint32_t* count, unsigned sgrid) -> cudaError_t {
-        CKE(launch_trace(AS, R.q.o_tmin, R.q.d_tmax, count, 0, B.cursor, B.hit_a, R.q_hit, true, nullptr, stream));
-        k_scatter_mask<<<sgrid, RS_BLOCK, 0, stream>>>(count, R.q.pid, R.q_hit, R.vmask, B.ray_counters);
+    const bool lpt = S.heavy_valid != 0u;
+    auto trace_queue = [&](const RayQueue& q) -> cudaError_t {
+        CKE(launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, B.cursor, B.hit_a, B.hit_inst, true, nullptr, stream, 1, q.order, q.n_heavy, q.cap,
+                         q.pid, nullptr, R.vmask));
+        k_count_shadow_rays<<<1, 1, 0, stream>>>(q.count, B.ray_counters);
         L += 2;
         return cudaGetLastError();
     };
-    CKE(cudaMemsetAsync(R.q_count, 0, 4 * 4, stream));
+    auto use_queue = [&](RayQueue& q, int i) {
+        q.count = R.q_count + i; q.n_heavy = R.q_count + 4 + i; q.n_light = R.q_count + 8 + i;
+        q.order = lpt ? R.q.order : nullptr;
+    };
+    CKE(cudaMemsetAsync(R.q_count, 0, 12 * 4, stream));
     CKE(cudaMemsetAsync(R.vmask, 0, (size_t)R.n * 4, stream));
     RayQueue q = R.q;
     // ---- RayGen2
-    q.count = R.q_count + 0;
+    use_queue(q, 0);
     k_temporal_a<<<grid, RS_BLOCK, 0, stream>>>(V, S, B.cam, AS.n_instances, q);
-    CKE(trace_queue(q.count, (unsigned)(((size_t)R.n * 2 + RS_BLOCK - 1) / RS_BLOCK)));
+    CKE(trace_queue(q));
     k_temporal_b<<<grid, RS_BLOCK, 0, stream>>>(V, S, B.cam, AS.n_instances, frame_index);
     // ---- RayGen3
     CKE(cudaMemsetAsync(R.vmask, 0, (size_t)R.n * 4, stream));
-    q.count = R.q_count + 1;
+    use_queue(q, 1);
     k_spatial_a<<<grid, RS_BLOCK, 0, stream>>>(V, S, B.cam, frame_index, q);
-    CKE(trace_queue(q.count, qgrid));
-    q.count = R.q_count + 2;
+    CKE(trace_queue(q));
+    use_queue(q, 2);
     k_spatial_b<<<grid, RS_BLOCK, 0, stream>>>(V, S, q);
-    CKE(trace_queue(q.count, grid));
+    CKE(trace_queue(q));
     k_spatial_c<<<grid, RS_BLOCK, 0, stream>>>(V, B.accum);
     L += 5;
     if (launches) *launches += L;

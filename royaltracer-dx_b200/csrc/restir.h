@@ -20,8 +20,7 @@ struct RestirBuffers {
     float4* tmp = nullptr;                   // 2 planes: (ReconnectDI vector, f_g), (GI contribution, kind)
     uint32_t* vmask = nullptr;               // occlusion bits of the pixel's visibility rays
     RayQueue q;                              // shadow-ray queue, capacity RS_MAX_RAYS_PER_PIXEL * n
-    uint32_t* q_hit = nullptr;
-    uint32_t* q_count = nullptr;             // 4 counters: temporal, spatial A, spatial B
+    uint32_t* q_count = nullptr;             // 12 counters: ray count, heavy rays, other rays of the temporal / spatial A / spatial B queues
 };
 
 cudaError_t restir_alloc(RestirBuffers* R, uint32_t width, uint32_t height);

@@ -46,7 +46,7 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
              const uint32_t* __restrict__ n_ptr, uint32_t n_fixed, unsigned int* __restrict__ cursor,
              float4* __restrict__ hit_a, uint32_t* __restrict__ hit_inst, TraceStats* st, int fetch_th, int sched,
              const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_heavy_ptr, uint32_t cap,
-             const uint32_t* __restrict__ vis_pid, float* __restrict__ vis) {
+             const uint32_t* __restrict__ vis_pid, float* __restrict__ vis, uint32_t* __restrict__ vmask) {
     // trace order (wavefront.h RayQueue): claim k -> slot order[k] (k < n_heavy) or order[cap-1-(k-n_heavy)]: expensive rays first
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
     const uint32_t n_heavy = order ? *n_heavy_ptr : 0u;
@@ -129,6 +129,10 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
                 if (!ANY_HIT) { const float4 h = *C.hit; RTX_ST(hit_a + j, make_float4(T.ht, h.x, h.y, h.z)); } \
                 /* any-hit with a visibility array: an occluded ray clears its path's entry (no scatter kernel) */ \
                 if (ANY_HIT && vis) { if (T.hinst != 0xFFFFFFFFu) vis[__ldg(vis_pid + j)] = 0.0f; }            \
+                /* ... or sets bit (pid & 15) of word pid >> 4 of an occlusion mask (the ReSTIR reuse passes) */   \
+                else if (ANY_HIT && vmask) {                                                                   \
+                    if (T.hinst != 0xFFFFFFFFu) { const uint32_t pid = __ldg(vis_pid + j); atomicOr(&vmask[pid >> 4], 1u << (pid & 15u)); } \
+                }                                                                                              \
                 else RTX_ST(hit_inst + j, T.hinst);                                                            \
             }
             if (pend == PEND_TRI) {
@@ -169,7 +173,7 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
     if (S.n_instances == 0u) {   // empty scene: everything misses
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             if (!ANY_HIT) hit_a[i] = make_float4(__ldg(d_tmax + i).w, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
-            hit_inst[i] = 0xFFFFFFFFu;
+            if (!(ANY_HIT && (vis || vmask))) hit_inst[i] = 0xFFFFFFFFu;
         }
     }
     // the last CTA to finish leaves the cursor at 0 for the next launch (cursor[1] counts finished CTAs and wraps to 0 by itself)
@@ -188,7 +192,7 @@ trace_kernel(SceneAS S, const float4* __restrict__ o_tmin, const float4* __restr
 cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
                          unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
                          cudaStream_t stream, int grid_share, const uint32_t* order, const uint32_t* n_heavy_ptr, uint32_t cap,
-                         const uint32_t* vis_pid, float* vis) {
+                         const uint32_t* vis_pid, float* vis, uint32_t* vmask) {
     // `cursor` = two words, both 0 between launches: [0] the ray cursor, [1] the count of finished CTAs; the last CTA of a launch
     // resets [0] (and atomicInc wraps [1]), so no memset precedes the launch.
     const int sms = S.num_sms > 0 ? S.num_sms : 148;
@@ -198,11 +202,11 @@ cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d
     const int ctas = S.ctas_per_sm > 0 ? min(S.ctas_per_sm, RTX_TRACE_MINB) : RTX_TRACE_MINB;
     const int grid = max(sms, sms * ctas * waves / max(grid_share, 1));
     if (stats) {
-        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
-        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
+        if (any_hit) trace_kernel<true, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis, vmask);
+        else trace_kernel<false, true><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, stats, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis, vmask);
     } else {
-        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
-        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis);
+        if (any_hit) trace_kernel<true, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis, vmask);
+        else trace_kernel<false, false><<<grid, TRACE_BLOCK, 0, stream>>>(S, o_tmin, d_tmax, n_ptr, n_fixed, cursor, hit_a, hit_inst, nullptr, fetch_th, sched, order, n_heavy_ptr, cap, vis_pid, vis, vmask);
     }
     return cudaGetLastError();
 }

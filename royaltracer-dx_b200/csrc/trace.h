@@ -10,10 +10,11 @@ namespace rtx {
 // launches expected to run concurrently (each gets 1/grid_share of the machine's resident CTAs).  order / n_heavy_ptr / cap: the queue's
 // trace order (wavefront.h RayQueue): slot indices, *n_heavy_ptr expensive rays from entry 0 upwards, the others from entry cap-1 downwards.
 // vis_pid / vis (any-hit only): instead of writing hit_inst, an occluded ray j stores 0 to vis[vis_pid[j]] (the wavefront's per-path visibility).
+// vis_pid / vmask (any-hit only): an occluded ray j sets bit (vis_pid[j] & 15) of vmask[vis_pid[j] >> 4] (the occlusion masks of the ReSTIR reuse passes).
 cudaError_t launch_trace(const SceneAS& S, const float4* o_tmin, const float4* d_tmax, const uint32_t* n_ptr, uint32_t n_fixed,
                          unsigned int* cursor, float4* hit_a, uint32_t* hit_inst, bool any_hit, TraceStats* stats,
                          cudaStream_t stream, int grid_share = 1, const uint32_t* order = nullptr, const uint32_t* n_heavy_ptr = nullptr,
-                         uint32_t cap = 0, const uint32_t* vis_pid = nullptr, float* vis = nullptr);
+                         uint32_t cap = 0, const uint32_t* vis_pid = nullptr, float* vis = nullptr, uint32_t* vmask = nullptr);
 
 struct Bvh8 {
     uint4* nodes = nullptr;     // 5 x uint4 per node
