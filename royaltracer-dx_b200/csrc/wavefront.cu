@@ -673,9 +673,10 @@ void wave_free(WaveBuffers* B) {
 // result does not depend on `parts`.
 static int pass_parts(const WaveBuffers& B, const SceneData& S, const PassTiming* T, uint32_t n, bool accumulate) {
     int parts = B.parts < 1 ? 1 : (B.parts > WAVE_MAX_PARTS ? WAVE_MAX_PARTS : B.parts);
-    // per-launch events, the counting traversal variant, the material-binned queues and the ReSTIR frame (which reads the hit records
-    // of the whole frame afterwards) run as one part
-    if (T->stage_timing || T->stats || !accumulate || (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) || n < 65536u) parts = 1;
+    // per-launch events, the counting traversal variant and the material-binned queues run as one part (the ReSTIR frame's first
+    // pass runs in parts too: what it hands to the reuse passes is per-path state, complete once the parts have joined)
+    (void)accumulate;
+    if (T->stage_timing || T->stats || (S.cfg_flags & RTX_FLAG_SORT_MATERIAL) || n < 65536u) parts = 1;
     return parts;
 }
 

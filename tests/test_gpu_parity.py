@@ -271,6 +271,37 @@ def test_restir_moving_camera_and_instances_bit_exact(rtdx, orc):
     _restir_frames(rtdx, orc, sc, 80, 64, 3, 0, [(None, moved(t)) for t in range(3)])
 
 
+def test_restir_frames_in_concurrent_parts(rtdx, orc):
+    """The ReSTIR frame's first pass runs as concurrent path ranges too (>= 65536 paths): reservoirs, ray counts and the accumulation of
+    three frames are bit-identical for 1, 2 and 3 parts, and frame 0 (no history: E0 of the fresh reservoirs) equals the oracle."""
+    sc = rtdx.scenes.mesh_room(n=16)
+    W, H, bounces = 384, 192, 2                                      # 73 728 paths
+    ref = None
+    for parts in (1, 2, 3):
+        ctx, up = _upload(rtdx, sc, W, H, bounces=bounces, flags=rtdx.FLAG_RESTIR)
+        ctx.set_option(rtdx.OPT_PASS_PARTS, parts)
+        ctx.reset_counters()
+        out = []
+        for f in range(3):
+            ctx.render_frame(f); ctx.synchronize()
+            out.append((ctx.read_restir(), ctx.read_accum(), ctx.counters()))
+        if ref is None:
+            ref = out
+            osc = _oracle(orc, sc, up)
+            frames = osc.new_frames(W, H)
+            acc = np.zeros((H, W, 4), dtype=np.float32)
+            octr = osc.render_frame(up["camera"], W, H, 0, frames, acc, bounces=bounces, flags=0)
+            assert (out[0][2]["closest_rays"], out[0][2]["shadow_rays"]) == (octr["closest_rays"], octr["shadow_rays"])
+            assert np.array_equal(bits(out[0][0]), bits(osc.dump_frames(frames, W, H))) and np.array_equal(bits(out[0][1]), bits(acc))
+            osc.free_frames(frames)
+        else:
+            for f in range(3):
+                assert np.array_equal(bits(out[f][0]), bits(ref[f][0])), (parts, f)
+                assert np.array_equal(bits(out[f][1]), bits(ref[f][1])), (parts, f)
+                assert (out[f][2]["closest_rays"], out[f][2]["shadow_rays"]) == (ref[f][2]["closest_rays"], ref[f][2]["shadow_rays"]), (parts, f)
+        ctx.close()
+
+
 def test_material_sorted_queues_do_not_change_the_image(rtdx, orc):
     """RTX_FLAG_SORT_MATERIAL bins every shading queue by hit material before k_gi_step; each path draws its own random numbers,
     so the image, the reservoirs and the ray counts are bit-identical to the unsorted run (and to the oracle)."""
