@@ -97,7 +97,7 @@ def config_dict(cfg, sc, world):
     """Identical in the b200 and the reference arm."""
     return {"workload": workload_name(cfg, sc), "triangles": int(sc.n_triangles()),
             "parallelism": "replicated scene, samples mod %d, one NCCL reduce per pass" % world,
-            "l2": "per-step path state + queues (%.0f MB) exceed the 126 MB L2; no explicit flush" % (cfg["W"] * cfg["H"] * cfg["spp"] * 440 / 1e6),
+            "l2": "per-step path state + queues (%.0f MB) exceed the 126 MB L2; no explicit flush" % (cfg["W"] * cfg["H"] * cfg["spp"] * 468 / 1e6),   # per path: 17 state planes x 16 B + seed 8 + 4 queues x 40 + hit record 20 + visibility 8
             "cpu_sample": "every %d-th pixel in x and y" % cfg["cpu_step"]}
 
 
