@@ -894,6 +894,7 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     else if (option == RTX_OPT_QUEUE_LPT) c->lpt = value != 0;
     else if (option == RTX_OPT_PASS_GRAPH) c->wb.use_graph = value != 0;
     else if (option == RTX_OPT_SHADOW_OVERLAP) c->wb.shadow_overlap = value != 0;
+    else if (option == RTX_OPT_PART_ROWS) { if (value > 64u && value != 0xffffffffu) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PART_ROWS must be 0..64 or 0xffffffff (automatic)"); c->wb.part_rows = value == 0xffffffffu ? -1 : (int)value; }
     else if (option == RTX_OPT_TRACE_CTAS) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_CTAS must be 0..32"); c->ctas_per_sm = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
     return RTX_OK;

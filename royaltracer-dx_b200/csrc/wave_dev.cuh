@@ -31,6 +31,13 @@ struct StateView {
 // queue entries and hit records a shading stage consumes (read once)
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return RTX_STREAM_HINTS ? __ldcs(p) : *p; }
 
+// Which paths a part (path range) of a pass owns: the contiguous range [p0, p0 + np), or — chunk != 0 — every parts-th chunk of `chunk`
+// consecutive paths (a few image rows), so that concurrent parts see the same mix of the image and finish together.  k = index in the part.
+struct PartMap {
+    uint32_t p0, chunk, parts, h;
+    __device__ __forceinline__ uint32_t path(uint32_t k) const { return chunk ? ((k / chunk) * parts + h) * chunk + (k % chunk) : p0 + k; }
+};
+
 __device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 __device__ __forceinline__ float4 f4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ float4 f4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }

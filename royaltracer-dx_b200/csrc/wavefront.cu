@@ -60,7 +60,7 @@ __device__ __forceinline__ void CameraRay(const rtx_camera_params* cam, uint32_t
 }
 
 __global__ void __launch_bounds__(WF_BLOCK)
-k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
+k_generate(StateView st, SceneData S, PartMap pm, uint32_t np, RayQueue q0, const rtx_camera_params* __restrict__ cam, uint32_t W, uint32_t H,
            const uint32_t* __restrict__ first_sample_ptr, uint32_t flags, float* __restrict__ vis_di, float* __restrict__ vis_gi,
            unsigned long long* ray_counters) {
     const uint32_t first_sample = *first_sample_ptr;     // a device word, so that a captured pass (CUDA graph) can be replayed for any sample
@@ -70,7 +70,7 @@ k_generate(StateView st, SceneData S, uint32_t p0, uint32_t np, RayQueue q0, con
     const bool live = k < np;
     f3 o = mk3(0, 0, 0), dir = mk3(0, 0, 1);
     if (live) {
-        const uint32_t p = p0 + k;
+        const uint32_t p = pm.path(k);
         const uint32_t npx = W * H;
         const uint32_t pixel = p % npx, s = p / npx;
         const uint32_t x = pixel % W, y = pixel / W;
@@ -477,12 +477,12 @@ k_gi_step(StateView st, SceneData S, RayQueue qin, const float4* __restrict__ hi
 
 // ---- stage: estimator E0 (Pass_init_di_v7.hlsl:166-181 + Pass_spat_di_v7.hlsl:334-372 with no accepted neighbours)
 __global__ void __launch_bounds__(WF_BLOCK)
-k_finalize(StateView st, uint32_t p0, uint32_t np, SceneData S, const float* __restrict__ vis_di, const float* __restrict__ vis_gi,
+k_finalize(StateView st, PartMap pm, uint32_t np, SceneData S, const float* __restrict__ vis_di, const float* __restrict__ vis_gi,
            const uint32_t* __restrict__ shadow_counts, unsigned long long* ray_counters) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) atomicAdd(&ray_counters[1], (unsigned long long)shadow_counts[0] + (unsigned long long)shadow_counts[1]);
     if (k >= np) return;
-    const uint32_t p = p0 + k;
+    const uint32_t p = pm.path(k);
     const float4 res = st.ld(SP_RESULT, p);
     if (res.w != 1.0f) return;
     const float4 a0 = st.ld(SP_X1, p);
@@ -694,13 +694,24 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
     const int parts = pass_parts(B, S, T, n, accumulate);
 
     struct Part {
-        cudaStream_t stream; uint32_t p0, np; unsigned grid, ggrid;
+        cudaStream_t stream; uint32_t p0, np; PartMap pm; unsigned grid, ggrid;
         uint32_t* counts; unsigned int* cursor; float4* hit_a; uint32_t* hit_inst;
         RayQueue q[2], sdi, sgi, qin, qout;
         int cur;
     } P[WAVE_MAX_PARTS];
     // `ordered` views carry the queue's trace order (wavefront.h RayQueue); the heavy / light counts of queue counter i are counters
     // 128 + i / 256 + i of the part's block
+    // Interleaved parts: chunks of a few image rows dealt round-robin, so that the concurrent parts see the same mix of the image and
+    // finish together (a part that finishes early leaves the other with its 1/parts share of the traversal grid): C2 7.34 -> 7.24 ms,
+    // and three or four parts stop losing (profiles/r02_part_interleave_ab.txt).  B.part_rows: rows per chunk, < 0 = the largest count
+    // <= 32 that divides the frame evenly among the parts, 0 (or no such count) = contiguous ranges.
+    uint32_t chunk = 0u;
+    if (parts > 1 && B.part_rows != 0) {
+        uint32_t rows = 0u;
+        if (B.part_rows > 0) rows = (S.height % ((uint32_t)B.part_rows * (uint32_t)parts)) == 0u ? (uint32_t)B.part_rows : 0u;
+        else for (uint32_t r = 32u; r >= 1u && !rows; r--) if ((S.height % (r * (uint32_t)parts)) == 0u) rows = r;
+        chunk = S.width * rows;
+    }
     const bool lpt = S.heavy_valid != 0u;
     auto view = [lpt](const RayQueue& q, uint32_t off, uint32_t cap, bool ordered) {
         RayQueue v = q; v.o_tmin += off; v.d_tmax += off; v.pid += off; v.cap = cap;
@@ -712,6 +723,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         Part& p = P[h];
         p.stream = h == 0 ? stream : B.aux[h - 1];
         p.p0 = (uint32_t)((uint64_t)n * h / parts); p.np = (uint32_t)((uint64_t)n * (h + 1) / parts) - p.p0;
+        p.pm = PartMap{p.p0, chunk, (uint32_t)parts, (uint32_t)h};
         p.grid = (p.np + WF_BLOCK - 1) / WF_BLOCK; p.ggrid = (p.np + RTX_GI_BLOCK - 1) / RTX_GI_BLOCK;
         p.counts = B.counts + 384 * h; p.cursor = B.cursor + 4 * h;
         p.hit_a = B.hit_a + p.p0; p.hit_inst = B.hit_inst + p.p0;
@@ -752,7 +764,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         if (s == 0) {
             CKE(cudaMemsetAsync(p.counts, 0, 384 * 4, p.stream));
             CKE(mark(SK_GENERATE));
-            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, p.p0, p.np, q0, B.cam, S.width, S.height, B.first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
+            k_generate<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, S, p.pm, p.np, q0, B.cam, S.width, S.height, B.first_sample, S.cfg_flags, B.vis_di, B.vis_gi,
                                                           B.ray_counters);
         } else if (s == 1) {
             CKE(closest(p, q0));
@@ -802,7 +814,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         } else {
             if (side_shadow) CKE(cudaStreamWaitEvent(p.stream, B.ev_sh_join[(int)(&p - P)], 0));
             CKE(mark(SK_FINALIZE));
-            k_finalize<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.p0, p.np, S, B.vis_di, B.vis_gi, p.counts + 2, B.ray_counters);
+            k_finalize<<<p.grid, WF_BLOCK, 0, p.stream>>>(st, p.pm, p.np, S, B.vis_di, B.vis_gi, p.counts + 2, B.ray_counters);
         }
         return cudaSuccess;
     };
@@ -862,7 +874,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     GraphKey key;
     memset(&key, 0, sizeof key);
     memcpy(&key.S, &S, sizeof S); memcpy(&key.AS, &AS, sizeof AS);
-    key.spp = spp; key.parts = parts; key.stream = stream; key.side_shadow = B.shadow_overlap ? 1 : 0;
+    key.spp = spp; key.parts = parts; key.stream = stream; key.side_shadow = (B.shadow_overlap ? 1 : 0) | (B.part_rows << 8);
 #ifdef RTX_FAST_MATH
     key.variant = 1;
 #endif

@@ -554,20 +554,22 @@ def test_tlas_refit_matches_rebuild_and_oracle(rtdx, orc):
 
 
 def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
-    """RTX_OPT_PASS_PARTS: a pass of >= 65536 paths is cut into path ranges that run on separate CUDA streams; ray counts and the
-    accumulated radiance stay bit-identical to the oracle for 1..4 parts (paths never interact before the accumulation)."""
+    """RTX_OPT_PASS_PARTS / RTX_OPT_PART_ROWS: a pass of >= 65536 paths is cut into path ranges (contiguous, or interleaved chunks of image
+    rows) that run on separate CUDA streams; ray counts and the accumulated radiance stay bit-identical to the oracle for 1..4 parts
+    (paths never interact before the accumulation)."""
     sc = rtdx.scenes.mesh_room(n=16)
     W, H, bounces = 384, 192, 3                                                            # 73 728 paths
     ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
     osc = orc.OracleScene(sc, up["props"], up["lights"])
     ref, octr = osc.render(up["camera"], W, H, 0, 1, bounces=bounces, flags=0)
-    for parts in (1, 2, 3, 4):
+    for parts, rows in [(1, 0xffffffff), (2, 0xffffffff), (3, 0xffffffff), (4, 0xffffffff), (2, 0), (3, 0), (4, 0), (2, 1), (3, 4), (4, 12), (3, 5)]:
         ctx.set_option(rtdx.OPT_PASS_PARTS, parts)
+        ctx.set_option(rtdx.OPT_PART_ROWS, rows)       # RTX_OPT_PART_ROWS: interleaved chunks of rows (automatic / contiguous / given / not a divisor)
         ctx.reset_accum(); ctx.reset_counters()
         ctx.render_pass(0, 1); ctx.synchronize()
         cnt = ctx.counters()
-        assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (parts, cnt, octr)
-        assert (bits(ctx.read_accum()) != bits(ref)).sum() == 0, parts
+        assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (parts, rows, cnt, octr)
+        assert (bits(ctx.read_accum()) != bits(ref)).sum() == 0, (parts, rows)
     ctx.close()
 
 
