@@ -571,6 +571,18 @@ def test_concurrent_pass_parts_match_the_oracle(rtdx, orc):
         assert cnt["closest_rays"] == octr["closest_rays"] and cnt["shadow_rays"] == octr["shadow_rays"], (parts, rows, cnt, octr)
         assert (bits(ctx.read_accum()) != bits(ref)).sum() == 0, (parts, rows)
     ctx.close()
+    # several samples per pass: the paths of a pass are (sample, pixel) pairs, the chunks are cut in that space
+    W2, H2, spp = 192, 96, 4                                                               # 73 728 paths again
+    ctx, up = _upload(rtdx, sc, W2, H2, bounces=bounces, samples_per_pass=spp)
+    ref2, octr2 = osc.render(up["camera"], W2, H2, 0, spp, bounces=bounces, flags=0)
+    for parts, rows in [(1, 0xffffffff), (2, 0xffffffff), (3, 0xffffffff), (2, 0), (4, 3)]:
+        ctx.set_option(rtdx.OPT_PASS_PARTS, parts); ctx.set_option(rtdx.OPT_PART_ROWS, rows)
+        ctx.reset_accum(); ctx.reset_counters()
+        ctx.render_pass(0, spp); ctx.synchronize()
+        cnt = ctx.counters()
+        assert cnt["closest_rays"] == octr2["closest_rays"] and cnt["shadow_rays"] == octr2["shadow_rays"], (parts, rows, cnt, octr2)
+        assert (bits(ctx.read_accum()) != bits(ref2)).sum() == 0, (parts, rows)
+    ctx.close()
 
 
 def test_graph_replay_and_trace_order_do_not_change_the_image(rtdx, orc):
