@@ -857,11 +857,8 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         if (!B.ev_sh_fork[h]) CKE(cudaEventCreateWithFlags(&B.ev_sh_fork[h], cudaEventDisableTiming));
         if (!B.ev_sh_join[h]) CKE(cudaEventCreateWithFlags(&B.ev_sh_join[h], cudaEventDisableTiming));
     }
-    static bool smem_opt_in = false;       // 72 KB of dynamic shared memory per CTA: above the 48 KB a kernel gets without asking
-    if (RTX_GI_STAGE && !smem_opt_in) {
-        CKE(cudaFuncSetAttribute(k_gi_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GI_STAGED * RTX_GI_BLOCK * sizeof(float4))));
-        smem_opt_in = true;
-    }
+    // (the staged planes of k_gi_step take 24 KB of dynamic shared memory per CTA: below the 48 KB a kernel gets without opting in)
+    static_assert(GI_STAGED * RTX_GI_BLOCK * sizeof(float4) <= 48 * 1024, "k_gi_step's staging area needs cudaFuncAttributeMaxDynamicSharedMemorySize");
     k_set_word<<<1, 1, 0, stream>>>(B.first_sample, first_sample);
     if (launches) *launches += 1;
 
