@@ -68,9 +68,31 @@ struct rtx_ctx {
     PassTiming timing;
     bool trace_stats = false;
     bool pass_timed = false;
+    // Pipelined passes (RTX_OPT_PASS_PIPELINE): rtx_render_pass calls that follow each other with no other call in between alternate
+    // between two sets of pass buffers ("lanes": wb and wb2) on two private streams, each pass as ONE path range, so that the start and
+    // the tail of a pass overlap the middle of the other one.  gPermanentData is shared: the k_accumulate launches are chained through
+    // ev_acc in call order, so the sums are bit-identical to passes run one after the other.  The API stays stream-ordered: a lane
+    // starts behind ev_state (whatever other entry points queued on the caller's stream), and the caller's stream is made to wait for
+    // every pass's accumulation (no host wait).  The first pass after any other call runs as before (B.parts path ranges on the
+    // caller's stream).
+    WaveBuffers wb2; bool wb2_ready = false, wb2_refused = false;
+    cudaStream_t lane_stream[2] = {nullptr, nullptr}; cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_state = nullptr;
+    PassTiming timing2;
+    bool pipeline = true, in_sequence = false, main_dirty = true, reduce_pending = false;
+    int last_lane = 0;
 };
 
 static rtx_status fail(rtx_status code, const char* msg) { set_error(msg); return code; }
+
+// Every entry point except rtx_render_pass and rtx_reduce_accum starts here: the device is made current, and a sequence of pipelined
+// passes ends (the caller's stream already waits for every pass queued so far; what this call queues there is ordered before the
+// passes that follow through ev_state).
+static rtx_status enter(rtx_ctx* c) {
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    c->in_sequence = false; c->main_dirty = true;
+    return RTX_OK;
+}
+#define RTX_ENTER(c) do { const rtx_status e__ = enter(c); if (e__ != RTX_OK) return e__; } while (0)
 
 extern "C" const char* rtx_last_error(void) { return g_err.c_str(); }
 
@@ -80,6 +102,10 @@ static rtx_status create_resources(rtx_ctx* c) {
     if (c->cfg.stream) c->stream = (cudaStream_t)c->cfg.stream;
     else { RTX_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) RTX_CK(cudaEventCreate(&c->timing.ev[i]));
+    for (int i = 0; i < 2; i++) RTX_CK(cudaEventCreate(&c->timing2.ev[i]));
+    for (int i = 0; i < 2; i++) RTX_CK(cudaEventCreateWithFlags(&c->ev_acc[i], cudaEventDisableTiming));
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) RTX_CK(cudaStreamCreateWithFlags(&c->lane_stream[i], cudaStreamNonBlocking));
     RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
     RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
     RTX_CK(cudaMalloc((void**)&c->d_overflow, sizeof(unsigned int)));
@@ -125,6 +151,7 @@ static void free_tables(rtx_ctx* c) {
 extern "C" void rtx_destroy(rtx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
+    for (int i = 0; i < 2; i++) if (c->lane_stream[i]) cudaStreamSynchronize(c->lane_stream[i]);
     if (c->stream) cudaStreamSynchronize(c->stream);
     rtx_comm_destroy(c);
     for (auto& m : c->models) { if (m.d_verts) cudaFree(m.d_verts); if (m.d_idx) cudaFree(m.d_idx); if (m.d_shade) cudaFree(m.d_shade); free_bvh(&m.bvh); }
@@ -140,9 +167,13 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     for (auto& sg : c->stage) { if (sg.p) cudaFreeHost(sg.p); if (sg.ev) cudaEventDestroy(sg.ev); }
     { void* q[] = {c->d_box_lo, c->d_box_hi, c->d_tlas_ctr, c->d_box6}; for (void* p : q) if (p) cudaFree(p); }
+    if (c->wb2_ready) wave_free_lane(&c->wb2);
     if (c->wb_ready) wave_free(&c->wb);
     if (c->rs_ready) restir_free(&c->rs);
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
+    for (int i = 0; i < 2; i++) { if (c->timing2.ev[i]) cudaEventDestroy(c->timing2.ev[i]); if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); }
+    if (c->ev_state) cudaEventDestroy(c->ev_state);
+    for (int i = 0; i < 2; i++) if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -181,7 +212,7 @@ extern "C" rtx_status rtx_upload_model(rtx_ctx* c, const rtx_vertex* v, uint32_t
     if (!c || (!v && nv) || (!idx && ni)) return fail(RTX_ERR_ARG, "rtx_upload_model: null argument");
     if (ni % 3) return fail(RTX_ERR_ARG, "rtx_upload_model: index count is not a multiple of 3");
     for (uint32_t i = 0; i < ni; i++) if (idx[i] >= nv) return fail(RTX_ERR_ARG, "rtx_upload_model: index out of range");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     ModelRec m;
     m.n_verts = nv; m.n_tris = ni / 3; m.mat_offset = material_id_offset;
     rtx_status st;
@@ -212,14 +243,14 @@ extern "C" rtx_status rtx_blas_info_get(rtx_ctx* c, uint32_t model_id, rtx_blas_
 
 extern "C" rtx_status rtx_set_material_ids(rtx_ctx* c, const uint32_t* ids, uint32_t n) {
     if (!c || (!ids && n)) return fail(RTX_ERR_ARG, "rtx_set_material_ids: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     c->n_material_ids = n;
     return upload(&c->d_material_ids, ids, n, c->stream, &c->cap_material_ids);
 }
 
 extern "C" rtx_status rtx_set_materials(rtx_ctx* c, const rtx_material* m, uint32_t n) {
     if (!c || (!m && n)) return fail(RTX_ERR_ARG, "rtx_set_materials: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     c->n_materials = n;
     return upload(&c->d_materials, m, n, c->stream, &c->cap_materials);
 }
@@ -257,7 +288,7 @@ static rtx_status reserve(T** dptr, size_t* cap, size_t n) {
 
 extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* descs, const rtx_instance_props* props, uint32_t n) {
     if (!c || ((!descs || !props) && n)) return fail(RTX_ERR_ARG, "rtx_set_instances: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     for (uint32_t i = 0; i < n; i++) {
         if (descs[i].blas >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_set_instances: instance references an unknown model");
         if (c->models[descs[i].blas].n_tris == 0) return fail(RTX_ERR_ARG, "rtx_set_instances: instance of an empty model");
@@ -362,7 +393,7 @@ extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* des
 
 extern "C" rtx_status rtx_set_emissive_triangles(rtx_ctx* c, const rtx_light_triangle* l, uint32_t n) {
     if (!c || (!l && n)) return fail(RTX_ERR_ARG, "rtx_set_emissive_triangles: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     c->n_lights = n;
     if (n == 0) {   // an out-of-bounds read of t6 returns zeros: keep one zero record
         rtx_light_triangle z; memset(&z, 0, sizeof z);
@@ -380,7 +411,7 @@ static rtx_status ensure_wave(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
     if (!c || !cam) return fail(RTX_ERR_ARG, "rtx_set_camera: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     // Pass_spat_di_v7.hlsl:407-423: any element of view differing from the previous view by more than s_bias resets the accumulation
@@ -420,6 +451,23 @@ static rtx_status check_overflow(rtx_ctx* c) {
     return RTX_OK;
 }
 
+// the second set of pass buffers, allocated when first needed and only if it takes less than a quarter of the free device memory
+static bool lane_buffers(rtx_ctx* c) {
+    if (c->wb2_ready) return true;
+    if (c->wb2_refused || !c->wb_ready) return false;
+    size_t free_b = 0, total_b = 0;
+    const size_t need = (size_t)c->wb.n_paths * 480u;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > free_b / 4) { c->wb2_refused = true; return false; }
+    c->wb2 = WaveBuffers();
+    if (wave_alloc_lane(&c->wb2, c->wb, c->cfg.width, c->cfg.height, c->cfg.samples_per_pass) != cudaSuccess) {
+        cudaGetLastError();
+        wave_free_lane(&c->wb2); c->wb2_refused = true;
+        return false;
+    }
+    c->wb2_ready = true;
+    return true;
+}
+
 extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_t n_samples) {
     if (!c) return fail(RTX_ERR_ARG, "rtx_render_pass: null context");
     if (!c->have_cam) return fail(RTX_ERR_STATE, "rtx_render_pass: camera not set");
@@ -440,13 +488,48 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
     for (int r = 0; r < 3; r++) { S.heavy_lo[r] = c->heavy_lo[r]; S.heavy_hi[r] = c->heavy_hi[r]; }
     S.heavy_valid = c->heavy_valid && c->lpt ? 1u : 0u;
     const SceneAS AS = make_as(c);
+    const uint32_t npx = c->cfg.width * c->cfg.height;
+    // pipelined passes (see rtx_ctx): the estimator E0 without per-launch instrumentation, frames large enough to be cut into path ranges
+    const bool eligible = c->pipeline && !(c->cfg.flags & (RTX_FLAG_LEGACY_RR | RTX_FLAG_RESTIR | RTX_FLAG_SORT_MATERIAL)) &&
+                          !c->timing.stage_timing && !c->trace_stats && (uint64_t)npx * c->cfg.samples_per_pass >= 65536u && lane_buffers(c);
     uint32_t done = 0;
     while (done < n_samples) {
         const uint32_t spp = std::min(c->cfg.samples_per_pass, n_samples - done);
         c->timing.stats = c->trace_stats ? c->d_stats : nullptr;
-        if (c->cfg.flags & RTX_FLAG_LEGACY_RR) RTX_CK(wave_render_pass_legacy(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
-        else if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
-        else RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
+        // whatever other entry points queued on the caller's stream (camera, instances, uploads, clears) is ordered before the passes of
+        // both lanes through ev_state, recorded BEFORE this pass is queued (a lane never waits for the other lane's pass)
+        if (c->main_dirty) { RTX_CK(cudaEventRecord(c->ev_state, c->stream)); c->main_dirty = false; }
+        if (!(eligible && c->in_sequence)) {
+            // the first pass after any other call: B.parts path ranges on the caller's stream, accumulation included
+            if (c->cfg.flags & RTX_FLAG_LEGACY_RR) RTX_CK(wave_render_pass_legacy(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
+            else if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
+            else RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
+            RTX_CK(cudaEventRecord(c->ev_acc[0], c->stream));
+            c->last_lane = 0;
+        } else {
+            // a pass that directly follows another: the other lane, one path range, its accumulation behind the previous pass's
+            const int lane = 1 - c->last_lane;
+            WaveBuffers& B = lane ? c->wb2 : c->wb;
+            PassTiming& T = lane ? c->timing2 : c->timing;
+            const cudaStream_t st_ = c->lane_stream[lane];
+            RTX_CK(cudaStreamWaitEvent(st_, c->ev_state, 0));
+            RTX_CK(cudaStreamWaitEvent(st_, c->ev_acc[lane], 0));           // the previous pass in these buffers (it may have run on the caller's stream)
+            if (lane) {
+                B.shadow_overlap = c->wb.shadow_overlap; B.part_rows = c->wb.part_rows;
+                if (!c->wb.use_graph) B.use_graph = false;
+                T.stage_timing = false; T.stats = nullptr;
+            }
+            if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(B, S, AS, first_sample + done, spp, st_, &c->launches, &T, true, 1, true));
+            else RTX_CK(wave_render_pass(B, S, AS, first_sample + done, spp, st_, &c->launches, &T, true, 1, true));
+            RTX_CK(cudaStreamWaitEvent(st_, c->ev_acc[1 - lane], 0));                         // gPermanentData += in call order
+            if (c->reduce_pending) RTX_CK(cudaStreamWaitEvent(st_, c->ev_reduced, 0));        // a pending multi-GPU reduce still reads it
+            RTX_CK(wave_accumulate(B, npx, spp, st_));
+            c->launches += 1;
+            RTX_CK(cudaEventRecord(c->ev_acc[lane], st_));
+            RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_acc[lane], 0));     // stream-ordered API: the caller's stream sees the pass as done
+            c->last_lane = lane;
+        }
+        c->in_sequence = true;
         done += spp;
     }
     c->pass_timed = true;
@@ -468,7 +551,7 @@ extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
     if (!c->have_cam) return fail(RTX_ERR_STATE, "rtx_render_frame: camera not set");
     if (!c->n_instances || !c->tlas.nodes) return fail(RTX_ERR_STATE, "rtx_render_frame: no instances");
     if (!c->d_materials || !c->d_material_ids) return fail(RTX_ERR_STATE, "rtx_render_frame: materials not set");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if (!c->d_lights && (st = rtx_set_emissive_triangles(c, nullptr, 0)) != RTX_OK) return st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
@@ -495,7 +578,7 @@ extern "C" rtx_status rtx_render_frame(rtx_ctx* c, uint32_t frame_index) {
 
 extern "C" rtx_status rtx_reset_restir(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_restir(c)) != RTX_OK) return st;
     RTX_CK(restir_clear(c->rs, c->stream));
@@ -504,7 +587,7 @@ extern "C" rtx_status rtx_reset_restir(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_read_restir(rtx_ctx* c, float* out) {
     if (!c || !out) return fail(RTX_ERR_ARG, "rtx_read_restir: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_restir(c)) != RTX_OK) return st;
     RTX_CK(restir_dump(c->rs, c->stream, out));
@@ -513,7 +596,7 @@ extern "C" rtx_status rtx_read_restir(rtx_ctx* c, float* out) {
 
 extern "C" rtx_status rtx_reset_accum(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
@@ -522,14 +605,14 @@ extern "C" rtx_status rtx_reset_accum(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_synchronize(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     RTX_CK(cudaStreamSynchronize(c->stream));
     return check_overflow(c);
 }
 
 extern "C" rtx_status rtx_read_accum(rtx_ctx* c, float* host_out) {
     if (!c || !host_out) return fail(RTX_ERR_ARG, "rtx_read_accum: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     RTX_CK(cudaMemcpyAsync(host_out, c->wb.accum, (size_t)c->cfg.width * c->cfg.height * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -539,7 +622,7 @@ extern "C" rtx_status rtx_read_accum(rtx_ctx* c, float* host_out) {
 
 extern "C" rtx_status rtx_read_output(rtx_ctx* c, uint8_t* rgba8_out) {
     if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     const uint32_t npx = c->cfg.width * c->cfg.height;
@@ -564,7 +647,7 @@ static rtx_status ensure_side_stream(rtx_ctx* c) {
 // reduce: the render stream never waits for NCCL, the next pass overlaps reduce + resolve + copy.
 extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
     if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output_async: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     if ((st = ensure_side_stream(c)) != RTX_OK) return st;
@@ -589,7 +672,7 @@ extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
 // per-pass ncclReduce) instead of this context's private partial sum.  nullptr restores the context's own buffer.
 extern "C" rtx_status rtx_set_resolve_source(rtx_ctx* c, const void* d_accum_float4) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     c->wb.resolve_source = (const float4*)d_accum_float4;
@@ -613,7 +696,7 @@ extern "C" rtx_status rtx_wait_output(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_accum_device_ptr(rtx_ctx* c, void** out) {
     if (!c || !out) return fail(RTX_ERR_ARG, "rtx_accum_device_ptr: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     *out = c->wb.accum;
@@ -658,7 +741,7 @@ static rtx_status trace_device_impl(rtx_ctx* c, const void* d_rays, uint32_t n, 
     if (!c || (!d_rays && n) || (!d_hits && n)) return fail(RTX_ERR_ARG, "rtx_trace: null argument");
     if (!c->n_instances || !c->tlas.nodes) return fail(RTX_ERR_STATE, "rtx_trace: no instances");
     if (n == 0) return RTX_OK;
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_trace_cap(c, n)) != RTX_OK) return st;
     static_assert(sizeof(rtx_ray) == 32, "rtx_ray must be 32 bytes");
@@ -684,7 +767,7 @@ extern "C" rtx_status rtx_trace_stats(rtx_ctx* c, const void* d_rays, uint32_t n
 extern "C" rtx_status rtx_trace(rtx_ctx* c, const rtx_ray* rays, uint32_t n, rtx_hit* out, int any_hit) {
     if (!c || (!rays && n) || (!out && n)) return fail(RTX_ERR_ARG, "rtx_trace: null argument");
     if (n == 0) return RTX_OK;
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status rs;       // staging buffers are kept between calls and only grow
     if ((rs = reserve((uint8_t**)&c->d_trace_rays, &c->cap_trace_rays, (size_t)n * sizeof(rtx_ray))) != RTX_OK) return rs;
     if ((rs = reserve((uint8_t**)&c->d_trace_hits, &c->cap_trace_hits, (size_t)n * sizeof(rtx_hit))) != RTX_OK) return rs;
@@ -757,6 +840,7 @@ extern "C" rtx_status rtx_comm_destroy(rtx_ctx* c) {
     nccl().CommDestroy(c->comm);
     c->comm = nullptr; c->comm_world = 1; c->comm_rank = 0;
     if (c->wb_ready) { if (c->wb.resolve_source == c->d_total) c->wb.resolve_source = nullptr; c->wb.wait_before_accumulate = nullptr; }
+    c->reduce_pending = false;
     if (c->d_total) { cudaFree(c->d_total); c->d_total = nullptr; }
     if (c->ev_pass) { cudaEventDestroy(c->ev_pass); c->ev_pass = nullptr; }
     if (c->ev_reduced) { cudaEventDestroy(c->ev_reduced); c->ev_reduced = nullptr; }
@@ -770,7 +854,7 @@ extern "C" rtx_status rtx_comm_init(rtx_ctx* c, const void* unique_id128, int ra
     if (c->comm) return fail(RTX_ERR_STATE, "rtx_comm_init: the context already has a communicator");
     NcclApi& n = nccl();
     if (!n.ok) return fail(RTX_ERR_STATE, n.err.c_str());
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     if ((st = ensure_side_stream(c)) != RTX_OK) return st;
@@ -796,6 +880,7 @@ extern "C" rtx_status rtx_reduce_accum(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
     if (!c->comm) return fail(RTX_ERR_STATE, "rtx_reduce_accum: no communicator (rtx_comm_init)");
     RTX_CK(cudaSetDevice(c->cfg.device));
+    // (not through enter(): a reduce between two passes does not end a pipelined sequence; the caller's stream is behind every pass)
     RTX_CK(cudaEventRecord(c->ev_pass, c->stream));
     RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_pass, 0));
     const size_t count = (size_t)c->cfg.width * c->cfg.height * 4;
@@ -804,6 +889,7 @@ extern "C" rtx_status rtx_reduce_accum(rtx_ctx* c) {
     if (r != 0) return nccl_fail("ncclReduce", r);
     RTX_CK(cudaEventRecord(c->ev_reduced, c->copy_stream));
     c->wb.wait_before_accumulate = c->ev_reduced;
+    c->reduce_pending = true;
     return RTX_OK;
 }
 
@@ -819,13 +905,17 @@ extern "C" rtx_status rtx_read_reduced_accum(rtx_ctx* c, float* host_out) {
 
 extern "C" rtx_status rtx_get_counters(rtx_ctx* c, rtx_counters* out) {
     if (!c || !out) return fail(RTX_ERR_ARG, "rtx_get_counters: null argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     memset(out, 0, sizeof *out);
     RTX_CK(cudaStreamSynchronize(c->stream));
     if (c->wb_ready) {
         unsigned long long h[8];
         RTX_CK(cudaMemcpy(h, c->wb.ray_counters, sizeof h, cudaMemcpyDeviceToHost));
         out->closest_rays = h[0]; out->shadow_rays = h[1]; out->paths = h[2];
+        if (c->wb2_ready) {
+            RTX_CK(cudaMemcpy(h, c->wb2.ray_counters, sizeof h, cudaMemcpyDeviceToHost));
+            out->closest_rays += h[0]; out->shadow_rays += h[1]; out->paths += h[2];
+        }
     }
     TraceStats ts;
     RTX_CK(cudaMemcpy(&ts, c->d_stats, sizeof ts, cudaMemcpyDeviceToHost));
@@ -836,9 +926,10 @@ extern "C" rtx_status rtx_get_counters(rtx_ctx* c, rtx_counters* out) {
 
 extern "C" rtx_status rtx_reset_counters(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     RTX_CK(cudaStreamSynchronize(c->stream));
     if (c->wb_ready) RTX_CK(cudaMemset(c->wb.ray_counters, 0, 64));
+    if (c->wb2_ready) RTX_CK(cudaMemset(c->wb2.ray_counters, 0, 64));
     RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
     c->launches = 0;
     return RTX_OK;
@@ -847,9 +938,14 @@ extern "C" rtx_status rtx_reset_counters(rtx_ctx* c) {
 static rtx_status stage_ms(rtx_ctx* c, float* by_kind, float* total) {
     if (!c->pass_timed) return fail(RTX_ERR_STATE, "rtx_last_pass_ms: no pass rendered yet");
     RTX_CK(cudaSetDevice(c->cfg.device));
+    for (int k = 0; k < SK_COUNT; k++) by_kind[k] = 0.0f;
+    if (c->last_lane == 1) {        // the last pass ran on the second lane (pipelined passes carry no per-launch events)
+        RTX_CK(cudaEventSynchronize(c->timing2.ev[1]));
+        RTX_CK(cudaEventElapsedTime(total, c->timing2.ev[0], c->timing2.ev[1]));
+        return RTX_OK;
+    }
     RTX_CK(cudaEventSynchronize(c->timing.ev[1]));
     RTX_CK(cudaEventElapsedTime(total, c->timing.ev[0], c->timing.ev[1]));
-    for (int k = 0; k < SK_COUNT; k++) by_kind[k] = 0.0f;
     for (int i = 0; i < c->timing.n_marks; i++) {
         float d = 0.0f;
         cudaEvent_t next = (i + 1 < c->timing.n_marks) ? c->timing.ev[3 + i] : c->timing.ev[1];
@@ -881,6 +977,7 @@ extern "C" rtx_status rtx_last_pass_stage_ms(rtx_ctx* c, float* ms_by_stage, uin
 
 extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
+    RTX_ENTER(c);
     if (option == RTX_OPT_TRACE_STATS) c->trace_stats = value != 0;
     else if (option == RTX_OPT_STAGE_TIMING) c->timing.stage_timing = value != 0;
     else if (option == RTX_OPT_TLAS_REBUILD) c->force_tlas_rebuild = value != 0;
@@ -892,8 +989,9 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     else if (option == RTX_OPT_TRACE_SCHED) c->sched = (int)(value & 0xffffffu);
     else if (option == RTX_OPT_TRACE_WAVES) { if (value > 8u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_WAVES must be 0..8"); c->waves = (int)value; }
     else if (option == RTX_OPT_QUEUE_LPT) c->lpt = value != 0;
-    else if (option == RTX_OPT_PASS_GRAPH) c->wb.use_graph = value != 0;
+    else if (option == RTX_OPT_PASS_GRAPH) { c->wb.use_graph = value != 0; c->wb2.use_graph = value != 0; }
     else if (option == RTX_OPT_SHADOW_OVERLAP) c->wb.shadow_overlap = value != 0;
+    else if (option == RTX_OPT_PASS_PIPELINE) c->pipeline = value != 0;
     else if (option == RTX_OPT_PART_ROWS) { if (value > 64u && value != 0xffffffffu) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PART_ROWS must be 0..64 or 0xffffffff (automatic)"); c->wb.part_rows = value == 0xffffffffu ? -1 : (int)value; }
     else if (option == RTX_OPT_TRACE_CTAS) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_CTAS must be 0..32"); c->ctas_per_sm = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");
@@ -902,7 +1000,7 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
 
 extern "C" rtx_status rtx_selftest_dmath(rtx_ctx* c, uint64_t* out, uint32_t n_out) {
     if (!c || !out || n_out == 0) return fail(RTX_ERR_ARG, "rtx_selftest_dmath: bad argument");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     unsigned long long h[8] = {0};
     RTX_CK(wave_selftest_dmath(c->stream, h, 8));
     for (uint32_t i = 0; i < n_out; i++) out[i] = i < 8 ? (uint64_t)h[i] : 0;
@@ -912,7 +1010,7 @@ extern "C" rtx_status rtx_selftest_dmath(rtx_ctx* c, uint64_t* out, uint32_t n_o
 extern "C" rtx_status rtx_debug_pixel(rtx_ctx* c, uint32_t x, uint32_t y, float* out64) {
     if (!c || !out64 || !c->wb_ready) return fail(RTX_ERR_ARG, "rtx_debug_pixel: bad argument");
     if (x >= c->cfg.width || y >= c->cfg.height) return fail(RTX_ERR_ARG, "rtx_debug_pixel: pixel out of range");
-    RTX_CK(cudaSetDevice(c->cfg.device));
+    RTX_ENTER(c);
     SceneData S; memset(&S, 0, sizeof S); S.width = c->cfg.width; S.height = c->cfg.height;
     RTX_CK(wave_debug_pixel(c->wb, S, x, y, c->stream, out64));
     return RTX_OK;

@@ -618,7 +618,7 @@ static void free_queue(RayQueue* q) {
     q->o_tmin = q->d_tmax = nullptr; q->pid = nullptr; q->order = nullptr;
 }
 
-cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp) {
+static cudaError_t wave_alloc_impl(WaveBuffers* B, const WaveBuffers* shared, uint32_t width, uint32_t height, uint32_t spp) {
     const uint32_t npx = width * height;
     const uint32_t n = npx * spp;
     B->n_paths = n;
@@ -635,16 +635,28 @@ cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t
     CKE(cudaMemset(B->cursor, 0, WAVE_MAX_PARTS * 16));      // launch_trace keeps the cursor words at zero between launches
     CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
     CKE(cudaMemset(B->ray_counters, 0, 64));
-    CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
-    CKE(cudaMemset(B->accum, 0, (size_t)npx * 16));
-    CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
-    CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
+    if (shared) { B->accum = shared->accum; B->output = shared->output; B->cam = shared->cam; }
+    else {
+        CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
+        CKE(cudaMemset(B->accum, 0, (size_t)npx * 16));
+        CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
+        CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
+    }
     CKE(cudaMalloc((void**)&B->first_sample, 4));
     CKE(cudaMalloc((void**)&B->debug, 64 * 4));
     CKE(cudaMalloc((void**)&B->perm, (size_t)n * 4));
     CKE(cudaMalloc((void**)&B->bin_keys, (size_t)n));
     CKE(cudaMalloc((void**)&B->bins, 2 * WF_NBIN * 4));
     return cudaSuccess;
+}
+
+cudaError_t wave_alloc(WaveBuffers* B, uint32_t width, uint32_t height, uint32_t spp) { return wave_alloc_impl(B, nullptr, width, height, spp); }
+cudaError_t wave_alloc_lane(WaveBuffers* L, const WaveBuffers& B, uint32_t width, uint32_t height, uint32_t spp) {
+    return wave_alloc_impl(L, &B, width, height, spp);
+}
+void wave_free_lane(WaveBuffers* L) {
+    L->accum = nullptr; L->output = nullptr; L->cam = nullptr;       // owned by the context's first set
+    wave_free(L);
 }
 
 void wave_free(WaveBuffers* B) {
@@ -671,8 +683,9 @@ void wave_free(WaveBuffers* B) {
 // every persistent traversal launch ends in a tail in which a few warps finish the longest rays on an otherwise empty GPU (0.14 ms of a
 // 0.43 ms launch at 1080p, profiles/r01_s4_*), and the other parts' kernels fill it.  Paths never interact before the accumulation, so the
 // result does not depend on `parts`.
-static int pass_parts(const WaveBuffers& B, const SceneData& S, const PassTiming* T, uint32_t n, bool accumulate) {
-    int parts = B.parts < 1 ? 1 : (B.parts > WAVE_MAX_PARTS ? WAVE_MAX_PARTS : B.parts);
+static int pass_parts(const WaveBuffers& B, const SceneData& S, const PassTiming* T, uint32_t n, bool accumulate, int parts_override) {
+    int parts = parts_override > 0 ? parts_override : B.parts;
+    parts = parts < 1 ? 1 : (parts > WAVE_MAX_PARTS ? WAVE_MAX_PARTS : parts);
     // per-launch events, the counting traversal variant and the material-binned queues run as one part (the ReSTIR frame's first
     // pass runs in parts too: what it hands to the reuse passes is per-path state, complete once the parts have joined)
     (void)accumulate;
@@ -685,13 +698,13 @@ __global__ void k_set_word(uint32_t* p, uint32_t v) { *p = v; }
 // the launches of one pass on `stream` (+ the auxiliary streams); the sample index comes from B.first_sample, so the same sequence serves
 // every pass of a static configuration: wave_render_pass captures it into a CUDA graph
 static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t spp, cudaStream_t stream, uint64_t* launches,
-                                  PassTiming* T, bool accumulate) {
+                                  PassTiming* T, bool accumulate, int parts_override, bool defer_accumulate) {
     const uint32_t npx = S.width * S.height;
     const uint32_t n = npx * spp;
     StateView st{B.state, n, B.seeds};
     uint64_t L = 0;
     T->n_marks = 0;
-    const int parts = pass_parts(B, S, T, n, accumulate);
+    const int parts = pass_parts(B, S, T, n, accumulate, parts_override);
 
     struct Part {
         cudaStream_t stream; uint32_t p0, np; PartMap pm; unsigned grid, ggrid;
@@ -828,7 +841,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         CKE(cudaEventRecord(B.ev_join[h - 1], P[h].stream));
         CKE(cudaStreamWaitEvent(stream, B.ev_join[h - 1], 0));
     }
-    if (accumulate) {       // E0: the pass's samples go straight to gPermanentData; the ReSTIR frame accumulates after RayGen3
+    if (accumulate && !defer_accumulate) {       // E0: the pass's samples go straight to gPermanentData; the ReSTIR frame accumulates after RayGen3
         if (B.wait_before_accumulate) CKE(cudaStreamWaitEvent(stream, B.wait_before_accumulate, 0));
         CKE(mark(SK_ACCUMULATE));
         k_accumulate<<<(npx + WF_BLOCK - 1) / WF_BLOCK, WF_BLOCK, 0, stream>>>(st, npx, spp, B.accum);
@@ -843,10 +856,10 @@ struct GraphKey { SceneData S; SceneAS AS; uint32_t spp; int parts; int variant;
 static_assert(sizeof(GraphKey) <= sizeof(WaveBuffers().graph_key), "WaveBuffers::graph_key too small");
 
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
-                             uint64_t* launches, PassTiming* T, bool accumulate) {
+                             uint64_t* launches, PassTiming* T, bool accumulate, int parts_override, bool defer_accumulate) {
     const uint32_t n = S.width * S.height * spp;
     if (n > B.n_paths) return cudaErrorInvalidValue;
-    const int parts = pass_parts(B, S, T, n, accumulate);
+    const int parts = pass_parts(B, S, T, n, accumulate, parts_override);
     for (int h = 1; h < parts; h++) {       // (never inside a capture)
         if (!B.aux[h - 1]) CKE(cudaStreamCreateWithFlags(&B.aux[h - 1], cudaStreamNonBlocking));
         if (!B.ev_join[h - 1]) CKE(cudaEventCreateWithFlags(&B.ev_join[h - 1], cudaEventDisableTiming));
@@ -867,7 +880,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     // replayed: one graph launch per pass instead of ~100 stream operations.  The first pass of a new configuration runs directly, the
     // second one captures (a scene whose instances move every frame never pays for captures).  Passes with per-launch events, the
     // counting variant, the ReSTIR frame or a pending multi-GPU reduce (an event from outside the capture) always run directly.
-    const bool graph_ok = B.use_graph && accumulate && !T->stage_timing && !T->stats && !B.wait_before_accumulate;
+    const bool graph_ok = B.use_graph && accumulate && !T->stage_timing && !T->stats && (defer_accumulate || !B.wait_before_accumulate);
     GraphKey key;
     memset(&key, 0, sizeof key);
     memcpy(&key.S, &S, sizeof S); memcpy(&key.AS, &AS, sizeof AS);
@@ -875,6 +888,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
 #ifdef RTX_FAST_MATH
     key.variant = 1;
 #endif
+    if (defer_accumulate) key.variant |= 2;
     CKE(cudaEventRecord(T->ev[0], stream));
     bool done = false;
     if (graph_ok) {
@@ -886,7 +900,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
             uint64_t L = 0;
             cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
             if (e == cudaSuccess) {
-                e = wave_pass_body(B, S, AS, spp, stream, &L, T, accumulate);
+                e = wave_pass_body(B, S, AS, spp, stream, &L, T, accumulate, parts_override, defer_accumulate);
                 const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
                 if (e == cudaSuccess) e = e2;
             }
@@ -907,7 +921,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
         }
     }
     memcpy(B.last_key, &key, sizeof key); B.have_last_key = true;
-    if (!done) CKE(wave_pass_body(B, S, AS, spp, stream, launches, T, accumulate));
+    if (!done) CKE(wave_pass_body(B, S, AS, spp, stream, launches, T, accumulate, parts_override, defer_accumulate));
     CKE(cudaEventRecord(T->ev[1], stream));
     return cudaGetLastError();
 }

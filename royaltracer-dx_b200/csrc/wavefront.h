@@ -89,13 +89,20 @@ struct PassTiming {
 };
 
 // One DispatchRays-equivalent: samples [first_sample, first_sample + spp) of every pixel.
+// parts_override > 0: that many path ranges instead of B.parts.  defer_accumulate: everything but the final k_accumulate (the caller
+// launches wave_accumulate itself, behind whatever has to touch gPermanentData first: api.cu pipelines consecutive passes that way).
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
-                             cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true);
+                             cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true, int parts_override = 0,
+                             bool defer_accumulate = false);
 // the same stage sequence built with fast math (wavefront.cu compiled with -DRTX_FAST_MATH): RTX_FLAG_FAST_MATH
 namespace fast {
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
-                             cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true);
+                             cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true, int parts_override = 0,
+                             bool defer_accumulate = false);
 }
+// a second set of pass buffers that shares gPermanentData, gOutput and the camera block with `B` (pipelined passes, api.cu)
+cudaError_t wave_alloc_lane(WaveBuffers* L, const WaveBuffers& B, uint32_t width, uint32_t height, uint32_t spp);
+void wave_free_lane(WaveBuffers* L);
 // The reference's legacy estimator (include/RayGen.hlsl + include/Hit.hlsl) as a wavefront: legacy.cu.  S.bounces caps the path length.
 cudaError_t wave_render_pass_legacy(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp,
                                     cudaStream_t stream, uint64_t* launches, PassTiming* timing);

@@ -621,6 +621,71 @@ def test_graph_replay_and_trace_order_do_not_change_the_image(rtdx, orc):
     ctx.close()
 
 
+def test_pipelined_passes_are_bit_identical(rtdx, orc):
+    """RTX_OPT_PASS_PIPELINE: rtx_render_pass calls that directly follow each other alternate between two sets of pass buffers on two
+    streams and overlap; gPermanentData is shared and the accumulations are chained in call order, so seven samples equal the oracle's
+    seven samples bit for bit — back to back, through the n_samples loop of one call, with the pipeline off, with other calls
+    (camera, engine-side reduce) between the passes — and a camera change in the middle of a sequence resets the accumulation at the
+    right place."""
+    sc = rtdx.scenes.mesh_room(n=16)
+    W, H, bounces, n_samples = 384, 192, 3, 7
+    ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
+    osc = orc.OracleScene(sc, up["props"], up["lights"])
+    ref, rays = None, [0, 0]
+    per_sample = []
+    for s in range(n_samples):
+        img, octr = osc.render(up["camera"], W, H, s, 1, bounces=bounces, flags=0)
+        per_sample.append(img)
+        ref = img if ref is None else ref + img
+        rays[0] += octr["closest_rays"]; rays[1] += octr["shadow_rays"]
+
+    def check(tag):
+        ctx.synchronize()
+        cnt = ctx.counters()
+        assert np.array_equal(bits(ctx.read_accum()), bits(ref)), tag
+        assert (cnt["closest_rays"], cnt["shadow_rays"]) == tuple(rays), (tag, cnt, rays)
+
+    for tag, pipeline in (("back to back", 1), ("pipeline off", 0)):
+        ctx.set_option(rtdx.OPT_PASS_PIPELINE, pipeline)
+        ctx.reset_accum(); ctx.reset_counters()
+        for s in range(n_samples):
+            ctx.render_pass(s, 1)
+        check(tag)
+    ctx.set_option(rtdx.OPT_PASS_PIPELINE, 1)
+    ctx.reset_accum(); ctx.reset_counters()
+    ctx.render_pass(0, n_samples)                       # one call, n_samples passes
+    check("n_samples loop")
+    ctx.reset_accum(); ctx.reset_counters()
+    for s in range(n_samples):                          # other calls in between end and restart the sequence
+        ctx.render_pass(s, 1)
+        if s % 3 == 1:
+            ctx.set_camera(up["camera"])
+        if s % 3 == 2:
+            ctx.read_output()
+    check("interleaved calls")
+    ctx.comm_init(ctx.comm_unique_id(), 0, 1)           # a reduce after every pass does not end the sequence
+    ctx.reset_accum(); ctx.reset_counters()
+    for s in range(n_samples):
+        ctx.render_pass(s, 1); ctx.reduce_accum()
+    assert np.array_equal(bits(ctx.read_reduced_accum()), bits(ref))
+    check("reduce between passes")
+    # a view change in the middle of a sequence: the reset lands between the right two passes
+    cam2 = rtdx.camera_params((sc.eye[0] + 0.3, sc.eye[1], sc.eye[2]), sc.center, sc.up, W / float(H))
+    ctx.reset_accum()
+    for s in range(3):
+        ctx.render_pass(s, 1)
+    ctx.set_camera(cam2)
+    for s in range(3, 6):
+        ctx.render_pass(s, 1)
+    ctx.synchronize()
+    ref2 = None
+    for s in range(3, 6):
+        img, _ = osc.render(cam2, W, H, s, 1, bounces=bounces, flags=0)
+        ref2 = img if ref2 is None else ref2 + img
+    assert np.array_equal(bits(ctx.read_accum()), bits(ref2))
+    ctx.close()
+
+
 def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
     (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""
