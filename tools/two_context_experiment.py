@@ -12,16 +12,18 @@ import rtdx  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--parts", type=int, default=2)
-ap.add_argument("--passes", type=int, default=40)
+ap.add_argument("--passes", type=int, default=42)
+ap.add_argument("--contexts", type=int, default=2)
 a = ap.parse_args()
 sc = rtdx.scenes.mesh_room(n=296)
 W, H = 1920, 1080
-streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+streams = [torch.cuda.Stream() for _ in range(a.contexts)]
 ctxs = []
 for s in streams:
     c = rtdx.Context(W, H, bounces=6, stream=s.cuda_stream)
     c.upload_scene(sc)
     c.set_option(rtdx.OPT_PASS_PARTS, a.parts)
+    c.set_option(rtdx.OPT_PASS_PIPELINE, 0)          # (the engine's own pipelining off: this experiment is what led to it)
     ctxs.append(c)
 
 
@@ -43,4 +45,4 @@ def run(n_ctx, passes):
 
 
 for rep in range(2):
-    print("parts=%d  one context %.3f ms/pass   two contexts, alternate passes %.3f ms/pass" % (a.parts, run(1, a.passes), run(2, a.passes)), flush=True)
+    print("parts=%d  one context %.3f ms/pass   %d contexts, alternate passes %.3f ms/pass" % (a.parts, run(1, a.passes), a.contexts, run(a.contexts, a.passes)), flush=True)
