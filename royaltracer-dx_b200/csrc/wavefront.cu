@@ -705,6 +705,9 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
     uint64_t L = 0;
     T->n_marks = 0;
     const int parts = pass_parts(B, S, T, n, accumulate, parts_override);
+    // traversal launches that run beside each other share the machine's resident CTAs: the parts of this pass, and (defer_accumulate:
+    // a pipelined pass, api.cu) the pass of the other lane
+    const int share = parts * (defer_accumulate ? 2 : 1);
 
     struct Part {
         cudaStream_t stream; uint32_t p0, np; PartMap pm; unsigned grid, ggrid;
@@ -757,7 +760,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
     };
     auto closest = [&](Part& p, const RayQueue& q) -> cudaError_t {
         CKE(mark(SK_CLOSEST));
-        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, parts, q.order, q.n_heavy, q.cap);
+        return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, p.cursor, p.hit_a, p.hit_inst, false, T->stats, p.stream, share, q.order, q.n_heavy, q.cap);
     };
     const bool side_shadow = B.shadow_overlap && !T->stage_timing && !T->stats;
     auto shadow = [&](Part& p, const RayQueue& q, float* vis, bool side) -> cudaError_t {
@@ -766,7 +769,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
         // a launch on the side stream has its own cursor words (it runs beside the part's closest-hit launches)
         const int h = (int)(&p - P);
         return launch_trace(AS, q.o_tmin, q.d_tmax, q.count, 0, side ? p.cursor + 2 : p.cursor, p.hit_a, p.hit_inst, true, nullptr,
-                            side ? B.aux_sh[h] : p.stream, parts, q.order, q.n_heavy, q.cap, q.pid, vis);
+                            side ? B.aux_sh[h] : p.stream, share, q.order, q.n_heavy, q.cap, q.pid, vis);
     };
     // stage s of one part; the parts are issued round-robin stage by stage so that every stream always has work queued
     const int n_stages = 7 + 2 * ((int)S.bounces + 1) + 2;

@@ -1,11 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/sweep_pipeline_ctas.txt; : > $O
-for ct in 0 4 5 6 7; do
-python tools/pass_time.py --passes 60 --opt TRACE_CTAS=$ct --tag "C2 pipelined, TRACE_CTAS=$ct" >> $O 2>&1
-done
-for th in 20 24; do
-python tools/pass_time.py --passes 60 --opt TRACE_FETCH_TH=$th --tag "C2 pipelined, fetch_th=$th" >> $O 2>&1
-done
-python tools/pass_time.py --passes 60 --opt SHADOW_OVERLAP=0 --tag "C2 pipelined, shadow rays in sequence" >> $O 2>&1
+O=gpurun_out/sweep_pipeline_share.txt; : > $O
+python tools/pass_time.py --passes 60 --tag "C2 pipelined, half grid per lane" >> $O 2>&1
+python tools/pass_time.py --passes 60 --tag "C2 pipelined, half grid per lane" >> $O 2>&1
+python tools/pass_time.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 12 --tag "C3 pipelined, half grid per lane" >> $O 2>&1
+python tools/pass_time.py --passes 40 --flags 32 --tag "C2 fast pipelined, half grid per lane" >> $O 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pipelined or graph or concurrent" 2>&1 | tail -2 >> $O
 cat $O
