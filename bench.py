@@ -364,8 +364,9 @@ def roofline_of(rtdx, ctx, cfg, steps, first, rank, world, stats, blas):
             "trace_share_of_step": trace_ms / pass_ms if pass_ms else None,
             "note": "BVH %.1f MB (L2-resident below ~100 MB: HBM peak is then the conservative denominator, SURVEY.md §8d); instance entries count every "
                     "64-B record read, incl. those rejected by the object-space bounds; per-launch durations from the same steps re-run with CUDA "
-                    "events around every traversal launch (one path range per pass, full-size launches); the timed steps of `value` run as 2 "
-                    "concurrent path ranges" % (sum(b["bytes"] for b in blas) / 1e6)}
+                    "events around every traversal launch (one path range per pass, one pass at a time, full-size launches); the timed steps of "
+                    "`value` are consecutive passes, which the engine overlaps two at a time (RTX_OPT_PASS_PIPELINE), the steps of `e2e` "
+                    "(instances + camera + pass + read-back per frame) run one at a time as 2 concurrent path ranges" % (sum(b["bytes"] for b in blas) / 1e6)}
 
 
 def parity_of(rtdx, ctx, cfg, up, sc, osc, img, cores):

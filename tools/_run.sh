@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/sweep_pipeline_share.txt; : > $O
-python tools/pass_time.py --passes 60 --tag "C2 pipelined, half grid per lane" >> $O 2>&1
-python tools/pass_time.py --passes 60 --tag "C2 pipelined, half grid per lane" >> $O 2>&1
-python tools/pass_time.py --scene inst --width 3840 --height 2160 --bounces 3 --passes 12 --tag "C3 pipelined, half grid per lane" >> $O 2>&1
-python tools/pass_time.py --passes 40 --flags 32 --tag "C2 fast pipelined, half grid per lane" >> $O 2>&1
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pipelined or graph or concurrent" 2>&1 | tail -2 >> $O
-cat $O
+O=gpurun_out; T=s5
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"trace_kernel|k_gi_step|k_shade_primary|k_di_finish" -s 52 -c 13 -o $O/r02_${T}_pass -f python tools/prof_pass.py --passes 3 --opt PASS_PARTS=1 --opt PASS_PIPELINE=0 > $O/ncu_full.log 2>&1
+tail -2 $O/ncu_full.log
+for l in 0 1; do
+RTX_B200_LIB=build/variants/timeline.so python tools/pass_timeline.py $l > $O/tl_$l.txt 2>&1
+python tools/pass_timeline.py --analyse $O/tl_$l.txt > $O/r02_${T}_trace_timeline_lpt$l.txt
+done
+head -7 $O/r02_${T}_trace_timeline_lpt1.txt
