@@ -84,7 +84,7 @@ struct rtx_ctx {
 
 static rtx_status fail(rtx_status code, const char* msg) { set_error(msg); return code; }
 
-// Every entry point except rtx_render_pass and rtx_reduce_accum starts here: the device is made current, and a sequence of pipelined
+// Every entry point except rtx_render_pass, rtx_reduce_accum and rtx_synchronize starts here: the device is made current, and a sequence of pipelined
 // passes ends (the caller's stream already waits for every pass queued so far; what this call queues there is ordered before the
 // passes that follow through ev_state).
 static rtx_status enter(rtx_ctx* c) {
@@ -446,6 +446,7 @@ static rtx_status check_overflow(rtx_ctx* c) {
     RTX_CK(cudaStreamSynchronize(c->stream));
     if (flag) {
         RTX_CK(cudaMemsetAsync(c->d_overflow, 0, sizeof flag, c->stream));
+        c->main_dirty = true; c->in_sequence = false;       // the passes that follow start behind the clear
         return fail(RTX_ERR_STATE, "traversal stack overflow (BVH deeper than RTX_STACK_SIZE): the results of this pass are invalid");
     }
     return RTX_OK;
@@ -605,8 +606,8 @@ extern "C" rtx_status rtx_reset_accum(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_synchronize(rtx_ctx* c) {
     if (!c) return fail(RTX_ERR_ARG, "null context");
-    RTX_ENTER(c);
-    RTX_CK(cudaStreamSynchronize(c->stream));
+    RTX_CK(cudaSetDevice(c->cfg.device));       // (not through enter(): waiting changes no state, a pipelined sequence of passes goes on after it)
+    RTX_CK(cudaStreamSynchronize(c->stream));   // the caller's stream is behind every pass queued so far
     return check_overflow(c);
 }
 
