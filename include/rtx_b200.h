@@ -187,6 +187,7 @@ rtx_status rtx_last_pass_stage_ms(rtx_ctx*, float* ms_by_stage, uint32_t n_stage
 #define RTX_OPT_SHADOW_OVERLAP 11u  /* 1 (default): the DI visibility rays of a pass are traced on a side stream beside the indirect bounces; 0: in sequence */
 #define RTX_OPT_PART_ROWS      12u  /* concurrent path ranges own interleaved chunks of this many image rows: 0 = contiguous ranges, 1..64, 0xffffffff (default) = chosen per frame size */
 #define RTX_OPT_PASS_PIPELINE  13u  /* 1 (default): rtx_render_pass calls that directly follow each other overlap (two sets of pass buffers, accumulation in call order: bit-identical); 0: one pass at a time */
+#define RTX_OPT_FRAME_PIPELINE 14u  /* 1 (default): a per-frame loop rtx_set_instances (<= 8 instances, same models) -> rtx_set_camera -> rtx_render_pass -> rtx_read_output_async keeps two sets of per-frame state and overlaps consecutive frames (bit-identical); 0: one frame at a time */
 rtx_status rtx_set_option(rtx_ctx*, uint32_t option, uint32_t value);
 /* debug: per-pixel record of one sample in the layout of the oracle's orc_debug_pixel (64 floats) */
 rtx_status rtx_debug_pixel(rtx_ctx*, uint32_t x, uint32_t y, float* out64);

@@ -35,7 +35,7 @@ assert vertex_dt.itemsize == 28 and material_dt.itemsize == 128 and props_dt.ite
 assert camera_dt.itemsize == 512 and desc_dt.itemsize == 64 and ray_dt.itemsize == 32 and hit_dt.itemsize == 20
 
 FLAG_JITTER, FLAG_LAMBERT_ONLY, FLAG_SORT_MATERIAL, FLAG_RESTIR, FLAG_LEGACY_RR, FLAG_FAST_MATH = 1, 2, 4, 8, 16, 32
-OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS, OPT_TLAS_REBUILD, OPT_TRACE_FETCH_TH, OPT_TRACE_SCHED, OPT_TRACE_WAVES, OPT_QUEUE_LPT, OPT_TRACE_CTAS, OPT_PASS_GRAPH, OPT_SHADOW_OVERLAP, OPT_PART_ROWS, OPT_PASS_PIPELINE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
+OPT_TRACE_STATS, OPT_STAGE_TIMING, OPT_PASS_PARTS, OPT_TLAS_REBUILD, OPT_TRACE_FETCH_TH, OPT_TRACE_SCHED, OPT_TRACE_WAVES, OPT_QUEUE_LPT, OPT_TRACE_CTAS, OPT_PASS_GRAPH, OPT_SHADOW_OVERLAP, OPT_PART_ROWS, OPT_PASS_PIPELINE, OPT_FRAME_PIPELINE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
 MISS = 0xFFFFFFFF
 STAGE_NAMES = ["generate", "closest", "any", "shade_primary", "di_finish", "gi_step", "scatter", "finalize", "accumulate", "sort"]
 
@@ -354,14 +354,25 @@ class Context:
         return p.value
 
     # multi-GPU: the per-pass NCCL reduce of gPermanentData lives behind the C ABI (rtx_comm_init / rtx_reduce_accum)
+    @staticmethod
+    def _nccl_of_the_process():
+        """The engine binds NCCL with dlopen("libnccl.so.2") at the first comm call and a process holds ONE library of that soname: in a
+        Python process torch must load its bundled (newer) NCCL first, or a later `import torch` finds the system's older one in its place."""
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
     def comm_unique_id(self):
         """128 bytes of ncclGetUniqueId (call on one rank, hand to the others)."""
+        self._nccl_of_the_process()
         buf = (C.c_ubyte * 128)()
         self._check(self.lib.rtx_comm_unique_id(C.cast(buf, C.c_void_p)))
         return bytes(buf)
 
     def comm_init(self, unique_id, rank, world):
         assert len(unique_id) == 128
+        self._nccl_of_the_process()
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self.lib.rtx_comm_init(self.handle, C.cast(buf, C.c_void_p), rank, world))
 

@@ -75,6 +75,22 @@ struct rtx_ctx {
     // starts behind ev_state (whatever other entry points queued on the caller's stream), and the caller's stream is made to wait for
     // every pass's accumulation (no host wait).  The first pass after any other call runs as before (B.parts path ranges on the
     // caller's stream).
+    // Pipelined FRAMES (RTX_OPT_FRAME_PIPELINE): a per-frame loop in the reference's order — rtx_set_instances, rtx_set_camera,
+    // rtx_render_pass, rtx_read_output_async — with a TLAS that fits one node (<= 8 instances: BASELINE config C2) keeps two sets of the
+    // per-frame state (instance records, properties, TLAS, camera block), one per lane: the calls of frame k+1 write the set of the lane
+    // frame k-1 used and queue on that lane's stream, so frame k+1 starts under the tail of frame k.  Every other call pattern takes
+    // the plain path above (enter() first copies lane 1's set back into the context's own buffers if it is the newer one).
+    struct FrameSet {
+        rtx_instance_desc* d_descs = nullptr; rtx_instance_props* d_props = nullptr; uint32_t* d_inst_model = nullptr;
+        float4* d_inst_recs = nullptr; float4 *d_box_lo = nullptr, *d_box_hi = nullptr; unsigned int* d_box6 = nullptr;
+        Bvh8 tlas; void* d_tlas_ctr = nullptr; bool ready = false;
+    } fs1;
+    bool frame_pipeline = true, frame_seq_ok = false, resolve_pending = false;
+    cudaEvent_t ev_fset = nullptr; bool fset_pending = false;       // behind the last fast rtx_set_instances / rtx_set_camera on a lane stream
+    int pending_lane = -1;              // >= 0: the fast rtx_set_instances of this frame prepared that lane
+    int cur_set = 0;                    // which set of per-frame instance state is the newest (0 = the context's own buffers)
+    int lane_read_set[2] = {0, 0};      // the set the last pass of each lane read
+    int cam_version = 0, cam_block_version[2] = {0, 0};   // the camera blocks of the two lanes (wb.cam, wb2.cam) against the latest rtx_set_camera
     WaveBuffers wb2; bool wb2_ready = false, wb2_refused = false;
     cudaStream_t lane_stream[2] = {nullptr, nullptr}; cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_state = nullptr;
     PassTiming timing2;
@@ -87,10 +103,13 @@ static rtx_status fail(rtx_status code, const char* msg) { set_error(msg); retur
 // Every entry point except rtx_render_pass, rtx_reduce_accum and rtx_synchronize starts here: the device is made current, and a sequence of pipelined
 // passes ends (the caller's stream already waits for every pass queued so far; what this call queues there is ordered before the
 // passes that follow through ev_state).
+static rtx_status sync_frame_state(rtx_ctx* c);
+static void free_frame_set(rtx_ctx* c);
 static rtx_status enter(rtx_ctx* c) {
     RTX_CK(cudaSetDevice(c->cfg.device));
-    c->in_sequence = false; c->main_dirty = true;
-    return RTX_OK;
+    c->in_sequence = false; c->main_dirty = true; c->frame_seq_ok = false; c->pending_lane = -1;
+    if (c->fset_pending) { RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_fset, 0)); c->fset_pending = false; }   // a prepared frame that was never rendered
+    return sync_frame_state(c);
 }
 #define RTX_ENTER(c) do { const rtx_status e__ = enter(c); if (e__ != RTX_OK) return e__; } while (0)
 
@@ -105,6 +124,7 @@ static rtx_status create_resources(rtx_ctx* c) {
     for (int i = 0; i < 2; i++) RTX_CK(cudaEventCreate(&c->timing2.ev[i]));
     for (int i = 0; i < 2; i++) RTX_CK(cudaEventCreateWithFlags(&c->ev_acc[i], cudaEventDisableTiming));
     RTX_CK(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+    RTX_CK(cudaEventCreateWithFlags(&c->ev_fset, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) RTX_CK(cudaStreamCreateWithFlags(&c->lane_stream[i], cudaStreamNonBlocking));
     RTX_CK(cudaMalloc((void**)&c->d_stats, sizeof(TraceStats)));
     RTX_CK(cudaMemset(c->d_stats, 0, sizeof(TraceStats)));
@@ -167,12 +187,14 @@ extern "C" void rtx_destroy(rtx_ctx* c) {
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     for (auto& sg : c->stage) { if (sg.p) cudaFreeHost(sg.p); if (sg.ev) cudaEventDestroy(sg.ev); }
     { void* q[] = {c->d_box_lo, c->d_box_hi, c->d_tlas_ctr, c->d_box6}; for (void* p : q) if (p) cudaFree(p); }
+    free_frame_set(c);
     if (c->wb2_ready) wave_free_lane(&c->wb2);
     if (c->wb_ready) wave_free(&c->wb);
     if (c->rs_ready) restir_free(&c->rs);
     for (int i = 0; i < WAVE_MAX_EVENTS; i++) if (c->timing.ev[i]) cudaEventDestroy(c->timing.ev[i]);
     for (int i = 0; i < 2; i++) { if (c->timing2.ev[i]) cudaEventDestroy(c->timing2.ev[i]); if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); }
     if (c->ev_state) cudaEventDestroy(c->ev_state);
+    if (c->ev_fset) cudaEventDestroy(c->ev_fset);
     for (int i = 0; i < 2; i++) if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -286,9 +308,84 @@ static rtx_status reserve(T** dptr, size_t* cap, size_t n) {
     return RTX_OK;
 }
 
+// the caller's arrays are copied into a pinned staging block (the library copies on upload, S-rows ownership) and from there to the
+// device on `s`; the block is reused two calls later, after the event recorded behind its H2D copies
+static rtx_status stage_instances(rtx_ctx* c, const rtx_instance_desc* descs, const rtx_instance_props* props, uint32_t n,
+                                  rtx_instance_desc* d_descs, rtx_instance_props* d_props, uint32_t* d_inst_model, cudaStream_t s) {
+    rtx_ctx::Stage& sg = c->stage[c->stage_i]; c->stage_i ^= 1;
+    if (!sg.ev) RTX_CK(cudaEventCreateWithFlags(&sg.ev, cudaEventDisableTiming));
+    if (sg.pending) { RTX_CK(cudaEventSynchronize(sg.ev)); sg.pending = false; }
+    const size_t b_descs = (size_t)n * sizeof(rtx_instance_desc), b_props = (size_t)n * sizeof(rtx_instance_props), b_im = (size_t)n * 4;
+    if (sg.cap < b_descs + b_props + b_im) {
+        if (sg.p) cudaFreeHost(sg.p);
+        sg.cap = b_descs + b_props + b_im + 4096;
+        RTX_CK(cudaMallocHost(&sg.p, sg.cap));
+    }
+    if (n) {
+        uint8_t* h = (uint8_t*)sg.p;
+        memcpy(h, descs, b_descs); memcpy(h + b_descs, props, b_props);
+        uint32_t* im = (uint32_t*)(h + b_descs + b_props);
+        for (uint32_t i = 0; i < n; i++) im[i] = (uint32_t)descs[i].blas;
+        RTX_CK(cudaMemcpyAsync(d_descs, h, b_descs, cudaMemcpyHostToDevice, s));
+        RTX_CK(cudaMemcpyAsync(d_props, h + b_descs, b_props, cudaMemcpyHostToDevice, s));
+        RTX_CK(cudaMemcpyAsync(d_inst_model, im, b_im, cudaMemcpyHostToDevice, s));
+        RTX_CK(cudaEventRecord(sg.ev, s)); sg.pending = true;
+    }
+    return RTX_OK;
+}
+
+static bool lane_buffers(rtx_ctx* c);
+
+static const size_t SINGLE_NODE_INSTANCES = 8;      // the largest TLAS that is one node (bvh_build.cu tlas_fits_one_node)
+// lane 1's set of per-frame state (<= 8 instances)
+static bool ensure_frame_set(rtx_ctx* c) {
+    rtx_ctx::FrameSet& f = c->fs1;
+    if (f.ready) return true;
+    const size_t n = SINGLE_NODE_INSTANCES;
+    bool ok = cudaMalloc((void**)&f.d_descs, n * sizeof(rtx_instance_desc)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.d_props, n * sizeof(rtx_instance_props)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.d_inst_model, n * 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.d_inst_recs, n * 64) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.d_box_lo, n * 16) == cudaSuccess && cudaMalloc((void**)&f.d_box_hi, n * 16) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.d_box6, n * 24) == cudaSuccess && cudaMalloc(&f.d_tlas_ctr, 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&f.tlas.nodes, 80) == cudaSuccess && cudaMalloc((void**)&f.tlas.prims, n * 64) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return false; }      // (freed by rtx_destroy)
+    f.ready = true;
+    return true;
+}
+static void free_frame_set(rtx_ctx* c) {
+    rtx_ctx::FrameSet& f = c->fs1;
+    void* p[] = {f.d_descs, f.d_props, f.d_inst_model, f.d_inst_recs, f.d_box_lo, f.d_box_hi, f.d_box6, f.d_tlas_ctr, f.tlas.nodes, f.tlas.prims};
+    for (void* q : p) if (q) cudaFree(q);
+    f = rtx_ctx::FrameSet();
+}
+// the context's own buffers become the newest set again (copied from lane 1's on the caller's stream, which is behind every pass)
+static rtx_status sync_frame_state(rtx_ctx* c) {
+    if (c->cur_set == 0) return RTX_OK;
+    const rtx_ctx::FrameSet& f = c->fs1;
+    const size_t n = c->n_instances;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    RTX_CK(cudaMemcpyAsync(c->d_descs, f.d_descs, n * sizeof(rtx_instance_desc), k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->d_props, f.d_props, n * sizeof(rtx_instance_props), k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->d_inst_model, f.d_inst_model, n * 4, k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->d_inst_recs, f.d_inst_recs, n * 64, k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->d_box_lo, f.d_box_lo, n * 16, k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->d_box_hi, f.d_box_hi, n * 16, k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->tlas.nodes, f.tlas.nodes, 80, k, c->stream));
+    RTX_CK(cudaMemcpyAsync(c->tlas.prims, f.tlas.prims, n * 64, k, c->stream));
+    c->cur_set = 0;
+    return RTX_OK;
+}
+// is the call part of a per-frame loop that can be pipelined?  (the previous frame ended with rtx_render_pass [+ read-back] and nothing else)
+static bool frame_fast_ok(rtx_ctx* c) {
+    return c->pipeline && c->frame_pipeline && c->frame_seq_ok && c->wb_ready &&
+           !(c->cfg.flags & (RTX_FLAG_LEGACY_RR | RTX_FLAG_RESTIR | RTX_FLAG_SORT_MATERIAL)) && !c->timing.stage_timing && !c->trace_stats &&
+           (uint64_t)c->cfg.width * c->cfg.height * c->cfg.samples_per_pass >= 65536u && lane_buffers(c) && ensure_frame_set(c);
+}
+
 extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* descs, const rtx_instance_props* props, uint32_t n) {
     if (!c || ((!descs || !props) && n)) return fail(RTX_ERR_ARG, "rtx_set_instances: null argument");
-    RTX_ENTER(c);
+    RTX_CK(cudaSetDevice(c->cfg.device));
     for (uint32_t i = 0; i < n; i++) {
         if (descs[i].blas >= c->models.size()) return fail(RTX_ERR_ARG, "rtx_set_instances: instance references an unknown model");
         if (c->models[descs[i].blas].n_tris == 0) return fail(RTX_ERR_ARG, "rtx_set_instances: instance of an empty model");
@@ -329,31 +426,43 @@ extern "C" rtx_status rtx_set_instances(rtx_ctx* c, const rtx_instance_desc* des
         for (int r = 0; r < 3; r++) { c->heavy_lo[r] = lo[r]; c->heavy_hi[r] = hi[r]; }
     }
     rtx_status st;
+    {
+        bool same = n > 0 && tlas_fits_one_node(n) && c->tlas.nodes && c->tlas.n_prims == n && c->n_instances == n && c->tlas_models.size() == n &&
+                    !c->force_tlas_rebuild && c->cap_tlas_prims >= n && c->d_blas && c->n_tables == c->models.size();
+        for (uint32_t i = 0; same && i < n; i++) same = c->tlas_models[i] == (uint32_t)descs[i].blas;
+        if (same && frame_fast_ok(c)) {
+            // the per-frame path of a pipelined frame loop: the state set of the lane this frame will render on, on that lane's stream
+            const int L = 1 - c->last_lane;
+            const cudaStream_t s_ = c->lane_stream[L];
+            if (c->main_dirty) { RTX_CK(cudaEventRecord(c->ev_state, c->stream)); c->main_dirty = false; }
+            RTX_CK(cudaStreamWaitEvent(s_, c->ev_state, 0));
+            RTX_CK(cudaStreamWaitEvent(s_, c->ev_acc[L], 0));                                        // the last pass of this lane ...
+            if (c->lane_read_set[1 - L] == L) RTX_CK(cudaStreamWaitEvent(s_, c->ev_acc[1 - L], 0));   // ... and of the other one if it read this set
+            rtx_instance_desc* dd = L ? c->fs1.d_descs : c->d_descs;
+            rtx_instance_props* dp = L ? c->fs1.d_props : c->d_props;
+            uint32_t* dm = L ? c->fs1.d_inst_model : c->d_inst_model;
+            float4* dr = L ? c->fs1.d_inst_recs : c->d_inst_recs;
+            float4* lo_ = L ? c->fs1.d_box_lo : c->d_box_lo; float4* hi_ = L ? c->fs1.d_box_hi : c->d_box_hi;
+            unsigned int* b6 = L ? c->fs1.d_box6 : c->d_box6;
+            Bvh8* tl = L ? &c->fs1.tlas : &c->tlas;
+            void* ctr = L ? c->fs1.d_tlas_ctr : c->d_tlas_ctr;
+            if (L) { const uint4* nn = tl->nodes; const float4* pp = tl->prims; c->fs1.tlas = c->tlas; tl->nodes = const_cast<uint4*>(nn); tl->prims = const_cast<float4*>(pp); }
+            if ((st = stage_instances(c, descs, props, n, dd, dp, dm, s_)) != RTX_OK) return st;
+            cudaError_t e = launch_instance_records(dd, dp, c->d_bounds, n, dr, lo_, hi_, b6, s_);
+            if (e == cudaSuccess) e = update_tlas_one_node(dr, lo_, hi_, n, tl, ctr, s_);
+            RTX_CK(e);
+            RTX_CK(cudaEventRecord(c->ev_fset, s_)); c->fset_pending = true;
+            c->pending_lane = L; c->cur_set = L;
+            c->launches += 6;
+            return RTX_OK;
+        }
+    }
+    RTX_ENTER(c);
     if ((st = ensure_tables(c)) != RTX_OK) return st;
     if ((st = reserve(&c->d_descs, &c->cap_descs, n)) != RTX_OK) return st;
     if ((st = reserve(&c->d_props, &c->cap_props, n)) != RTX_OK) return st;
     if ((st = reserve(&c->d_inst_model, &c->cap_inst_model, n)) != RTX_OK) return st;
-    // the caller's arrays are copied into a pinned staging block (the library copies on upload, S-rows ownership); the block is reused
-    // two calls later, after the event recorded behind its H2D copies
-    rtx_ctx::Stage& sg = c->stage[c->stage_i]; c->stage_i ^= 1;
-    if (!sg.ev) RTX_CK(cudaEventCreateWithFlags(&sg.ev, cudaEventDisableTiming));
-    if (sg.pending) { RTX_CK(cudaEventSynchronize(sg.ev)); sg.pending = false; }
-    const size_t b_descs = (size_t)n * sizeof(rtx_instance_desc), b_props = (size_t)n * sizeof(rtx_instance_props), b_im = (size_t)n * 4;
-    if (sg.cap < b_descs + b_props + b_im) {
-        if (sg.p) cudaFreeHost(sg.p);
-        sg.cap = b_descs + b_props + b_im + 4096;
-        RTX_CK(cudaMallocHost(&sg.p, sg.cap));
-    }
-    if (n) {
-        uint8_t* h = (uint8_t*)sg.p;
-        memcpy(h, descs, b_descs); memcpy(h + b_descs, props, b_props);
-        uint32_t* im = (uint32_t*)(h + b_descs + b_props);
-        for (uint32_t i = 0; i < n; i++) im[i] = (uint32_t)descs[i].blas;
-        RTX_CK(cudaMemcpyAsync(c->d_descs, h, b_descs, cudaMemcpyHostToDevice, c->stream));
-        RTX_CK(cudaMemcpyAsync(c->d_props, h + b_descs, b_props, cudaMemcpyHostToDevice, c->stream));
-        RTX_CK(cudaMemcpyAsync(c->d_inst_model, im, b_im, cudaMemcpyHostToDevice, c->stream));
-        RTX_CK(cudaEventRecord(sg.ev, c->stream)); sg.pending = true;
-    }
+    if ((st = stage_instances(c, descs, props, n, c->d_descs, c->d_props, c->d_inst_model, c->stream)) != RTX_OK) return st;
     c->n_instances = n;
     if ((st = reserve(&c->d_inst_recs, &c->cap_recs, (size_t)n * 4)) != RTX_OK) return st;
     if ((st = reserve(&c->d_box_lo, &c->cap_lo, n)) != RTX_OK) return st;
@@ -411,9 +520,13 @@ static rtx_status ensure_wave(rtx_ctx* c) {
 
 extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
     if (!c || !cam) return fail(RTX_ERR_ARG, "rtx_set_camera: null argument");
-    RTX_ENTER(c);
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    const int fast_lane = c->pending_lane;       // >= 0: the camera of a pipelined frame (its rtx_set_instances chose the lane)
     rtx_status st;
-    if ((st = ensure_wave(c)) != RTX_OK) return st;
+    if (fast_lane < 0) {
+        RTX_ENTER(c);
+        if ((st = ensure_wave(c)) != RTX_OK) return st;
+    }
     // Pass_spat_di_v7.hlsl:407-423: any element of view differing from the previous view by more than s_bias resets the accumulation
     // The shader compares view with prevView of the SAME constant buffer; a host that does not maintain prevView (all zeros, or a copy of
     // view) is covered by also comparing with the view of the previous call.
@@ -423,15 +536,30 @@ extern "C" rtx_status rtx_set_camera(rtx_ctx* c, const rtx_camera_params* cam) {
         if (c->have_cam && fabsf(cam->view[i] - c->cam.view[i]) > RTX_S_BIAS) different = true;
     }
     c->cam = *cam; c->have_cam = true;
+    c->cam_version++;
+    if (fast_lane >= 0) {
+        const cudaStream_t s_ = c->lane_stream[fast_lane];      // (already behind ev_state and the lane's last pass: rtx_set_instances)
+        RTX_CK(cudaMemcpyAsync(fast_lane ? c->wb2.cam : c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, s_));
+        c->cam_block_version[fast_lane] = c->cam_version;
+        if (different) {        // the reset lands between the previous frame's accumulation (and resolve) and this frame's
+            RTX_CK(cudaStreamWaitEvent(s_, c->ev_acc[1 - fast_lane], 0));
+            if (c->resolve_pending) RTX_CK(cudaStreamWaitEvent(s_, c->ev_resolved, 0));
+            RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, s_));
+        }
+        RTX_CK(cudaEventRecord(c->ev_fset, s_)); c->fset_pending = true;
+        return RTX_OK;
+    }
     RTX_CK(cudaMemcpyAsync(c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, c->stream));
+    c->cam_block_version[0] = c->cam_version;       // (lane 1's block is brought up to date when a pass runs there)
     if (different) RTX_CK(cudaMemsetAsync(c->wb.accum, 0, (size_t)c->cfg.width * c->cfg.height * 16, c->stream));
     return RTX_OK;      // the 512-B copy from pageable memory is staged by the driver before the call returns
 }
 
-static SceneAS make_as(rtx_ctx* c) {
+static SceneAS make_as(rtx_ctx* c, int set = 0) {
     SceneAS a;
     memset(&a, 0, sizeof a);            // (padding bytes too: the wavefront compares these structs bytewise to reuse a captured pass)
-    a.tlas_nodes = c->tlas.nodes; a.inst_recs = c->tlas.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
+    const Bvh8& tl = set ? c->fs1.tlas : c->tlas;
+    a.tlas_nodes = tl.nodes; a.inst_recs = tl.prims; a.blas = c->d_blas; a.n_instances = c->n_instances;
     a.one_bits = 0x3F800000u;
     a.overflow = c->d_overflow;
     a.num_sms = c->num_sms; a.fetch_th = c->fetch_th; a.sched = c->sched; a.waves = c->waves; a.ctas_per_sm = c->ctas_per_sm;
@@ -488,7 +616,7 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
     S.width = c->cfg.width; S.height = c->cfg.height;
     for (int r = 0; r < 3; r++) { S.heavy_lo[r] = c->heavy_lo[r]; S.heavy_hi[r] = c->heavy_hi[r]; }
     S.heavy_valid = c->heavy_valid && c->lpt ? 1u : 0u;
-    const SceneAS AS = make_as(c);
+    SceneAS AS = make_as(c);
     const uint32_t npx = c->cfg.width * c->cfg.height;
     // pipelined passes (see rtx_ctx): the estimator E0 without per-launch instrumentation, frames large enough to be cut into path ranges
     const bool eligible = c->pipeline && !(c->cfg.flags & (RTX_FLAG_LEGACY_RR | RTX_FLAG_RESTIR | RTX_FLAG_SORT_MATERIAL)) &&
@@ -500,16 +628,26 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
         // whatever other entry points queued on the caller's stream (camera, instances, uploads, clears) is ordered before the passes of
         // both lanes through ev_state, recorded BEFORE this pass is queued (a lane never waits for the other lane's pass)
         if (c->main_dirty) { RTX_CK(cudaEventRecord(c->ev_state, c->stream)); c->main_dirty = false; }
-        if (!(eligible && c->in_sequence)) {
+        if (c->pending_lane >= 0 && !eligible) RTX_ENTER(c);          // (cannot happen: the fast calls test the same conditions)
+        const int frame_lane = eligible ? c->pending_lane : -1;       // >= 0: a frame prepared by the fast rtx_set_instances [+ rtx_set_camera]
+        if (!(eligible && (c->in_sequence || frame_lane >= 0))) {
             // the first pass after any other call: B.parts path ranges on the caller's stream, accumulation included
+            if (c->cam_block_version[0] != c->cam_version) {
+                RTX_CK(cudaMemcpyAsync(c->wb.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, c->stream));
+                c->cam_block_version[0] = c->cam_version;
+            }
             if (c->cfg.flags & RTX_FLAG_LEGACY_RR) RTX_CK(wave_render_pass_legacy(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
             else if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
             else RTX_CK(wave_render_pass(c->wb, S, AS, first_sample + done, spp, c->stream, &c->launches, &c->timing));
             RTX_CK(cudaEventRecord(c->ev_acc[0], c->stream));
-            c->last_lane = 0;
+            c->last_lane = 0; c->lane_read_set[0] = 0;
         } else {
-            // a pass that directly follows another: the other lane, one path range, its accumulation behind the previous pass's
-            const int lane = 1 - c->last_lane;
+            // a pass that directly follows another (or a pipelined frame): the other lane, one path range, its accumulation behind the
+            // previous pass's
+            const int lane = frame_lane >= 0 ? frame_lane : 1 - c->last_lane;
+            const int set = frame_lane >= 0 ? frame_lane : c->cur_set;       // the per-frame state it reads
+            S.props = set ? c->fs1.d_props : c->d_props; S.inst_model = set ? c->fs1.d_inst_model : c->d_inst_model;
+            AS = make_as(c, set);
             WaveBuffers& B = lane ? c->wb2 : c->wb;
             PassTiming& T = lane ? c->timing2 : c->timing;
             const cudaStream_t st_ = c->lane_stream[lane];
@@ -520,20 +658,26 @@ extern "C" rtx_status rtx_render_pass(rtx_ctx* c, uint32_t first_sample, uint32_
                 if (!c->wb.use_graph) B.use_graph = false;
                 T.stage_timing = false; T.stats = nullptr;
             }
+            if (c->cam_block_version[lane] != c->cam_version) {              // the lane's camera block lags behind the last rtx_set_camera
+                RTX_CK(cudaMemcpyAsync(B.cam, &c->cam, sizeof c->cam, cudaMemcpyHostToDevice, st_));
+                c->cam_block_version[lane] = c->cam_version;
+            }
             if (c->cfg.flags & RTX_FLAG_FAST_MATH) RTX_CK(fast::wave_render_pass(B, S, AS, first_sample + done, spp, st_, &c->launches, &T, true, 1, true));
             else RTX_CK(wave_render_pass(B, S, AS, first_sample + done, spp, st_, &c->launches, &T, true, 1, true));
             RTX_CK(cudaStreamWaitEvent(st_, c->ev_acc[1 - lane], 0));                         // gPermanentData += in call order
             if (c->reduce_pending) RTX_CK(cudaStreamWaitEvent(st_, c->ev_reduced, 0));        // a pending multi-GPU reduce still reads it
+            if (c->resolve_pending) RTX_CK(cudaStreamWaitEvent(st_, c->ev_resolved, 0));      // ... or the resolve of the previous frame
             RTX_CK(wave_accumulate(B, npx, spp, st_));
             c->launches += 1;
             RTX_CK(cudaEventRecord(c->ev_acc[lane], st_));
             RTX_CK(cudaStreamWaitEvent(c->stream, c->ev_acc[lane], 0));     // stream-ordered API: the caller's stream sees the pass as done
-            c->last_lane = lane;
+            c->last_lane = lane; c->lane_read_set[lane] = set;
         }
-        c->in_sequence = true;
+        c->in_sequence = true; c->pending_lane = -1; c->fset_pending = false;
         done += spp;
     }
     c->pass_timed = true;
+    c->frame_seq_ok = true;         // a frame loop may go on from here (rtx_read_output_async / rtx_wait_output keep it, enter() ends it)
     return RTX_OK;
 }
 
@@ -648,7 +792,11 @@ static rtx_status ensure_side_stream(rtx_ctx* c) {
 // reduce: the render stream never waits for NCCL, the next pass overlaps reduce + resolve + copy.
 extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
     if (!c || !rgba8_out) return fail(RTX_ERR_ARG, "rtx_read_output_async: null argument");
-    RTX_ENTER(c);
+    RTX_CK(cudaSetDevice(c->cfg.device));
+    // a read-back right after a pass keeps a pipelined sequence alive: the resolve below runs on the caller's stream, which is behind the
+    // pass, and the next pass's accumulation waits for it (ev_resolved); from anywhere else it is an ordinary call
+    const bool keep = c->in_sequence && c->frame_seq_ok;
+    if (!keep) RTX_ENTER(c);
     rtx_status st;
     if ((st = ensure_wave(c)) != RTX_OK) return st;
     if ((st = ensure_side_stream(c)) != RTX_OK) return st;
@@ -661,6 +809,7 @@ extern "C" rtx_status rtx_read_output_async(rtx_ctx* c, uint8_t* rgba8_out) {
         RTX_CK(wave_resolve(c->wb, npx, c->stream, &c->launches));
         RTX_CK(cudaEventRecord(c->ev_resolved, c->stream));
         RTX_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved, 0));
+        c->resolve_pending = true;
     }
     RTX_CK(cudaMemcpyAsync(rgba8_out, c->wb.output, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->copy_stream));
     RTX_CK(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->copy_stream));   // for rtx_wait_output
@@ -993,6 +1142,7 @@ extern "C" rtx_status rtx_set_option(rtx_ctx* c, uint32_t option, uint32_t value
     else if (option == RTX_OPT_PASS_GRAPH) { c->wb.use_graph = value != 0; c->wb2.use_graph = value != 0; }
     else if (option == RTX_OPT_SHADOW_OVERLAP) c->wb.shadow_overlap = value != 0;
     else if (option == RTX_OPT_PASS_PIPELINE) c->pipeline = value != 0;
+    else if (option == RTX_OPT_FRAME_PIPELINE) c->frame_pipeline = value != 0;
     else if (option == RTX_OPT_PART_ROWS) { if (value > 64u && value != 0xffffffffu) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_PART_ROWS must be 0..64 or 0xffffffff (automatic)"); c->wb.part_rows = value == 0xffffffffu ? -1 : (int)value; }
     else if (option == RTX_OPT_TRACE_CTAS) { if (value > 32u) return fail(RTX_ERR_ARG, "rtx_set_option: RTX_OPT_TRACE_CTAS must be 0..32"); c->ctas_per_sm = (int)value; }
     else return fail(RTX_ERR_ARG, "rtx_set_option: unknown option");

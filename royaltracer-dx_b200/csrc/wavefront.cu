@@ -635,13 +635,13 @@ static cudaError_t wave_alloc_impl(WaveBuffers* B, const WaveBuffers* shared, ui
     CKE(cudaMemset(B->cursor, 0, WAVE_MAX_PARTS * 16));      // launch_trace keeps the cursor words at zero between launches
     CKE(cudaMalloc((void**)&B->ray_counters, 8 * 8));
     CKE(cudaMemset(B->ray_counters, 0, 64));
-    if (shared) { B->accum = shared->accum; B->output = shared->output; B->cam = shared->cam; }
+    if (shared) { B->accum = shared->accum; B->output = shared->output; }
     else {
         CKE(cudaMalloc((void**)&B->accum, (size_t)npx * 16));
         CKE(cudaMemset(B->accum, 0, (size_t)npx * 16));
         CKE(cudaMalloc((void**)&B->output, (size_t)npx * 4));
-        CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));
     }
+    CKE(cudaMalloc((void**)&B->cam, sizeof(rtx_camera_params)));     // (a lane has its own camera block: pipelined frames)
     CKE(cudaMalloc((void**)&B->first_sample, 4));
     CKE(cudaMalloc((void**)&B->debug, 64 * 4));
     CKE(cudaMalloc((void**)&B->perm, (size_t)n * 4));
@@ -655,7 +655,7 @@ cudaError_t wave_alloc_lane(WaveBuffers* L, const WaveBuffers& B, uint32_t width
     return wave_alloc_impl(L, &B, width, height, spp);
 }
 void wave_free_lane(WaveBuffers* L) {
-    L->accum = nullptr; L->output = nullptr; L->cam = nullptr;       // owned by the context's first set
+    L->accum = nullptr; L->output = nullptr;       // owned by the context's first set
     wave_free(L);
 }
 

@@ -100,7 +100,7 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
                              cudaStream_t stream, uint64_t* launches, PassTiming* timing, bool accumulate = true, int parts_override = 0,
                              bool defer_accumulate = false);
 }
-// a second set of pass buffers that shares gPermanentData, gOutput and the camera block with `B` (pipelined passes, api.cu)
+// a second set of pass buffers that shares gPermanentData and gOutput with `B` (pipelined passes, api.cu)
 cudaError_t wave_alloc_lane(WaveBuffers* L, const WaveBuffers& B, uint32_t width, uint32_t height, uint32_t spp);
 void wave_free_lane(WaveBuffers* L);
 // The reference's legacy estimator (include/RayGen.hlsl + include/Hit.hlsl) as a wavefront: legacy.cu.  S.bounces caps the path length.

@@ -686,6 +686,70 @@ def test_pipelined_passes_are_bit_identical(rtdx, orc):
     ctx.close()
 
 
+def test_pipelined_frames_are_bit_identical(rtdx, orc):
+    """RTX_OPT_FRAME_PIPELINE: a per-frame loop in the reference's order (rtx_set_instances with a moving instance, rtx_set_camera,
+    rtx_render_pass, rtx_read_output_async with one frame in flight) on a one-node TLAS keeps two sets of per-frame state and overlaps
+    consecutive frames.  The accumulation equals the oracle's frame by frame sum (each sample rendered with that frame's transforms),
+    every frame's RGBA8 image equals the one of the same loop with the option off, a camera change in the middle resets the
+    accumulation between the right two frames, and calls that leave the pattern (a blocking read, a trace) see the newest state."""
+    import torch
+    sc = rtdx.scenes.mesh_room(n=16)
+    W, H, bounces, n_frames = 384, 192, 2, 8
+    base = [np.asarray(i[1], dtype=np.float64).reshape(4, 4).T for i in sc.instances]          # column-vector 4x4
+    model_ids = [i[0] for i in sc.instances]
+    cam2 = rtdx.camera_params((sc.eye[0] + 0.25, sc.eye[1], sc.eye[2]), sc.center, sc.up, W / float(H))
+
+    def xforms(f):
+        out = []
+        for k, m in enumerate(base):
+            m2 = m.copy()
+            if k == 1:
+                m2[0, 3] += 0.03 * f; m2[1, 3] += 0.01 * f                                    # the mesh moves, the room (and its light) stays
+            out.append(rtdx.xmmatrix_from_colvec(m2))
+        return out
+
+    def loop(pipeline, osc=None):
+        ctx, up = _upload(rtdx, sc, W, H, bounces=bounces)
+        ctx.set_option(rtdx.OPT_FRAME_PIPELINE, pipeline)
+        pinned = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        images, ref, prev = [], None, up["props"]
+        cam = up["camera"]
+        for f in range(n_frames):
+            props, descs = rtdx.instance_properties(xforms(f), [up["model_ids"][m] for m in model_ids])
+            props["prevObjectToWorld"] = prev["objectToWorld"]; props["prevObjectToWorldInverse"] = prev["objectToWorldInverse"]
+            props["prevObjectToWorldNormal"] = prev["objectToWorldNormal"]
+            prev = props
+            ctx.set_instances(descs, props)
+            if f == 5:
+                cam = cam2.copy()
+            ctx.set_camera(cam)
+            ctx.render_pass(f, 1)
+            if f > 0:
+                ctx.wait_output(); images.append(pinned[(f - 1) & 1].copy())
+            ctx.read_output_async(pinned[f & 1])
+            if osc is not None:
+                osc.set_props(props)
+                img, _ = osc.render(cam, W, H, f, 1, bounces=bounces, flags=0)
+                ref = img if (ref is None or f == 5) else ref + img                            # the view change resets gPermanentData
+        ctx.wait_output(); images.append(pinned[(n_frames - 1) & 1].copy())
+        accum = ctx.read_accum()                                                               # (leaves the pattern: enter())
+        rays = rtdx.scenes.camera_rays(cam, 96, 48)
+        hits = ctx.trace(rays)                                                                 # sees the LAST frame's transforms
+        ctx.close()
+        return images, accum, ref, hits, props
+
+    ctx0, up0 = _upload(rtdx, sc, W, H, bounces=bounces)
+    osc = orc.OracleScene(sc, up0["props"], up0["lights"])
+    ctx0.close()
+    img_on, acc_on, ref, hits_on, last_props = loop(1, osc)
+    img_off, acc_off, _, hits_off, _ = loop(0)
+    assert np.array_equal(bits(acc_on), bits(ref)) and np.array_equal(bits(acc_off), bits(ref))
+    assert len(img_on) == n_frames and all(np.array_equal(a, b) for a, b in zip(img_on, img_off))
+    osc.set_props(last_props)
+    rays = rtdx.scenes.camera_rays(cam2, 96, 48)
+    _assert_hits_equal(hits_on, osc.trace(rays, mode=1)); _assert_hits_equal(hits_off, hits_on)
+
+
 def test_device_arithmetic_fast_paths_exhaustive(rtdx):
     """csrc/dmath.cuh: the hand-scheduled rsqrt (and shared-reciprocal divide) equal the IEEE operations the oracle defines
     (oracle/det_math.h) on every one of the 2^32 binary32 bit patterns — checked on the device, tolerance 0."""

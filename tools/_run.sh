@@ -1,7 +1,11 @@
 #!/bin/bash
-# scratch runner for gpurun calls: edit, run as `gpurun -- 'bash tools/_run.sh'`; outputs under gpurun_out/
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r02_s6_bench_n1.json 2> gpurun_out/bench_err.log
-tail -1 gpurun_out/r02_s6_bench_n1.json | cut -c1-200
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_s6_bench_reference_arm.json 2>> gpurun_out/bench_err.log
-tail -1 gpurun_out/r02_s6_bench_reference_arm.json | cut -c1-200
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/gpu_tests.log
+cat gpurun_out/gpu_tests.log
+S=gpurun_out/sanitizer4.txt; : > $S
+timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pipelined or async_readback or instance_list_changes" >> $S 2>&1; echo "memcheck tests rc=$?" >> $S
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "racecheck smoke rc=$?" >> $S
+grep -E "SUMMARY|rc=|passed|failed|Error" $S
+python bench.py --no-extras --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench value', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],3), 'launches', d['gpu_launches'])"
