@@ -1,11 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/gpu_tests.log
-cat gpurun_out/gpu_tests.log
 S=gpurun_out/sanitizer4.txt; : > $S
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pipelined or async_readback or instance_list_changes" >> $S 2>&1; echo "memcheck tests rc=$?" >> $S
+timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pipelined or async_readback or instance_list_changes or concurrent_pass_parts or graph_replay or engine_side_reduce or restir_frames_in" >> $S 2>&1; echo "memcheck tests rc=$?" >> $S
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "memcheck smoke rc=$?" >> $S
 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "racecheck smoke rc=$?" >> $S
+timeout 900 compute-sanitizer --tool initcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" >> $S 2>&1; echo "initcheck smoke rc=$?" >> $S
 grep -E "SUMMARY|rc=|passed|failed|Error" $S
-python bench.py --no-extras --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench value', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],3), 'launches', d['gpu_launches'])"
