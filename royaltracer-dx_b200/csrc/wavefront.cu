@@ -672,7 +672,7 @@ void wave_free(WaveBuffers* B) {
     }
     if (B->state) cudaFree(B->state);
     for (int i = 0; i < 2; i++) { free_queue(&B->q[i]); free_queue(&B->sq[i]); }
-    if (B->graph_exec) cudaGraphExecDestroy(B->graph_exec);
+    for (auto& g : B->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     void* ptrs[] = {B->seeds, B->first_sample, B->hit_a, B->hit_inst, B->vis_di, B->vis_gi, B->counts, B->cursor, B->ray_counters, B->accum, B->output, B->cam, B->debug, B->perm, B->bin_keys, B->bins};
     for (void* p : ptrs) if (p) cudaFree(p);
     *B = WaveBuffers();
@@ -856,7 +856,7 @@ static cudaError_t wave_pass_body(WaveBuffers& B, const SceneData& S, const Scen
 
 // What a captured pass depends on besides the sample index: every kernel argument is in here (device pointers, counts, flags, bounds).
 struct GraphKey { SceneData S; SceneAS AS; uint32_t spp; int parts; int variant; int side_shadow; cudaStream_t stream; };
-static_assert(sizeof(GraphKey) <= sizeof(WaveBuffers().graph_key), "WaveBuffers::graph_key too small");
+static_assert(sizeof(GraphKey) <= sizeof(WaveBuffers().last_key), "WaveBuffers::last_key / GraphSlot::key too small");
 
 cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& AS, uint32_t first_sample, uint32_t spp, cudaStream_t stream,
                              uint64_t* launches, PassTiming* T, bool accumulate, int parts_override, bool defer_accumulate) {
@@ -881,7 +881,8 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     // ---- CUDA graph of the pass.  A pass is ~50 dependent launches per path range plus memsets and the fork / join of the auxiliary
     // streams; for a static configuration (same buffers, counts, flags, bounds as the pass before) the sequence is captured once and
     // replayed: one graph launch per pass instead of ~100 stream operations.  The first pass of a new configuration runs directly, the
-    // second one captures (a scene whose instances move every frame never pays for captures).  Passes with per-launch events, the
+    // second one captures (a scene whose instance LIST changes every frame never pays for captures; transforms that move do not
+    // change the configuration: the buffers are rewritten in place).  Passes with per-launch events, the
     // counting variant, the ReSTIR frame or a pending multi-GPU reduce (an event from outside the capture) always run directly.
     const bool graph_ok = B.use_graph && accumulate && !T->stage_timing && !T->stats && (defer_accumulate || !B.wait_before_accumulate);
     GraphKey key;
@@ -895,10 +896,16 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
     CKE(cudaEventRecord(T->ev[0], stream));
     bool done = false;
     if (graph_ok) {
-        if (B.graph_exec && memcmp(&key, B.graph_key, sizeof key) != 0 && B.have_last_key && memcmp(&key, B.last_key, sizeof key) == 0) {
-            cudaGraphExecDestroy(B.graph_exec); B.graph_exec = nullptr;        // the configuration changed and has settled again
-        }
-        if (!B.graph_exec && B.have_last_key && memcmp(&key, B.last_key, sizeof key) == 0) {
+        // a small cache of captured passes: a context alternates between a few configurations (the first pass of a sequence and the
+        // pipelined ones, the two sets of per-frame state), none of them should evict the others
+        WaveBuffers::GraphSlot* slot = nullptr;
+        for (auto& g : B.graphs) if (g.exec && memcmp(&key, g.key, sizeof key) == 0) slot = &g;
+        // A pipelined pass (defer_accumulate) is captured the first time it is seen: the configurations of the two lanes are stable by
+        // construction, and a capture in the middle of a sequence stalls it.  Any other pass is captured when it repeats the one before.
+        if (!slot && (defer_accumulate || (B.have_last_key && memcmp(&key, B.last_key, sizeof key) == 0))) {
+            WaveBuffers::GraphSlot* victim = &B.graphs[0];
+            for (auto& g : B.graphs) if (!g.exec) { victim = &g; break; } else if (g.last_used < victim->last_used) victim = &g;
+            if (victim->exec) { cudaGraphExecDestroy(victim->exec); victim->exec = nullptr; }
             cudaGraph_t g = nullptr;
             uint64_t L = 0;
             cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
@@ -907,18 +914,20 @@ cudaError_t wave_render_pass(WaveBuffers& B, const SceneData& S, const SceneAS& 
                 const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
                 if (e == cudaSuccess) e = e2;
             }
-            if (e == cudaSuccess) e = cudaGraphInstantiate(&B.graph_exec, g, 0);
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&victim->exec, g, 0);
             if (g) cudaGraphDestroy(g);
-            if (e != cudaSuccess) {            // no graph for this context then: the direct path below is always valid
+            if (e != cudaSuccess) {            // no graphs for this context then: the direct path below is always valid
                 cudaGetLastError();
-                B.graph_exec = nullptr; B.use_graph = false;
+                victim->exec = nullptr; B.use_graph = false;
             } else {
-                memcpy(B.graph_key, &key, sizeof key); B.graph_launches = L;
+                memcpy(victim->key, &key, sizeof key); victim->launches = L;
+                slot = victim;
             }
         }
-        if (B.graph_exec && memcmp(&key, B.graph_key, sizeof key) == 0) {
-            CKE(cudaGraphLaunch(B.graph_exec, stream));
-            if (launches) *launches += B.graph_launches;
+        if (slot) {
+            CKE(cudaGraphLaunch(slot->exec, stream));
+            slot->last_used = ++B.graph_clock;
+            if (launches) *launches += slot->launches;
             T->n_marks = 0;
             done = true;
         }

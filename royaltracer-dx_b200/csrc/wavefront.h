@@ -64,8 +64,9 @@ struct WaveBuffers {
     const float4* resolve_source = nullptr;   // rtx_set_resolve_source: an external accumulation buffer (the multi-GPU sum) to resolve instead
     uint32_t* first_sample = nullptr;  // device word: the sample index of the pass being rendered (k_generate reads it)
     // CUDA graph of a pass (wavefront.cu wave_render_pass): replayed while the configuration (graph_key) stays what was captured
-    bool use_graph = true, have_last_key = false; cudaGraphExec_t graph_exec = nullptr; uint64_t graph_launches = 0;
-    unsigned char graph_key[512] = {}, last_key[512] = {};
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t launches = 0, last_used = 0; unsigned char key[512] = {}; };
+    bool use_graph = true, have_last_key = false; GraphSlot graphs[4]; uint64_t graph_clock = 0;
+    unsigned char last_key[512] = {};
     cudaEvent_t wait_before_accumulate = nullptr;   // multi-GPU: the pending reduce of gPermanentData (k_accumulate rewrites it)
     float4* accum = nullptr;           // gPermanentData
     uint8_t* output = nullptr;         // gOutput slice 0
