@@ -107,7 +107,11 @@ rtx_status rtx_set_emissive_triangles(rtx_ctx*, const rtx_light_triangle* l, uin
 /* binding b0 (rdn/Renderer.cpp:1722-1768); a view change resets the accumulation (Pass_spat_di_v7.hlsl:407-423) */
 rtx_status rtx_set_camera(rtx_ctx*, const rtx_camera_params*);
 /* replaces the DispatchRays sequence (rdn/Renderer.cpp:611-673): renders samples [first_sample, first_sample+n_samples)
- * of every pixel with estimator E0 and accumulates them (gPermanentData).  Asynchronous on the context stream. */
+ * of every pixel with estimator E0 and accumulates them (gPermanentData).  Asynchronous and ordered on the context stream: work
+ * queued there before the call is seen by the pass, work queued there after the call runs after the pass.  Calls that directly follow
+ * each other (and whole frames rtx_set_instances -> rtx_set_camera -> rtx_render_pass -> rtx_read_output_async on a TLAS of <= 8
+ * instances) overlap on internal streams; gPermanentData receives them in call order, the results are bit-identical to running them
+ * one after the other (RTX_OPT_PASS_PIPELINE, RTX_OPT_FRAME_PIPELINE). */
 rtx_status rtx_render_pass(rtx_ctx*, uint32_t first_sample, uint32_t n_samples);
 /* One frame of the reference's dispatch sequence (rdn/Renderer.cpp:611-673): DispatchRays RayGen (pass 1, 1 spp, sample
  * index = frame_index) -> RayGen2 (temporal reuse against last frame's reservoirs, reprojected with prevView/prevProjection
