@@ -108,6 +108,16 @@ def test_abi_library_exports_every_declared_symbol(rtdx):
         assert hasattr(host, name)
 
 
+def test_python_constants_equal_the_header(rtdx):
+    """Every RTX_FLAG_* / RTX_OPT_* of include/rtx_b200.h has a Python constant of the same value (the bindings of tests and bench)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rtx_b200.h")).read()
+    defs = dict((m.group(1), int(m.group(2), 0)) for m in re.finditer(r"#define\s+RTX_((?:FLAG|OPT)_\w+)\s+(0x[0-9a-fA-F]+|\d+)u", hdr))
+    assert len([k for k in defs if k.startswith("OPT_")]) >= 14 and len([k for k in defs if k.startswith("FLAG_")]) >= 6
+    for name, value in defs.items():
+        assert getattr(rtdx, name) == value, name
+
+
 def test_abi_struct_sizes_match_reference_layouts(rtdx):
     assert rtdx.vertex_dt.itemsize == 28 and rtdx.material_dt.itemsize == 128       # S1, S4
     assert rtdx.props_dt.itemsize == 384 and rtdx.light_dt.itemsize == 80           # S6, S7
