@@ -247,6 +247,15 @@ def test_legacy_estimator_equals_the_reference_text(rtdx, orc, name, bounces):
     the legacy text's older Material / InstanceProperties / LightTriangle layouts are filled field by field (ref_legacy_harness.cpp)."""
     if not ref.legacy_available(bounces):
         pytest.skip("libref_legacy_b%d.so not built" % bounces)
+    from oracle.ref import make_ref
+    if os.path.isdir(make_ref.INCLUDE) and name == "cornell":      # the filter touches spellings only, here too
+        import difflib
+        for unit in ("leg_rg", "leg_hit"):
+            src = make_ref.expand(make_ref.LEGACY_UNITS[unit]).split()
+            gen = make_ref.filtered_legacy(make_ref.LEGACY_UNITS[unit], bounces).split()
+            sm = difflib.SequenceMatcher(None, src, gen, autojunk=False)
+            touched = [t for tag, i1, i2, j1, j2 in sm.get_opcodes() if tag != "equal" for t in src[i1:i2]]
+            assert sm.ratio() > 0.9 and len(touched) < 0.12 * len(src), (unit, sm.ratio(), len(touched), len(src))
     W, H = 40, 24
     sc = SCENES[name](rtdx)
     props, descs, lights, cam = host_inputs(rtdx, sc, W, H)
