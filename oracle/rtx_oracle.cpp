@@ -42,7 +42,7 @@ constexpr uint32_t MISS_ID = 4294967294u;   // shaders/Miss_v7.hlsl:7
 
 // ------------------------------------------------------------------------------------------ scene
 struct Box { f3 lo, hi; };
-struct Node2 { Box b; uint32_t left, right; uint32_t first, count; };   // count>0 => leaf
+struct Node2 { Box b; uint32_t left, right; uint32_t first, count; uint32_t axis; };   // count>0 => leaf; axis: the split axis (left = the lower side)
 
 struct Model {
     std::vector<f3> pos;
@@ -64,6 +64,7 @@ struct orc_scene {
     std::vector<orc_material> materials;
     std::vector<Instance> instances;
     std::vector<orc_light_tri> lights;
+    std::vector<Node2> tlas; std::vector<uint32_t> tlas_order;     // BVH2 over the instances' world boxes (orc_build)
     orc_counters* ctr = nullptr;
 };
 
@@ -141,14 +142,100 @@ inline void box_pad(Box& b, float pad) {
     b.hi = mk3(b.hi.x + pad, b.hi.y + pad, b.hi.z + pad);
 }
 
+// Top-down BVH2 over primitive boxes: median split of the widest axis, or (sah) the binned surface-area heuristic (16 bins per axis, all
+// three axes) with the median split where the bins cannot separate anything.  Children are visited nearer side first.  The oracle's hits do not depend on the tree (closest = lexicographic minimum of
+// (t, instance, primitive) over everything the conservative boxes let through; tests compare with the brute-force mode); a decent tree
+// only makes the CPU arm of bench.py a fairer baseline and the parity tests at full size faster.
+inline float box_half_area(const Box& b) {
+    const float dx = b.hi.x - b.lo.x, dy = b.hi.y - b.lo.y, dz = b.hi.z - b.lo.z;
+    return (dx * dy + dy * dz) + dz * dx;
+}
+void build_tree(const std::vector<Box>& tb, const std::vector<f3>& cen, float pad, uint32_t leaf_max, bool sah, std::vector<uint32_t>& order,
+                std::vector<Node2>& nodes) {
+    const uint32_t nt = (uint32_t)tb.size();
+    order.resize(nt);
+    for (uint32_t t = 0; t < nt; t++) order[t] = t;
+    nodes.clear();
+    if (nt == 0) return;
+    nodes.reserve(2 * nt);
+    struct Job { uint32_t node, first, count; };
+    std::vector<Job> stack;
+    nodes.push_back(Node2{});
+    stack.push_back({0u, 0u, nt});
+    const int NB = 16;
+    while (!stack.empty()) {
+        Job j = stack.back(); stack.pop_back();
+        Box b = box_empty(), cb = box_empty();
+        for (uint32_t i = j.first; i < j.first + j.count; i++) {
+            uint32_t t = order[i];
+            box_grow(b, tb[t].lo); box_grow(b, tb[t].hi); box_grow(cb, cen[t]);
+        }
+        box_pad(b, pad);
+        nodes[j.node].b = b; nodes[j.node].axis = 0;
+        f3 ext = cb.hi - cb.lo;
+        int wide = 0; if (ext.y > ext.x) wide = 1; if (ext.z > comp(ext, wide)) wide = 2;
+        if (j.count <= leaf_max || !(comp(ext, wide) > 0.0f)) {
+            Node2& n = nodes[j.node];
+            n.first = j.first; n.count = j.count; n.left = n.right = 0;
+            continue;
+        }
+        // binned SAH
+        int best_axis = -1, best_split = 0; float best_cost = INFINITY;
+        for (int axis = 0; sah && axis < 3; axis++) {
+            const float lo = comp(cb.lo, axis), e = comp(ext, axis);
+            if (!(e > 0.0f)) continue;
+            const float k = (float)NB / e;
+            uint32_t cnt[NB] = {0}; Box bb[NB];
+            for (int q = 0; q < NB; q++) bb[q] = box_empty();
+            for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                const uint32_t t = order[i];
+                int q = (int)((comp(cen[t], axis) - lo) * k); q = q < 0 ? 0 : (q >= NB ? NB - 1 : q);
+                cnt[q]++; box_grow(bb[q], tb[t].lo); box_grow(bb[q], tb[t].hi);
+            }
+            float la[NB]; uint32_t lc[NB]; Box acc = box_empty(); uint32_t c = 0;
+            for (int q = 0; q < NB - 1; q++) { if (cnt[q]) { box_grow(acc, bb[q].lo); box_grow(acc, bb[q].hi); } c += cnt[q]; la[q] = c ? box_half_area(acc) : 0.0f; lc[q] = c; }
+            acc = box_empty(); c = 0;
+            for (int q = NB - 1; q >= 1; q--) {
+                if (cnt[q]) { box_grow(acc, bb[q].lo); box_grow(acc, bb[q].hi); } c += cnt[q];
+                const uint32_t nl = lc[q - 1];
+                if (nl == 0 || c == 0) continue;
+                const float cost = la[q - 1] * (float)nl + box_half_area(acc) * (float)c;
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = q; }       // bins [0, q) left, [q, NB) right
+            }
+        }
+        uint32_t mid;
+        int axis;
+        if (best_axis >= 0) {
+            axis = best_axis;
+            const float lo = comp(cb.lo, axis), k = (float)NB / comp(ext, axis);
+            auto it = std::stable_partition(order.begin() + j.first, order.begin() + j.first + j.count, [&](uint32_t t) {
+                int q = (int)((comp(cen[t], axis) - lo) * k); q = q < 0 ? 0 : (q >= NB ? NB - 1 : q);
+                return q < best_split;
+            });
+            mid = (uint32_t)(it - order.begin());
+        } else {
+            axis = wide;
+            mid = j.first + j.count / 2;
+            std::nth_element(order.begin() + j.first, order.begin() + mid, order.begin() + j.first + j.count, [&](uint32_t a, uint32_t c) {
+                float ca = comp(cen[a], axis), cc = comp(cen[c], axis);
+                return ca < cc || (ca == cc && a < c);
+            });
+        }
+        uint32_t l = (uint32_t)nodes.size();
+        nodes.push_back(Node2{}); nodes.push_back(Node2{});
+        Node2& n2 = nodes[j.node];
+        n2.count = 0; n2.first = 0; n2.left = l; n2.right = l + 1; n2.axis = (uint32_t)axis;
+        stack.push_back({l, j.first, mid - j.first});
+        stack.push_back({l + 1, mid, j.first + j.count - mid});
+    }
+}
+
 void build_bvh2(Model& m) {
     uint32_t nt = (uint32_t)m.idx.size() / 3;
-    m.order.resize(nt);
     std::vector<f3> cen(nt);
     std::vector<Box> tb(nt);
     Box all = box_empty();
     for (uint32_t t = 0; t < nt; t++) {
-        m.order[t] = t;
         Box b = box_empty();
         for (int k = 0; k < 3; k++) box_grow(b, m.pos[m.idx[3 * t + k]]);
         tb[t] = b;
@@ -162,42 +249,9 @@ void build_bvh2(Model& m) {
     }
     float pad = scale * 3.0517578125e-5f + 1e-30f;   // 2^-15 of the model's scale
     m.bounds = all; box_pad(m.bounds, pad);
-    m.nodes.clear();
-    if (nt == 0) return;
-    m.nodes.reserve(2 * nt);
-    struct Job { uint32_t node, first, count; };
-    std::vector<Job> stack;
-    m.nodes.push_back(Node2{});
-    stack.push_back({0u, 0u, nt});
-    while (!stack.empty()) {
-        Job j = stack.back(); stack.pop_back();
-        Box b = box_empty(), cb = box_empty();
-        for (uint32_t i = j.first; i < j.first + j.count; i++) {
-            uint32_t t = m.order[i];
-            box_grow(b, tb[t].lo); box_grow(b, tb[t].hi); box_grow(cb, cen[t]);
-        }
-        box_pad(b, pad);
-        Node2& n = m.nodes[j.node];
-        n.b = b;
-        f3 ext = cb.hi - cb.lo;
-        int axis = 0; if (ext.y > ext.x) axis = 1; if (ext.z > comp(ext, axis)) axis = 2;
-        if (j.count <= 4 || comp(ext, axis) <= 0.0f) {
-            n.first = j.first; n.count = j.count; n.left = n.right = 0;
-            continue;
-        }
-        uint32_t mid = j.first + j.count / 2;
-        std::nth_element(m.order.begin() + j.first, m.order.begin() + mid, m.order.begin() + j.first + j.count,
-                         [&](uint32_t a, uint32_t c) {
-                             float ca = comp(cen[a], axis), cc = comp(cen[c], axis);
-                             return ca < cc || (ca == cc && a < c);
-                         });
-        uint32_t l = (uint32_t)m.nodes.size();
-        m.nodes.push_back(Node2{}); m.nodes.push_back(Node2{});
-        Node2& n2 = m.nodes[j.node];
-        n2.count = 0; n2.first = 0; n2.left = l; n2.right = l + 1;
-        stack.push_back({l, j.first, mid - j.first});
-        stack.push_back({l + 1, mid, j.first + j.count - mid});
-    }
+    // (median splits for the models: measured on the bench scene the CPU arm is bound by its shading arithmetic, the binned SAH bought
+    // nothing there and triples the build time of the 10 M-triangle parity scenes)
+    build_tree(tb, cen, pad, 4u, false, m.order, m.nodes);
 }
 
 struct Hit { float t, b1, b2; uint32_t prim, inst; };
@@ -246,8 +300,10 @@ bool trace_instance(const orc_scene& S, uint32_t ii, f3 wo, f3 wd, float tmin, f
         if (!box_test(n.b, o, inv, tmin, far)) continue;
         if (n.count) {
             for (uint32_t i = 0; i < n.count; i++) if (test_tri(M.order[n.first + i])) return true;
-        } else {
+        } else if (comp(d, (int)n.axis) < 0.0f) {       // the nearer child is popped first (the left one holds the lower side of the axis)
             stack[sp++] = n.left; stack[sp++] = n.right;
+        } else {
+            stack[sp++] = n.right; stack[sp++] = n.left;
         }
     }
     return false;
@@ -256,6 +312,24 @@ bool trace_instance(const orc_scene& S, uint32_t ii, f3 wo, f3 wd, float tmin, f
 bool trace(const orc_scene& S, f3 o, f3 d, float tmin, float tmax, bool any_hit, int mode, Hit& best, orc_counters& C) {
     best.t = tmax; best.b1 = best.b2 = 0.0f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
     f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    if (mode != 0 && !S.tlas.empty()) {             // the instances through their own BVH2 (1000 of them in BASELINE config C3)
+        uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const Node2& n = S.tlas[stack[--sp]];
+            float far = (best.inst == 0xFFFFFFFFu || any_hit) ? tmax : fminf(tmax, best.t);
+            if (!box_test(n.b, o, inv, tmin, far)) continue;
+            if (n.count) {
+                for (uint32_t k = 0; k < n.count; k++) {
+                    const uint32_t i = S.tlas_order[n.first + k];
+                    far = (best.inst == 0xFFFFFFFFu || any_hit) ? tmax : fminf(tmax, best.t);
+                    if (!box_test(S.instances[i].wbox, o, inv, tmin, far)) continue;
+                    if (trace_instance(S, i, o, d, tmin, tmax, any_hit, mode, best, C)) return true;
+                }
+            } else if (comp(d, (int)n.axis) < 0.0f) { stack[sp++] = n.left; stack[sp++] = n.right; }
+            else { stack[sp++] = n.right; stack[sp++] = n.left; }
+        }
+        return best.inst != 0xFFFFFFFFu;
+    }
     for (uint32_t i = 0; i < (uint32_t)S.instances.size(); i++) {
         if (mode != 0) {
             float far = (best.inst == 0xFFFFFFFFu || any_hit) ? tmax : fminf(tmax, best.t);
@@ -1510,7 +1584,7 @@ void orc_set_instances(orc_scene* s, const uint32_t* model_ids, const orc_instan
 void orc_set_lights(orc_scene* s, const orc_light_tri* l, uint32_t n) { s->lights.assign(l, l + n); }
 
 void orc_build(orc_scene* s) {
-    for (auto& m : s->models) build_bvh2(m);
+    for (auto& m : s->models) if (m.nodes.empty()) build_bvh2(m);       // (models never change after orc_add_model; orc_build runs again after every instance update)
     for (auto& in : s->instances) {
         const Model& m = s->models[in.model];
         Box w = box_empty();
@@ -1524,6 +1598,17 @@ void orc_build(orc_scene* s) {
             box_pad(w, sc * 3.0517578125e-5f + 1e-30f);
         }
         in.wbox = w;
+    }
+    s->tlas.clear(); s->tlas_order.clear();
+    if (s->instances.size() > 4) {
+        std::vector<Box> ib; std::vector<f3> ic;
+        for (const auto& in : s->instances) {
+            Box w = in.wbox;
+            if (!(w.lo.x <= w.hi.x)) { w.lo = mk3(0, 0, 0); w.hi = mk3(0, 0, 0); }      // an instance of an empty model
+            ib.push_back(w);
+            ic.push_back(mk3(0.5f * (w.lo.x + w.hi.x), 0.5f * (w.lo.y + w.hi.y), 0.5f * (w.lo.z + w.hi.z)));
+        }
+        build_tree(ib, ic, 0.0f, 2u, true, s->tlas_order, s->tlas);
     }
 }
 
