@@ -237,6 +237,33 @@ def test_trace_known_answers_and_bvh_equals_brute_force(rtdx, orc):
     assert np.array_equal(osc.trace(r, any_hit=True, mode=1)["inst"] != rtdx.MISS, a["inst"] != rtdx.MISS)
 
 
+def test_instance_tree_of_the_ray_caster_equals_brute_force(rtdx, orc):
+    """The oracle's ray caster walks a BVH2 over the instances' world boxes when there are more than four (BASELINE config C3 has 1000),
+    nearer child first; hits, ties and any-hit answers equal the brute-force definition (mode 0), also after the instances moved and
+    with coincident instances."""
+    from util import random_rays
+    sc = rtdx.scenes.instanced_blobs(n_models=3, n_side=5, lattice=4)                 # 64 instances
+    sc.add_instance(sc.instances[0][0], np.asarray(sc.instances[0][1]).reshape(4, 4).T)   # a copy on top of instance 0: ties go to the lower id
+    props, descs, lights, cam = host_inputs(rtdx, sc, 64, 64)
+    osc = orc.OracleScene(sc, props, lights)
+    rng = np.random.RandomState(8)
+    rays = np.concatenate([rtdx.scenes.camera_rays(cam, 64, 64), random_rays(rtdx, rng, 8000, (-3, -3, -3), (3, 3, 3))])
+    rays["tmax"][::7] = 1.5                                                            # short rays: the far-side culling
+    a, b = osc.trace(rays, mode=0), osc.trace(rays, mode=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a["inst"] != rtdx.MISS).mean() > 0.2
+    assert (a["inst"] != len(sc.instances) - 1).all()                                  # the coincident copy never wins a tie
+    assert np.array_equal(osc.trace(rays, any_hit=True, mode=1)["inst"] != rtdx.MISS, a["inst"] != rtdx.MISS)
+    xf = []
+    for k, inst in enumerate(sc.instances):
+        m = np.asarray(inst[1], dtype=np.float64).reshape(4, 4).T.copy()
+        m[0, 3] += 0.4 * ((k % 3) - 1); m[2, 3] -= 0.2 * (k % 2)
+        xf.append(rtdx.xmmatrix_from_colvec(m))
+    moved, _ = rtdx.instance_properties(xf, [i[0] for i in sc.instances])
+    osc.set_props(moved)
+    a, b = osc.trace(rays, mode=0), osc.trace(rays, mode=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_closest_hit_tie_break_is_smallest_instance_then_primitive(rtdx, orc):
     """Two coincident copies of the same model: the contract picks the smaller instance id at equal t."""
     sc = rtdx.scenes.cornell()
