@@ -89,6 +89,41 @@ def test_bsdf_functions_equal_the_reference(rtdx, orc):
     assert not bad, "ops differing from the reference (of %d inputs each): %s" % (N, bad)
 
 
+def test_bsdf_functions_equal_the_reference_on_hostile_inputs(rtdx, orc):
+    """The same eight BSDF entry points with zero, negative-zero, denormal, huge, infinite and NaN components in the normal, incidence and
+    outgoing vectors (a quarter of all components): every result equals the reference text's bit for bit (a NaN equals any NaN)."""
+    sc = rtdx.scenes.mesh_room(n=4)
+    props, descs, lights, cam = host_inputs(rtdx, sc, 8, 8)
+    osc = orc.OracleScene(sc, props, lights)
+    rs = ref.RefScene(sc, props, lights, osc)
+    L, O = ref.lib(), orc.lib()
+    n_mat = len(sc.materials)
+    specials = [0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, np.inf, -np.inf, np.nan, 1e-45, 0.5, 3.4e38]
+    rng = np.random.RandomState(5)
+
+    def vec():
+        v = rng.normal(size=3).astype(np.float32)
+        v /= np.linalg.norm(v)
+        for c in range(3):
+            if rng.rand() < 0.25:
+                v[c] = np.float32(specials[rng.randint(len(specials))])
+        return v
+    bad = {}
+    for k in range(4000):
+        n, i, o = vec(), vec(), vec()
+        mat = int(rng.randint(0, n_mat + 1))
+        for op in range(8):
+            seed = rng.randint(0, 2 ** 32, size=2, dtype=np.uint64).astype(np.uint32)
+            sa, sb = seed.copy(), seed.copy()
+            a = np.zeros(4, dtype=np.float32); b = np.zeros(4, dtype=np.float32)
+            L.ref_kat_bsdf(op, mat, _p(n), _p(i), _p(o), _p(sa), _p(a))
+            O.orc_kat_bsdf(osc.h, op, mat, _p(n), _p(i), _p(o), _p(sb), _p(b))
+            same = np.array_equal(sa, sb) and all((np.isnan(x) and np.isnan(y)) or bits(np.float32(x) + 0) == bits(np.float32(y) + 0) for x, y in zip(a, b))
+            if not same:
+                bad[op] = bad.get(op, 0) + 1
+    assert not bad, bad
+
+
 def test_reservoir_updates_equal_the_reference(orc):
     """UpdateReservoir / UpdateReservoir_GI (Reservoir_v7.hlsl:30-80) through the pass-1 comparison below; here the uint16 M arithmetic."""
     L = ref.lib()
