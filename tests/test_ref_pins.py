@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from util import bits, host_inputs, load_scene_npz
+from util import bits, hostile_material_scene, host_inputs, load_scene_npz
 
 ref = pytest.importorskip("oracle.ref.ref")
 pytestmark = pytest.mark.skipif(not ref.available(), reason="neither /root/reference nor a prebuilt oracle/_ref/libref.so")
@@ -144,6 +144,7 @@ SCENES = {
     "mesh_room": lambda rtdx: rtdx.scenes.mesh_room(n=8),                                  # closed room, GGX + diffuse, two instances
     "garage_monke": lambda rtdx: load_scene_npz(rtdx, os.path.join(GOLDEN, "reference_scene.npz")),   # the reference's own assets
     "cornell": lambda rtdx: rtdx.scenes.cornell(),                                         # open front: primary misses (deviation D1)
+    "hostile_materials": hostile_material_scene,                                           # Pr = 0, Ks > 1, LUT = 0, zero-area light, missing normals
 }
 
 
@@ -183,7 +184,10 @@ def test_pass1_and_estimator_e0_equal_the_reference(rtdx, orc, name, bounces):
         assert (acc[..., 3] == 1).all()
         if not miss.any():
             # ray counts: the oracle issues the reference's rays minus the visibility rays whose result cannot matter (deviation D6)
-            assert ctr["closest_rays"] <= rc <= ctr["closest_rays"] * 1.01 + 4 and ctr["shadow_rays"] <= rsh <= ctr["shadow_rays"] * 1.2 + 8
+            # (with the hostile materials most candidates have no contribution at all: most visibility rays are skipped)
+            # and more paths end on emitters without contribution, where the reference traces on for nothing: deviation D4)
+            slack, slack_c = (2.0, 1.03) if name == "hostile_materials" else (1.2, 1.01)
+            assert ctr["closest_rays"] <= rc <= ctr["closest_rays"] * slack_c + 4 and ctr["shadow_rays"] <= rsh <= ctr["shadow_rays"] * slack + 8
 
 
 def _frames(rtdx, orc, sc, W, H, script, allow_miss=False):
@@ -311,7 +315,7 @@ def test_legacy_estimator_equals_the_reference_text(rtdx, orc, name, bounces):
         b, ctr = osc.render(cam, W, H, sample, 1, bounces=bounces, flags=flags)
         assert rc == (ctr["closest_rays"], ctr["shadow_rays"]), (sample, rc, ctr)
         assert np.array_equal(bits(a + 0), bits(b + 0)), (sample, int((bits(a + 0) != bits(b + 0)).any(axis=2).sum()))
-        assert np.isfinite(a).all() and a[..., :3].sum() > 0 and (a[..., 3] == 1).all()
+        assert np.isfinite(a).all() and a[..., :3].sum() > 0 and ((a[..., 3] == 1).all() or name == "hostile_materials")   # (non-finite samples are dropped: RayGen.hlsl:145)
     # three samples accumulated by the reference's own temporal accumulation (RayGen.hlsl:140-156), then its averaged output (:176-183)
     rs.L.ref_write_permanent(_p(zeros))
     for sample in range(3):
@@ -324,4 +328,5 @@ def test_legacy_estimator_equals_the_reference_text(rtdx, orc, name, bounces):
     # accumulation): its third frame shows the three-sample sum over 2.  The engine resolves every accumulation buffer with the current
     # count (F20, Common_v7 / Pass_spat_di_v7.hlsl:425-444); only gPermanentData is the legacy row's contract.  Asserted as found:
     out = rs.output()
-    assert np.array_equal(bits(out[..., :3] + 0), bits((b[..., :3] / np.float32(2.0)) + 0))
+    if name != "hostile_materials":        # (there the count before the frame differs per pixel: dropped samples)
+        assert np.array_equal(bits(out[..., :3] + 0), bits((b[..., :3] / np.float32(2.0)) + 0))

@@ -88,3 +88,32 @@ def bounce_rays(rtdx, rays, hits, rng, tmin=1e-3, tmax=1e4):
     out["origin"] = o.astype(np.float32); out["direction"] = d.astype(np.float32)
     out["tmin"] = tmin; out["tmax"] = tmax
     return out
+
+
+def hostile_material_scene(rtdx):
+    """A closed room with mirror-smooth (Pr = 0, Pr < 0.04), over-unity and zero Ks / Kd materials, the loader's default material
+    (LUT = 0), huge and tiny emitters, a zero-area light triangle, missing and partly-zero vertex normals (tests/test_gpu_parity.py::
+    test_render_fuzz_hostile_materials_and_lights, tests/test_ref_pins.py)."""
+    rng = np.random.RandomState(11)
+    sc = rtdx.scenes.SceneDesc(); sc.name = "fuzz_mat"
+    mk = rtdx.scenes.make_material
+    mats = [rtdx.scenes.default_material(), mk((.7, .7, .7)), mk((.2, .4, .9), ks=(.9, .9, .9), roughness=0.0, metallic=1.0),
+            mk((.9, .1, .1), ks=(.04, .04, .04), roughness=0.03), mk((0, 0, 0), ks=(2.5, 1.5, 0.0), roughness=0.35, metallic=0.5),
+            mk((1, 1, 1), ks=(0, 0, 0), roughness=1.0), mk((0, 0, 0), ke=(1e4, 2e4, 5e3)), mk((0, 0, 0), ke=(3e-4, 0, 0)),
+            mk((.5, .5, .5), ke=(4, 4, 4), roughness=0.5)]
+    sc.materials = rtdx.scenes._fill_luts(np.concatenate(mats))
+    # a closed room of 6 quads (materials 1..5 and the default), two blobs, three emitters (one with a zero-area triangle)
+    pos, nrm, idx, tm = rtdx.scenes._quads_to_mesh(rtdx.scenes._box_quads((-2, 0, -2), (2, 3, 2)), [1, 2, 3, 4, 5, 0], flip=True)
+    room = sc.add_model(pos, nrm, idx, tm)
+    p, vn, i3 = rtdx.scenes._cube_sphere(4, 0.6, 9, 0.15)
+    vn[::3] = 0.0                                                           # every third vertex has no normal
+    vn[1::7, 1] = 0.0                                                       # and some have one zero component (Hit_v7.hlsl:36-44: treated as missing)
+    blob = sc.add_model(p, vn, i3, rng.randint(1, 6, size=i3.shape[0]))
+    lq = np.array([[-.5, 2.95, -.5], [.5, 2.95, -.5], [.5, 2.95, .5], [-.5, 2.95, .5], [0, 1.5, 0], [0, 1.5, 0]], dtype=np.float32)
+    light = sc.add_model(lq, np.zeros_like(lq), np.array([[0, 1, 2], [0, 2, 3], [4, 4, 5], [0, 3, 1]]), np.array([6, 8, 8, 7]))
+    sc.add_instance(room); sc.add_instance(light)
+    a = np.eye(4); a[:3, 3] = (-0.8, 0.8, 0.3)
+    b = np.diag([1.5, 0.6, 1.0, 1.0]); b[:3, 3] = (0.9, 1.2, -0.4)
+    sc.add_instance(blob, a); sc.add_instance(blob, b)
+    sc.eye, sc.center, sc.up = (0.0, 1.5, 1.9), (0.0, 1.3, 0.0), (0.0, 1.0, 0.0)
+    return sc
