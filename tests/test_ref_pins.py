@@ -252,6 +252,7 @@ def test_restir_frames_static_equal_the_reference(rtdx, orc):
     """RayGen + RayGen2 (temporal) + RayGen3 (spatial, shade, accumulate, sRGB) from the reference's text, 4 frames."""
     _frames(rtdx, orc, SCENES["mesh_room"](rtdx), 48, 32, [(None, None)] * 4)
     _frames(rtdx, orc, SCENES["cornell"](rtdx), 40, 32, [(None, None)] * 3, allow_miss=True)
+    _frames(rtdx, orc, SCENES["hostile_materials"](rtdx), 40, 30, [(None, None)] * 3)          # reuse across NaN-prone materials and a zero-area light
 
 
 def test_restir_frames_reference_scene_with_rotating_instance_equal_the_reference(rtdx, orc):
