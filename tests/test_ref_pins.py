@@ -145,7 +145,9 @@ SCENES = {
     "garage_monke": lambda rtdx: load_scene_npz(rtdx, os.path.join(GOLDEN, "reference_scene.npz")),   # the reference's own assets
     "cornell": lambda rtdx: rtdx.scenes.cornell(),                                         # open front: primary misses (deviation D1)
     "hostile_materials": hostile_material_scene,                                           # Pr = 0, Ks > 1, LUT = 0, zero-area light, missing normals
+    "instanced_emitters": lambda rtdx: rtdx.scenes.instanced_blobs(n_models=2, n_side=5, lattice=3, emissive_fraction=0.15),   # 27 instances, many lights, open
 }
+OPEN_SCENES = ("cornell", "instanced_emitters")                                            # primary rays can miss (deviation D1)
 
 
 def _primary_miss_mask(orc, osc, cam, W, H, sample, bounces):
@@ -177,7 +179,7 @@ def test_pass1_and_estimator_e0_equal_the_reference(rtdx, orc, name, bounces):
         rc, rsh = rs.ray_counts()
         acc, ctr = osc.render(cam, W, H, sample, 1, bounces=bounces)
         miss = _primary_miss_mask(orc, osc, cam, W, H, sample, bounces)
-        if name != "cornell":
+        if name not in OPEN_SCENES:
             assert not miss.any()
         differ = (bits(e0[..., :3] + 0) != bits(acc[..., :3])).any(-1)
         assert not (differ & ~miss).any(), "%d pixels differ from the reference" % int((differ & ~miss).sum())
